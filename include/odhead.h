@@ -75,6 +75,11 @@ typedef enum {
   OD_ERR_PARAM = -8       /* parameter out of supported range */
 } od_status;
 
+/* every entry point below has default ELF visibility (the library is built -fvisibility=hidden) */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 int od_version(void);                       /* 10000*major + 100*minor + patch */
 const char* od_strerror(int status);
 const char* od_last_error_detail(void);     /* thread-local, never NULL */
@@ -261,6 +266,10 @@ int od_frcnn_proposal_forward(const DLTensor* rpn_box_class_prob, const DLTensor
  * out [n,7,7,D] = max_pool2x2(crop_and_resize(14x14)) with boxes / (H,W,H,W). */
 int od_roi_pool_forward(const DLTensor* feature_map, const DLTensor* proposals,
                         float image_h, float image_w, DLTensor* out, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }

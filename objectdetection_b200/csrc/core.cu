@@ -1,0 +1,70 @@
+// core.cu — status strings, thread-local error detail, DLPack tensor validation.
+#include "common.cuh"
+
+namespace od {
+
+static thread_local char g_detail[512] = "";
+
+void set_error_detail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_detail, sizeof(g_detail), fmt, ap);
+  va_end(ap);
+}
+
+bool is_contiguous(const DLTensor* t) {
+  if (!t->strides) return true;
+  int64_t expect = 1;
+  for (int i = t->ndim - 1; i >= 0; --i) {
+    if (t->shape[i] != 1 && t->strides[i] != expect) return false;
+    expect *= t->shape[i];
+  }
+  return true;
+}
+
+int check_tensor(const DLTensor* t, const char* name, DType dt, int ndim, bool need_contig, int* device) {
+  if (!t) OD_FAIL(OD_ERR_NULL, "%s is NULL", name);
+  if (t->device.device_type != kDLCUDA)
+    OD_FAIL(OD_ERR_DEVICE, "%s: device_type %d is not kDLCUDA (there is no CPU path)", name, (int)t->device.device_type);
+  if (device) {
+    if (*device < 0) *device = t->device.device_id;
+    else if (*device != t->device.device_id)
+      OD_FAIL(OD_ERR_DEVICE, "%s is on cuda:%d, expected cuda:%d", name, t->device.device_id, *device);
+  }
+  const uint8_t code = (dt == I32) ? (uint8_t)kDLInt : (uint8_t)kDLFloat;
+  const uint8_t bits = (dt == F64) ? 64 : 32;
+  if (t->dtype.code != code || t->dtype.bits != bits || t->dtype.lanes != 1)
+    OD_FAIL(OD_ERR_DTYPE, "%s: dtype (code %d, bits %d) != expected (code %d, bits %d)", name, t->dtype.code,
+            t->dtype.bits, code, bits);
+  if (ndim >= 0 && t->ndim != ndim) OD_FAIL(OD_ERR_SHAPE, "%s: rank %d != %d", name, t->ndim, ndim);
+  for (int i = 0; i < t->ndim; ++i)
+    if (t->shape[i] < 0) OD_FAIL(OD_ERR_SHAPE, "%s: negative extent", name);
+  if (need_contig && !is_contiguous(t)) OD_FAIL(OD_ERR_LAYOUT, "%s must be C-contiguous", name);
+  if (numel(t) > 0 && dptr<char>(t) == nullptr) OD_FAIL(OD_ERR_NULL, "%s: data pointer is NULL", name);
+  return OD_OK;
+}
+
+}  // namespace od
+
+extern "C" {
+
+int od_version(void) { return 10000 * 0 + 100 * 1 + 0; }
+
+const char* od_strerror(int status) {
+  switch (status) {
+    case OD_OK: return "ok";
+    case OD_ERR_NULL: return "required pointer is NULL";
+    case OD_ERR_DTYPE: return "wrong dtype";
+    case OD_ERR_SHAPE: return "wrong shape";
+    case OD_ERR_DEVICE: return "wrong device (CUDA tensors on one device required)";
+    case OD_ERR_LAYOUT: return "tensor must be contiguous / aligned";
+    case OD_ERR_WORKSPACE: return "workspace missing or too small";
+    case OD_ERR_CUDA: return "CUDA runtime error";
+    case OD_ERR_PARAM: return "parameter out of supported range";
+    default: return "unknown status";
+  }
+}
+
+const char* od_last_error_detail(void) { return od::g_detail; }
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+// nms.cuh — internal interface of the bitmask NMS (nms.cu).
+#pragma once
+#include "common.cuh"
+
+namespace od {
+
+// Workspace for nms_sorted_launch (mask + transposed diagonal blocks).
+size_t nms_sorted_workspace_bytes(int64_t batch, int64_t K);
+
+// Greedy hard NMS over boxes ALREADY in visiting order (score desc, index asc).
+//   boxes      [B,K] float4 (y1,x1,y2,x2)
+//   num_valid  [B] or nullptr: only the first num_valid[b] boxes take part
+//   group      [B,K] or nullptr: boxes only suppress boxes of the same group (per-class NMS)
+//   keep_pos   [B,max_out] or nullptr: kept positions in selection order, -1 padded
+//   num_kept   [B] or nullptr
+//   keep_flag  [B,K] or nullptr: 1 if position kept (0 otherwise, including invalid positions)
+int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32_t* group, int64_t B, int64_t K,
+                      float thr, int64_t max_out, int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
+
+// The keep scan alone, over a precomputed suppression bitmask:
+//   mask  [B,K,W] (W = ceil(K/64)) word (i,w) bit j: box i suppresses box w*64+j (only j > i is read)
+//   diagT [B,W,128] uint32 pairs: transposed diagonal tiles (word j of chunk c, bit t: box c*64+t suppresses c*64+j)
+int nms_scan_launch(const unsigned long long* mask, const uint32_t* diagT, const int32_t* num_valid, int64_t B,
+                    int64_t K, int64_t max_out, int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag,
+                    cudaStream_t st);
+
+}  // namespace od

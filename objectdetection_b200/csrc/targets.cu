@@ -1,0 +1,309 @@
+// targets.cu — DetectionTargetLayer: BuildDetectionTargets.build_detection_target
+// (data_processor.py:512-652) with get_iou_tf (:473-510) and box_refinement_tf (:443-471), batched.
+//
+// One CTA per image. The N x G IoU matrix is never materialised (unless the debug tensor is requested):
+// GT boxes sit in shared memory and each thread reduces one proposal row to (max, first argmax).
+// pos/neg index lists are stable block compactions (ascending index == tf.where order). tf.random_shuffle
+// (:587,:597) is replaced by explicit permutation inputs: the shuffled list is list[q] for q in perm (in
+// order) with q < len(list).
+#include "common.cuh"
+
+namespace od {
+
+constexpr int kTgtThreads = 1024;
+
+struct TargetDebugPtrs {
+  float* iou;              // [B,N,G]
+  float* roi_iou_max;      // [B,N]
+  int32_t* pos_indices;    // [B,N]
+  int32_t* neg_indices;    // [B,N]
+  int32_t* counts;         // [B,6]
+  int32_t* sampled_pos;    // [B,R]
+  int32_t* sampled_neg;    // [B,R]
+  int32_t* gt_assignment;  // [B,R]
+};
+
+// get_iou_tf: no canonicalisation, no area guard.
+__device__ __forceinline__ float target_iou(float4 p, float4 g) {
+  const float p_area = (p.z - p.x) * (p.w - p.y);
+  const float g_area = (g.z - g.x) * (g.w - g.y);
+  const float iy1 = f_max(p.x, g.x), ix1 = f_max(p.y, g.y);
+  const float iy2 = f_min(p.z, g.z), ix2 = f_min(p.w, g.w);
+  const float inter = f_max(iy2 - iy1, 0.0f) * f_max(ix2 - ix1, 0.0f);
+  return inter / ((p_area + g_area) - inter);
+}
+
+// box_refinement_tf followed by "/= stddev".
+__device__ __forceinline__ float4 refine_box(float4 box, float4 gt, float4 sd) {
+  const float height = box.z - box.x;
+  const float width = box.w - box.y;
+  const float center_y = box.x + 0.5f * height;
+  const float center_x = box.y + 0.5f * width;
+  const float gt_height = gt.z - gt.x;
+  const float gt_width = gt.w - gt.y;
+  const float gt_center_y = gt.x + 0.5f * gt_height;
+  const float gt_center_x = gt.y + 0.5f * gt_width;
+  return make_float4(((gt_center_y - center_y) / height) / sd.x, ((gt_center_x - center_x) / width) / sd.y,
+                     f_log(gt_height / height) / sd.z, f_log(gt_width / width) / sd.w);
+}
+
+// Stable compaction of {i in [0,n) : pred(i)}; emit(i, rank) is called for every selected i. Returns the
+// count. All threads of the CTA must call it; `scratch` holds 34 ints.
+template <typename Pred, typename Emit>
+__device__ int block_stable_compact(int n, Pred pred, Emit emit, int* scratch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  int base = 0;
+  for (int t0 = 0; t0 < n; t0 += blockDim.x) {
+    const int i = t0 + tid;
+    const bool p = (i < n) && pred(i);
+    const uint32_t bal = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      const int c = scratch[w];
+      if (w < warp) off += c;
+      total += c;
+    }
+    if (p) emit(i, base + off + __popc(bal & ((1u << lane) - 1u)));
+    base += total;
+    __syncthreads();
+  }
+  return base;
+}
+
+__global__ void __launch_bounds__(kTgtThreads)
+detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __restrict__ gt_class_ids,
+                        const float4* __restrict__ gt_boxes, const int32_t* __restrict__ perm_pos,
+                        const int32_t* __restrict__ perm_neg, int N, int G, int R, float4 stddev,
+                        float4* __restrict__ rois, int32_t* __restrict__ roi_cls, float4* __restrict__ roi_deltas,
+                        int32_t* __restrict__ ws_i32, float* __restrict__ ws_f32, TargetDebugPtrs dbg) {
+  extern __shared__ float4 s_gt[];                        // [G] compacted GT boxes
+  int32_t* s_gt_src = reinterpret_cast<int32_t*>(s_gt + G);  // [G] original GT row of compacted j
+  __shared__ int scratch[40];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float4* prop = proposals + (int64_t)b * N;
+  const int32_t* gcls = gt_class_ids + (int64_t)b * G;
+  const float4* gbox = gt_boxes + (int64_t)b * G;
+  // per-image scratch in global memory: prop_src | arg | pos_list | neg_list (int32) and iou_max (f32)
+  int32_t* prop_src = ws_i32 + (int64_t)b * 4 * N;
+  int32_t* iou_arg = prop_src + N;
+  int32_t* pos_list = iou_arg + N;
+  int32_t* neg_list = pos_list + N;
+  float* iou_max = ws_f32 + (int64_t)b * N;
+
+  // (1) strip zero padding (:564-571)
+  const int n_gt = block_stable_compact(
+      G, [&](int j) { return gcls[j] != 0; },
+      [&](int j, int r) {
+        s_gt[r] = gbox[j];
+        s_gt_src[r] = j;
+      },
+      scratch);
+  const int n_prop = block_stable_compact(
+      N,
+      [&](int i) {
+        const float4 p = prop[i];
+        return (((fabsf(p.x) + fabsf(p.y)) + fabsf(p.z)) + fabsf(p.w)) != 0.0f;
+      },
+      [&](int i, int r) { prop_src[r] = i; }, scratch);
+  __syncthreads();
+
+  // (2) IoU rows -> max / first argmax (:576-579, :610)
+  for (int i = tid; i < n_prop; i += kTgtThreads) {
+    const float4 p = prop[prop_src[i]];
+    float best = -INFINITY;
+    int arg = 0;
+    for (int j = 0; j < n_gt; ++j) {
+      const float v = target_iou(p, s_gt[j]);
+      if (dbg.iou) dbg.iou[((int64_t)b * N + i) * G + j] = v;
+      if (v > best) {
+        best = v;
+        arg = j;
+      }
+    }
+    iou_max[i] = best;
+    iou_arg[i] = arg;
+    if (dbg.roi_iou_max) dbg.roi_iou_max[(int64_t)b * N + i] = best;
+  }
+  __syncthreads();
+
+  // (3) where(max >= 0.5) / where(max < 0.5), ascending (:582-583)
+  const int n_pos = block_stable_compact(
+      n_prop, [&](int i) { return iou_max[i] >= 0.5f; }, [&](int i, int r) { pos_list[r] = i; }, scratch);
+  const int n_neg = block_stable_compact(
+      n_prop, [&](int i) { return iou_max[i] < 0.5f; }, [&](int i, int r) { neg_list[r] = i; }, scratch);
+  __syncthreads();
+  if (dbg.pos_indices)
+    for (int i = tid; i < N; i += kTgtThreads) dbg.pos_indices[(int64_t)b * N + i] = (i < n_pos) ? pos_list[i] : -1;
+  if (dbg.neg_indices)
+    for (int i = tid; i < N; i += kTgtThreads) dbg.neg_indices[(int64_t)b * N + i] = (i < n_neg) ? neg_list[i] : -1;
+
+  // (4) counts (:586-594), fp32 arithmetic with truncation
+  const int num_pos_inst = (int)((double)R * 0.33);
+  const int pos_count = min(n_pos, num_pos_inst);
+  const float inv = (float)(1.0 / 0.33);
+  int neg_cnt = f_to_i32_x86(inv * (float)pos_count) - pos_count;
+  neg_cnt = max(neg_cnt, 0);
+  const int neg_count = min(min(n_neg, neg_cnt), R - pos_count);  // host guarantees the last bound never binds
+  if (dbg.counts && tid == 0) {
+    int32_t* c = dbg.counts + (int64_t)b * 6;
+    c[0] = n_prop; c[1] = n_gt; c[2] = n_pos; c[3] = n_neg; c[4] = pos_count; c[5] = neg_count;
+  }
+
+  // (8) zero padding first, sampled rows overwrite below after a barrier
+  float4* o_rois = rois + (int64_t)b * R;
+  int32_t* o_cls = roi_cls + (int64_t)b * R;
+  float4* o_del = roi_deltas + (int64_t)b * R;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = tid; t < R; t += kTgtThreads) {
+    if (t >= pos_count + neg_count) o_rois[t] = z4;
+    if (t >= pos_count) {
+      o_cls[t] = 0;
+      o_del[t] = z4;
+    }
+    if (dbg.sampled_pos) dbg.sampled_pos[(int64_t)b * R + t] = -1;
+    if (dbg.sampled_neg) dbg.sampled_neg[(int64_t)b * R + t] = -1;
+    if (dbg.gt_assignment) dbg.gt_assignment[(int64_t)b * R + t] = -1;
+  }
+  __syncthreads();
+
+  // (5)-(7) shuffled sampling, gather from the UN-compacted proposals (:600-616)
+  const int32_t* pp = perm_pos + (int64_t)b * N;
+  const int32_t* pn = perm_neg + (int64_t)b * N;
+  block_stable_compact(
+      N,
+      [&](int t) {
+        const int q = pp[t];
+        return q >= 0 && q < n_pos;
+      },
+      [&](int t, int r) {
+        if (r >= pos_count) return;
+        const int idx = pos_list[pp[t]];
+        const float4 box = prop[idx];
+        const int a = iou_arg[idx];
+        const int g = s_gt_src[a];
+        o_rois[r] = box;
+        o_cls[r] = gcls[g];
+        o_del[r] = refine_box(box, gbox[g], stddev);
+        if (dbg.sampled_pos) dbg.sampled_pos[(int64_t)b * R + r] = idx;
+        if (dbg.gt_assignment) dbg.gt_assignment[(int64_t)b * R + r] = a;
+      },
+      scratch);
+  block_stable_compact(
+      N,
+      [&](int t) {
+        const int q = pn[t];
+        return q >= 0 && q < n_neg;
+      },
+      [&](int t, int r) {
+        if (r >= neg_count) return;
+        const int idx = neg_list[pn[t]];
+        o_rois[pos_count + r] = prop[idx];
+        if (dbg.sampled_neg) dbg.sampled_neg[(int64_t)b * R + r] = idx;
+      },
+      scratch);
+}
+
+static int check_opt_nd(const DLTensor* t, const char* name, DType dt, int* dev, std::initializer_list<int64_t> shape) {
+  if (!t) return OD_OK;
+  OD_CHECK(check_tensor(t, name, dt, (int)shape.size(), true, dev));
+  int d = 0;
+  for (int64_t s : shape) {
+    if (t->shape[d] != s) OD_FAIL(OD_ERR_SHAPE, "%s: extent %d is %lld, expected %lld", name, d, (long long)t->shape[d], (long long)s);
+    ++d;
+  }
+  return OD_OK;
+}
+
+}  // namespace od
+
+using namespace od;
+
+extern "C" {
+
+size_t od_detection_target_workspace_bytes(int64_t batch, int64_t num_proposals, int64_t num_gt) {
+  Workspace w(nullptr, 0);
+  w.take<int32_t>((size_t)(batch * 4 * num_proposals));
+  w.take<float>((size_t)(batch * num_proposals));
+  return w.off + 256;
+}
+
+int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_class_ids, const DLTensor* gt_boxes,
+                                const DLTensor* perm_pos, const DLTensor* perm_neg, const od_target_params* params,
+                                DLTensor* rois, DLTensor* roi_gt_class_ids, DLTensor* roi_gt_box_deltas,
+                                const DLTensor* gt_masks, DLTensor* mask_targets, const od_target_debug* debug,
+                                void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!params) OD_FAIL(OD_ERR_NULL, "params is NULL");
+  int dev = -1;
+  OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
+  OD_CHECK(check_tensor(gt_class_ids, "gt_class_ids", I32, 2, true, &dev));
+  OD_CHECK(check_tensor(gt_boxes, "gt_boxes", F32, 3, true, &dev));
+  OD_CHECK(check_tensor(perm_pos, "perm_pos", I32, 2, true, &dev));
+  OD_CHECK(check_tensor(perm_neg, "perm_neg", I32, 2, true, &dev));
+  OD_CHECK(check_tensor(rois, "rois", F32, 3, true, &dev));
+  OD_CHECK(check_tensor(roi_gt_class_ids, "roi_gt_class_ids", I32, 2, true, &dev));
+  OD_CHECK(check_tensor(roi_gt_box_deltas, "roi_gt_box_deltas", F32, 3, true, &dev));
+  const int64_t B = proposals->shape[0], N = proposals->shape[1], G = gt_class_ids->shape[1], R = params->rois_per_image;
+  if (proposals->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "proposals must be [B,N,4]");
+  if (gt_class_ids->shape[0] != B || gt_boxes->shape[0] != B || gt_boxes->shape[1] != G || gt_boxes->shape[2] != 4)
+    OD_FAIL(OD_ERR_SHAPE, "gt_class_ids [B,G] / gt_boxes [B,G,4] mismatch");
+  if (perm_pos->shape[0] != B || perm_pos->shape[1] != N || perm_neg->shape[0] != B || perm_neg->shape[1] != N)
+    OD_FAIL(OD_ERR_SHAPE, "perm_pos / perm_neg must be [B,N]");
+  if (R < 0 || rois->shape[0] != B || rois->shape[1] != R || rois->shape[2] != 4 || roi_gt_class_ids->shape[0] != B ||
+      roi_gt_class_ids->shape[1] != R || roi_gt_box_deltas->shape[0] != B || roi_gt_box_deltas->shape[1] != R ||
+      roi_gt_box_deltas->shape[2] != 4)
+    OD_FAIL(OD_ERR_SHAPE, "outputs must be rois [B,R,4], roi_gt_class_ids [B,R], roi_gt_box_deltas [B,R,4]");
+  if (gt_masks || mask_targets) OD_FAIL(OD_ERR_PARAM, "mask targets are not built in this version (pass NULL)");
+  if (G > 8192) OD_FAIL(OD_ERR_PARAM, "at most 8192 GT boxes per image");
+  if (N >= (1 << 30)) OD_FAIL(OD_ERR_PARAM, "too many proposals");
+  // pos_count + neg_count must fit R for every reachable pos_count (data_processor.py:586-594 arithmetic)
+  {
+    const int num_pos_inst = (int)((double)R * 0.33);
+    const float inv = (float)(1.0 / 0.33);
+    for (int p = 0; p <= num_pos_inst; ++p)
+      if ((int)(inv * (float)p) > R) OD_FAIL(OD_ERR_PARAM, "rois_per_image=%lld cannot hold pos+neg samples", (long long)R);
+  }
+  for (const DLTensor* t : {proposals, (const DLTensor*)gt_boxes, (const DLTensor*)rois, (const DLTensor*)roi_gt_box_deltas})
+    if (reinterpret_cast<uintptr_t>(dptr<float>(t)) % 16) OD_FAIL(OD_ERR_LAYOUT, "box tensors must be 16-byte aligned");
+  od_target_debug dbg;
+  memset(&dbg, 0, sizeof(dbg));
+  if (debug) dbg = *debug;
+  OD_CHECK(check_opt_nd(dbg.iou, "debug.iou", F32, &dev, {B, N, G}));
+  OD_CHECK(check_opt_nd(dbg.roi_iou_max, "debug.roi_iou_max", F32, &dev, {B, N}));
+  OD_CHECK(check_opt_nd(dbg.pos_indices, "debug.pos_indices", I32, &dev, {B, N}));
+  OD_CHECK(check_opt_nd(dbg.neg_indices, "debug.neg_indices", I32, &dev, {B, N}));
+  OD_CHECK(check_opt_nd(dbg.counts, "debug.counts", I32, &dev, {B, 6}));
+  OD_CHECK(check_opt_nd(dbg.sampled_pos, "debug.sampled_pos", I32, &dev, {B, R}));
+  OD_CHECK(check_opt_nd(dbg.sampled_neg, "debug.sampled_neg", I32, &dev, {B, R}));
+  OD_CHECK(check_opt_nd(dbg.gt_assignment, "debug.gt_assignment", I32, &dev, {B, R}));
+  if (B == 0 || R == 0) return OD_OK;
+  if (!ws) OD_FAIL(OD_ERR_WORKSPACE, "workspace is NULL");
+  Workspace w(ws, ws_bytes);
+  int32_t* ws_i32 = w.take<int32_t>((size_t)(B * 4 * N));
+  float* ws_f32 = w.take<float>((size_t)(B * N));
+  if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, w.off);
+  TargetDebugPtrs dp;
+  dp.iou = dptr<float>(dbg.iou);
+  dp.roi_iou_max = dptr<float>(dbg.roi_iou_max);
+  dp.pos_indices = dptr<int32_t>(dbg.pos_indices);
+  dp.neg_indices = dptr<int32_t>(dbg.neg_indices);
+  dp.counts = dptr<int32_t>(dbg.counts);
+  dp.sampled_pos = dptr<int32_t>(dbg.sampled_pos);
+  dp.sampled_neg = dptr<int32_t>(dbg.sampled_neg);
+  dp.gt_assignment = dptr<int32_t>(dbg.gt_assignment);
+  const float4 sd = make_float4(params->bbox_stddev[0], params->bbox_stddev[1], params->bbox_stddev[2], params->bbox_stddev[3]);
+  const size_t smem = (size_t)(G > 0 ? G : 1) * (sizeof(float4) + sizeof(int32_t));
+  if (smem > 48 * 1024)
+    OD_CUDA(cudaFuncSetAttribute(detection_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  detection_target_kernel<<<(unsigned)B, kTgtThreads, smem, st>>>(
+      dptr<float4>(proposals), dptr<int32_t>(gt_class_ids), dptr<float4>(gt_boxes), dptr<int32_t>(perm_pos),
+      dptr<int32_t>(perm_neg), (int)N, (int)G, (int)R, sd, dptr<float4>(rois), dptr<int32_t>(roi_gt_class_ids),
+      dptr<float4>(roi_gt_box_deltas), ws_i32, ws_f32, dp);
+  OD_LAUNCH_CHECK("detection_target_kernel");
+  return OD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+// topk.cu — segmented radix select + in-segment sort: tf.nn.top_k(sorted=True) semantics
+// (k largest per row, descending, ties -> lower index). Call sites replaced: proposals_tf.py:169,
+// detection.py:221; also the score ordering inside tf.image.non_max_suppression.
+//
+// Every element gets a unique orderable key  c = (score_key << ib) | (2^ib - 1 - index),  ib = ceil(log2(cols)),
+// so "k largest by (value desc, index asc)" is "k largest c". A most-significant-digit radix select
+// (12-bit digits) narrows a per-row prefix until the bucket that still straddles the k-th element is
+// fully taken (`done`), which for distinct scores happens after 2-3 digits; later passes exit at once.
+// Passes are one launch each: per-CTA shared-memory histograms -> global histogram (atomics) -> the
+// last CTA of the row (ticket counter) scans the 4096 buckets and advances the row's state.
+// Then one collect pass compacts the k winners and a single-CTA bitonic sort (shared memory, up to
+// 16384 keys; global-memory bitonic above that) orders them.
+#include "topk.cuh"
+
+namespace od {
+
+constexpr int kDigitBits = 12;
+constexpr int kBins = 1 << kDigitBits;
+constexpr int kSelThreads = 256;
+constexpr int kSortThreads = 1024;
+constexpr int64_t kSmemSortMax = 16384;
+
+struct __align__(16) SelState {
+  unsigned long long prefix;  // determined high bits of the k-th key (low `shift` bits are zero)
+  int32_t shift;              // number of undetermined low bits
+  int32_t k_rem;              // how many to take among the elements matching `prefix`
+  int32_t done;               // every element matching `prefix` is selected
+  uint32_t blocks_done;       // ticket counter for last-CTA detection
+  uint32_t out_count;         // slot counter of the collect pass
+  uint32_t pad;
+};
+
+__device__ __forceinline__ unsigned long long topk_key(float s, uint32_t idx, int ib) {
+  return ((unsigned long long)score_key(s) << ib) | (unsigned long long)((1u << ib) - 1u - idx);
+}
+
+struct RowChunk {
+  int64_t begin, end;
+};
+__device__ __forceinline__ RowChunk row_chunk(int64_t cols) {
+  const int64_t per = (cols + gridDim.x - 1) / gridDim.x;
+  RowChunk c;
+  c.begin = per * blockIdx.x;
+  c.end = min(cols, c.begin + per);
+  return c;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+topk_hist_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
+                 int shift, int bits, int first, int k, SelState* __restrict__ states, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kBins];
+  __shared__ uint32_t warp_sums[kSelThreads / 32];
+  __shared__ int is_last;
+  const int row = blockIdx.y;
+  SelState* st = states + row;
+  const int done = first ? 0 : st->done;
+  if (done) return;
+  const unsigned long long prefix = first ? 0ull : st->prefix;
+  const int k_rem = first ? k : st->k_rem;
+  const int total_bits = 32 + ib;
+  const int hi_shift = shift + bits;
+  const uint32_t mask = (1u << bits) - 1u;
+  for (int b = threadIdx.x; b < kBins; b += kSelThreads) sh[b] = 0;
+  __syncthreads();
+  const float* srow = scores + (int64_t)row * row_stride;
+  const RowChunk ch = row_chunk(cols);
+  for (int64_t i = ch.begin + threadIdx.x; i < ch.end; i += kSelThreads) {
+    const unsigned long long c = topk_key(srow[i * col_stride], (uint32_t)i, ib);
+    if (hi_shift >= total_bits || (c >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(uint32_t)(c >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  uint32_t* hrow = hist + (int64_t)row * kBins;
+  for (int b = threadIdx.x; b < kBins; b += kSelThreads) {
+    const uint32_t v = sh[b];
+    if (v) atomicAdd(&hrow[b], v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(&st->blocks_done, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- last CTA of this row: find the bucket holding the k_rem-th largest key
+  constexpr int kPer = kBins / kSelThreads;  // buckets per thread, walked from the top
+  const int top_bin = kBins - 1 - threadIdx.x * kPer;
+  uint32_t local[kPer];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    local[q] = __ldcg(&hrow[top_bin - q]);
+    hrow[top_bin - q] = 0;  // ready for the next pass
+    sum += local[q];
+  }
+  // inclusive scan of `sum` over threads (thread 0 owns the highest buckets)
+  uint32_t incl = sum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t warp_off = 0;
+  for (int w = 0; w < warp; ++w) warp_off += warp_sums[w];
+  const uint32_t before = warp_off + incl - sum;  // elements in buckets above this thread's range
+  if ((uint32_t)k_rem > before && (uint32_t)k_rem <= before + sum) {
+    uint32_t cum = before;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      if ((uint32_t)k_rem > cum && (uint32_t)k_rem <= cum + local[q]) {
+        const int d = top_bin - q;
+        const int new_k = k_rem - (int)cum;
+        st->prefix = prefix | ((unsigned long long)d << shift);
+        st->shift = shift;
+        st->k_rem = new_k;
+        st->done = ((int)local[q] == new_k);
+      }
+      cum += local[q];
+    }
+  }
+  if (threadIdx.x == 0) st->blocks_done = 0;
+}
+
+// Selected <=> (c >> shift) >= (prefix >> shift). Exactly k elements qualify.
+__global__ void __launch_bounds__(kSelThreads)
+topk_collect_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
+                    int take_all, int64_t buf_stride, SelState* __restrict__ states,
+                    unsigned long long* __restrict__ buf) {
+  const int row = blockIdx.y;
+  SelState* st = states + row;
+  const int shift = take_all ? 0 : st->shift;
+  const unsigned long long thr = take_all ? 0ull : (st->prefix >> shift);
+  const float* srow = scores + (int64_t)row * row_stride;
+  unsigned long long* out = buf + (int64_t)row * buf_stride;
+  const RowChunk ch = row_chunk(cols);
+  const int lane = threadIdx.x & 31;
+  for (int64_t i0 = ch.begin; i0 < ch.end; i0 += kSelThreads) {
+    const int64_t i = i0 + threadIdx.x;
+    unsigned long long c = 0;
+    bool sel = false;
+    if (i < ch.end) {
+      c = topk_key(srow[i * col_stride], (uint32_t)i, ib);
+      sel = (c >> shift) >= thr;
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, sel);
+    if (ballot) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&st->out_count, (uint32_t)__popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (sel) out[base + __popc(ballot & ((1u << lane) - 1u))] = c;
+    }
+  }
+}
+
+// One CTA per row: sort k keys (padded with 0 to n_pow2) descending in shared memory, emit indices / values.
+__global__ void __launch_bounds__(kSortThreads)
+topk_sort_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int64_t k, int n_pow2, int ib,
+                      const float* __restrict__ scores, int64_t row_stride, int64_t col_stride,
+                      int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  extern __shared__ unsigned long long skeys[];
+  const int row = blockIdx.x;
+  const unsigned long long* in = buf + (int64_t)row * buf_stride;
+  for (int i = threadIdx.x; i < n_pow2; i += kSortThreads) skeys[i] = (i < k) ? in[i] : 0ull;
+  __syncthreads();
+  block_bitonic_sort_desc(skeys, n_pow2);
+  const uint32_t imask = (1u << ib) - 1u;
+  const float* srow = scores + (int64_t)row * row_stride;
+  for (int i = threadIdx.x; i < k; i += kSortThreads) {
+    const uint32_t idx = imask - (uint32_t)(skeys[i] & imask);
+    idx_out[(int64_t)row * k + i] = (int32_t)idx;
+    if (val_out) val_out[(int64_t)row * k + i] = srow[(int64_t)idx * col_stride];
+  }
+}
+
+// ---- generic descending sort of uint64 segments (shared-memory when it fits, global bitonic otherwise)
+__global__ void __launch_bounds__(kSortThreads)
+sort_u64_smem_kernel(unsigned long long* __restrict__ keys, int n_pow2) {
+  extern __shared__ unsigned long long skeys[];
+  unsigned long long* seg = keys + (int64_t)blockIdx.x * n_pow2;
+  for (int i = threadIdx.x; i < n_pow2; i += kSortThreads) skeys[i] = seg[i];
+  __syncthreads();
+  block_bitonic_sort_desc(skeys, n_pow2);
+  for (int i = threadIdx.x; i < n_pow2; i += kSortThreads) seg[i] = skeys[i];
+}
+
+__global__ void bitonic_step_global_kernel(unsigned long long* __restrict__ keys, int64_t n_pow2, int64_t k, int64_t j) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (n_pow2 >> 1)) return;
+  unsigned long long* seg = keys + (int64_t)blockIdx.y * n_pow2;
+  const int64_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+  const int64_t l = i | j;
+  const bool desc = ((i & k) == 0);
+  const unsigned long long a = seg[i], b = seg[l];
+  if ((a < b) == desc) {
+    seg[i] = b;
+    seg[l] = a;
+  }
+}
+
+__global__ void pad_emit_kernel(const unsigned long long* __restrict__ buf, int64_t k, int ib,
+                                const float* __restrict__ scores, int64_t row_stride, int64_t col_stride,
+                                int64_t buf_stride, int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (i >= k) return;
+  const uint32_t imask = (1u << ib) - 1u;
+  const uint32_t idx = imask - (uint32_t)(buf[(int64_t)row * buf_stride + i] & imask);
+  idx_out[(int64_t)row * k + i] = (int32_t)idx;
+  if (val_out) val_out[(int64_t)row * k + i] = scores[(int64_t)row * row_stride + (int64_t)idx * col_stride];
+}
+
+int sort_u64_desc_launch(unsigned long long* keys, int64_t rows, int64_t n_pow2, cudaStream_t st) {
+  if (rows == 0 || n_pow2 <= 1) return OD_OK;
+  if (n_pow2 <= kSmemSortMax) {
+    const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
+    OD_CUDA(cudaFuncSetAttribute(sort_u64_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_u64_smem_kernel<<<(unsigned)rows, kSortThreads, smem, st>>>(keys, (int)n_pow2);
+    OD_LAUNCH_CHECK("sort_u64_smem_kernel");
+    return OD_OK;
+  }
+  const dim3 grid((unsigned)((n_pow2 / 2 + 255) / 256), (unsigned)rows);
+  for (int64_t k = 2; k <= n_pow2; k <<= 1)
+    for (int64_t j = k >> 1; j > 0; j >>= 1) bitonic_step_global_kernel<<<grid, 256, 0, st>>>(keys, n_pow2, k, j);
+  OD_LAUNCH_CHECK("bitonic_step_global_kernel");
+  return OD_OK;
+}
+
+static int blocks_per_row(int64_t rows, int64_t cols) {
+  const int64_t by_work = (cols + 2047) / 2048;
+  const int64_t by_fill = (2 * kNumSMsB200 + rows - 1) / rows;
+  int64_t b = by_work < by_fill ? by_work : by_fill;
+  return (int)(b < 1 ? 1 : b);
+}
+
+size_t topk_workspace_bytes(int64_t rows, int64_t cols, int64_t k) {
+  Workspace w(nullptr, 0);
+  w.take<SelState>((size_t)rows);
+  w.take<uint32_t>((size_t)rows * kBins);
+  w.take<unsigned long long>((size_t)rows * (size_t)next_pow2(k > 0 ? k : 1));
+  return w.off + 256;
+}
+
+int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride, int64_t k,
+                int32_t* idx_out, float* val_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (k < 0 || k > cols) OD_FAIL(OD_ERR_PARAM, "k=%lld must be in [0, cols=%lld]", (long long)k, (long long)cols);
+  if (rows == 0 || k == 0) return OD_OK;
+  if (cols >= ((int64_t)1 << 31) || rows > 65535) OD_FAIL(OD_ERR_PARAM, "top-k supports cols < 2^31 and rows <= 65535");
+  if (!ws) OD_FAIL(OD_ERR_WORKSPACE, "top-k workspace is NULL");
+  Workspace w(ws, ws_bytes);
+  const int64_t n_pow2 = next_pow2(k);
+  SelState* states = w.take<SelState>((size_t)rows);
+  uint32_t* hist = w.take<uint32_t>((size_t)rows * kBins);
+  unsigned long long* buf = w.take<unsigned long long>((size_t)rows * (size_t)n_pow2);
+  if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "top-k workspace %zu < %zu bytes", ws_bytes, w.off);
+  const int ib = index_bits(cols);
+  const int total_bits = 32 + ib;
+  const dim3 grid((unsigned)blocks_per_row(rows, cols), (unsigned)rows);
+  // state + histogram are contiguous at the head of the workspace
+  OD_CUDA(cudaMemsetAsync(states, 0, (size_t)((char*)buf - (char*)states), st));
+  const int take_all = (k == cols);
+  if (!take_all) {
+    int shift = total_bits;
+    int first = 1;
+    while (shift > 0) {
+      const int bits = shift >= kDigitBits ? kDigitBits : shift;
+      shift -= bits;
+      topk_hist_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, shift, bits, first, (int)k,
+                                                     states, hist);
+      first = 0;
+    }
+    OD_LAUNCH_CHECK("topk_hist_kernel");
+  }
+  topk_collect_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, take_all, n_pow2, states, buf);
+  OD_LAUNCH_CHECK("topk_collect_kernel");
+  if (n_pow2 <= kSmemSortMax) {
+    const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
+    OD_CUDA(cudaFuncSetAttribute(topk_sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_sort_emit_kernel<<<(unsigned)rows, kSortThreads, smem, st>>>(buf, n_pow2, k, (int)n_pow2, ib, scores, row_stride,
+                                                                      col_stride, idx_out, val_out);
+    OD_LAUNCH_CHECK("topk_sort_emit_kernel");
+  } else {
+    // zero the padding, sort in global memory, then emit
+    for (int64_t r = 0; r < rows; ++r)
+      if (n_pow2 > k) OD_CUDA(cudaMemsetAsync(buf + r * n_pow2 + k, 0, (size_t)(n_pow2 - k) * 8, st));
+    OD_CHECK(sort_u64_desc_launch(buf, rows, n_pow2, st));
+    const dim3 g2((unsigned)((k + 255) / 256), (unsigned)rows);
+    pad_emit_kernel<<<g2, 256, 0, st>>>(buf, k, ib, scores, row_stride, col_stride, n_pow2, idx_out, val_out);
+    OD_LAUNCH_CHECK("pad_emit_kernel");
+  }
+  return OD_OK;
+}
+
+}  // namespace od
+
+using namespace od;
+
+extern "C" {
+
+size_t od_topk_workspace_bytes(int64_t rows, int64_t cols, int64_t k) { return topk_workspace_bytes(rows, cols, k); }
+
+int od_topk(const DLTensor* scores, int64_t k, DLTensor* values, DLTensor* indices, void* ws, size_t ws_bytes,
+            void* stream) {
+  int dev = -1;
+  OD_CHECK(check_tensor(scores, "scores", F32, 2, false, &dev));
+  OD_CHECK(check_tensor(indices, "indices", I32, 2, true, &dev));
+  const int64_t rows = scores->shape[0], cols = scores->shape[1];
+  if (indices->shape[0] != rows || indices->shape[1] != k) OD_FAIL(OD_ERR_SHAPE, "indices must be [rows,k]");
+  if (values) {
+    OD_CHECK(check_tensor(values, "values", F32, 2, true, &dev));
+    if (values->shape[0] != rows || values->shape[1] != k) OD_FAIL(OD_ERR_SHAPE, "values must be [rows,k]");
+  }
+  return topk_launch(dptr<float>(scores), rows, cols, stride_of(scores, 0), stride_of(scores, 1), k,
+                     dptr<int32_t>(indices), dptr<float>(values), ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""DetectionTargetLayer with the reference's interface
+(MaskRCNN/building_blocks/data_processor.py:430-658, class BuildDetectionTargets)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .proposals import _stddev4
+
+
+class BuildDetectionTargets():
+    """Proposal <-> GT IoU, positive/negative sampling, GT assignment, box-delta targets, zero padding.
+
+    ``BuildDetectionTargets(conf, proposals, gt_class_ids, gt_bboxes, DEBUG=False)`` is per image like the
+    reference (proposals [N,4], gt_class_ids [G], gt_bboxes [G,4]); a leading batch dimension on all three runs
+    the whole batch in one launch (the batched generalisation of training.py:66-81).
+
+    ``tf.random_shuffle`` (data_processor.py:587,:597) is unseeded in the reference. Here the two shuffles are
+    driven by explicit permutations ``perm_pos`` / ``perm_neg`` ([N] or [B,N] int32 permutations of 0..N-1): the
+    shuffled list is ``list[q]`` for q in perm (in order) with q < len(list). If omitted they are drawn with
+    ``torch.randperm`` from ``generator`` (or the global CUDA RNG).
+    """
+
+    def __init__(self, conf, proposals, gt_class_ids, gt_bboxes, DEBUG=False, perm_pos=None, perm_neg=None,
+                 generator=None):
+        self.train_rois_per_image = conf.MRCNN_TRAIN_ROIS_PER_IMAGE
+        self.box_stddev = conf.BBOX_STD_DEV
+        self.DEBUG = bool(DEBUG)
+        self.build_detection_target(proposals, gt_class_ids, gt_bboxes, perm_pos, perm_neg, generator)
+
+    def build_detection_target(self, proposals, gt_class_ids, gt_bboxes, perm_pos=None, perm_neg=None, generator=None):
+        L = _lib.lib()
+        props = _lib.as_cuda(proposals, torch.float32)
+        dev = props.device
+        cls = _lib.as_cuda(gt_class_ids, torch.int32, dev)
+        gtb = _lib.as_cuda(gt_bboxes, torch.float32, dev)
+        single = props.dim() == 2
+        if single:
+            props, cls, gtb = props[None], cls[None], gtb[None]
+        B, N = props.shape[0], props.shape[1]
+        if N == 0:
+            raise ValueError("roi_assertion: proposals must not be empty")   # tf.Assert, data_processor.py:550-555
+        G, R = cls.shape[1], int(self.train_rois_per_image)
+
+        def perm(p):
+            if p is None:
+                return torch.stack([torch.randperm(N, device=dev, generator=generator) for _ in range(B)]).to(torch.int32)
+            p = _lib.as_cuda(p, torch.int32, dev)
+            return p[None] if p.dim() == 1 else p
+        pp, pn = perm(perm_pos).contiguous(), perm(perm_neg).contiguous()
+        rois = torch.empty((B, R, 4), dtype=torch.float32, device=dev)
+        rcls = torch.empty((B, R), dtype=torch.int32, device=dev)
+        deltas = torch.empty((B, R, 4), dtype=torch.float32, device=dev)
+        params = _lib.TargetParams(R, _stddev4(self.box_stddev), 28, 28)
+        dl = _lib.DL()
+        dbg = _lib.TargetDebug()
+        if self.DEBUG:
+            d = dict(iou=torch.full((B, N, G), float("nan"), dtype=torch.float32, device=dev),
+                     roi_iou_max=torch.full((B, N), float("nan"), dtype=torch.float32, device=dev),
+                     pos_indices=torch.empty((B, N), dtype=torch.int32, device=dev),
+                     neg_indices=torch.empty((B, N), dtype=torch.int32, device=dev),
+                     counts=torch.empty((B, 6), dtype=torch.int32, device=dev),
+                     sampled_pos=torch.empty((B, R), dtype=torch.int32, device=dev),
+                     sampled_neg=torch.empty((B, R), dtype=torch.int32, device=dev),
+                     gt_assignment=torch.empty((B, R), dtype=torch.int32, device=dev))
+            for k, v in d.items():
+                setattr(dbg, k, dl(v))
+            self.debug_dict = d
+        ws = _lib.workspace(L.od_detection_target_workspace_bytes(B, N, G), dev)
+        _lib.check(L.od_detection_target_forward(dl(props), dl(cls), dl(gtb), dl(pp), dl(pn), ctypes.byref(params),
+                                                 dl(rois), dl(rcls), dl(deltas), None, None, ctypes.byref(dbg),
+                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+                   "od_detection_target_forward")
+        if single:
+            self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas = rois[0], rcls, deltas[0]   # cls is [1,R] (:627)
+        else:
+            self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas = rois, rcls, deltas
+
+    def get_target_rois(self):
+        return self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas
+
+    def debug_outputs(self):
+        return self.debug_dict

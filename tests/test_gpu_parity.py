@@ -1,0 +1,465 @@
+"""GPU parity: the CUDA path (through the reference-named layer classes -> C ABI -> sm_100a kernels) against the CPU
+oracle on identical seeded inputs. Integer / index outputs must be bit-exact; decoded boxes and deltas are asserted
+bit-exact as well (the oracle and the kernels share the numeric contract) with the north-star tolerance (rtol 1e-5)
+as the documented fallback bound; ROIAlign features rtol 1e-4."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _synth  # noqa: E402
+
+import oracle  # noqa: E402
+from objectdetection_b200.config import ShapesConfig, config as Conf  # noqa: E402
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+STRIDES = [4, 8, 16, 32, 64]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (there is no CPU path)")
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.detach().cpu().numpy()
+
+
+def assert_bits(a, b, what=""):
+    a, b = np.asarray(a, f32), np.asarray(b, f32)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    if not same.all():
+        bad = np.argwhere(~same)
+        raise AssertionError(f"{what}: {bad.shape[0]} of {a.size} differ; first {bad[:3].tolist()} "
+                             f"got {a[tuple(bad[0])]!r} want {b[tuple(bad[0])]!r}; "
+                             f"max rel {np.nanmax(np.abs(a - b) / (np.abs(b) + 1e-30)):.3e}")
+
+
+# ------------------------------------------------------------------ anchors
+def test_gen_anchors_bit_exact():
+    from objectdetection_b200 import utils
+    for shape, scales, ratios, astride in (([128, 128, 3], (8, 16, 32, 64, 128), [0.5, 1, 2], 1),
+                                           ([1024, 1024, 3], (32, 64, 128, 256, 512), [0.5, 1, 2], 1),
+                                           ([192, 320, 3], (16, 32, 64, 128, 256), [0.5, 1, 2, 3], 2)):
+        c = Conf()
+        shapes = utils.get_resnet_stage_shapes(c, shape)
+        got = host(utils.gen_anchors(shape, 2, scales, ratios, shapes, STRIDES, astride))
+        want = oracle.gen_anchors(shape, 2, scales, ratios, shapes, STRIDES, astride)
+        assert_bits(got, want, f"anchors {shape}")
+        gp = host(utils.gen_anchors_pixel_coord(scales, ratios, shapes, STRIDES, astride))
+        assert np.array_equal(gp, oracle.gen_anchors_pixel_coord(scales, ratios, shapes, STRIDES, astride))
+
+
+def test_anchors_golden_on_gpu(golden):
+    from objectdetection_b200 import utils
+    got = host(utils.gen_anchors([1024, 1024, 3], 1, (32, 64, 128, 256, 512), [0.5, 1, 2], golden["stage_shapes_1024"], STRIDES, 1))
+    assert got.shape == (1, 261888, 4)
+    assert np.array_equal(got[0, golden["anchors_1024_sample_rows"]], golden["anchors_1024_sample"])
+    toy = host(utils.gen_anchors_pixel_coord((8, 16, 32, 64, 128), [0.5, 1, 2], golden["stage_shapes_128"], STRIDES, 1))
+    assert np.array_equal(toy, golden["anchors_toy_pixel"])
+
+
+# ------------------------------------------------------------------ top-k
+@pytest.mark.parametrize("rows,cols,k", [(3, 500, 200), (2, 300, 300), (2, 4092, 4092), (2, 261888, 6000), (1, 70000, 20000),
+                                         (5, 33, 1)])
+def test_topk(rows, cols, k):
+    from objectdetection_b200.proposals import top_k
+    rs = np.random.RandomState(rows * 7 + cols)
+    probs = rs.random_sample((rows, cols, 2)).astype(f32)
+    if cols <= 4092:
+        probs = (np.round(probs * 64) / 64).astype(f32)           # heavy ties
+        probs[0, 7 % cols, 1], probs[0, 9 % cols, 1] = -0.0, 0.0
+    view = cu(probs)[:, :, 1]                                      # strided view, like proposals_tf.py:153
+    v, i = top_k(view, k)
+    wv, wi = oracle.topk(probs[:, :, 1], k)
+    assert np.array_equal(host(i), wi)
+    assert_bits(host(v), wv, "values")
+
+
+def test_topk_all_equal_scores():
+    from objectdetection_b200.proposals import top_k
+    s = np.full((2, 10000), 0.5, f32)
+    v, i = top_k(cu(s), 777)
+    assert np.array_equal(host(i), np.tile(np.arange(777, dtype=np.int32), (2, 1)))
+
+
+# ------------------------------------------------------------------ decode / clip
+def test_apply_box_deltas_and_clip():
+    from objectdetection_b200.proposals import apply_box_deltas, clip_boxes_to_01
+    rs = np.random.RandomState(1)
+    a = rs.random_sample((2, 1031, 4)).astype(f32)
+    d = rs.normal(0, 1, size=(2, 1031, 4)).astype(f32)
+    dec = host(apply_box_deltas(cu(a), cu(d)))
+    want = oracle.apply_box_deltas(a, d)
+    assert_bits(dec, want, "apply_box_deltas")
+    assert np.allclose(dec, want, rtol=1e-5)
+    assert_bits(host(clip_boxes_to_01(cu(want), cu(np.array([0, 0, 1, 1], f32)))), oracle.clip_boxes(want, np.array([0, 0, 1, 1], f32)), "clip")
+    win = np.array([[0.1, 0.2, 0.8, 0.9], [0, 0.3, 1, 0.7]], f32)
+    assert_bits(host(clip_boxes_to_01(cu(want), cu(win))), oracle.clip_boxes(want, win), "clip per image")
+
+
+# ------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("n,thr", [(300, 0.3), (1000, 0.5), (6000, 0.7), (65, 0.1), (1, 0.5)])
+def test_nms(n, thr):
+    from objectdetection_b200.proposals import non_max_suppression
+    rs = np.random.RandomState(n)
+    boxes = np.stack([_synth.random_boxes(rs, n, flip=True) for _ in range(2)])
+    if n > 10:
+        boxes[0, 5] = boxes[0, 6]
+        boxes[0, 10, 2:] = boxes[0, 10, :2]
+    scores = (rs.randint(0, 200, (2, n)) / 200).astype(f32)
+    for max_out in sorted({1, min(100, n), n}):
+        keep, num = non_max_suppression(cu(boxes), cu(scores), max_out, thr)
+        keep, num = host(keep), host(num)
+        for b in range(2):
+            want = oracle.nms(boxes[b], scores[b], max_out, thr)
+            assert num[b] == want.shape[0], (b, max_out)
+            assert np.array_equal(keep[b, :num[b]], want) and np.all(keep[b, num[b]:] == -1)
+
+
+def test_nms_num_valid_and_single_image_form():
+    from objectdetection_b200.proposals import non_max_suppression
+    rs = np.random.RandomState(4)
+    boxes, scores = _synth.random_boxes(rs, 500), rs.random_sample(500).astype(f32)
+    k = non_max_suppression(cu(boxes), cu(scores), 500, 0.4)
+    assert np.array_equal(host(k), oracle.nms(boxes, scores, 500, 0.4))
+    keep, num = non_max_suppression(cu(boxes[None]), cu(scores[None]), 500, 0.4, num_valid=np.array([123], np.int32))
+    want = oracle.nms(boxes[:123], scores[:123], 500, 0.4)
+    assert host(num)[0] == want.shape[0] and np.array_equal(host(keep)[0, :want.shape[0]], want)
+
+
+def test_nms_stress_100k_boxes():
+    """BASELINE config 5: 100,000 boxes, one image, thr 0.5; sqrt(area) log-uniform [8,256] px in 4096^2."""
+    from objectdetection_b200.proposals import non_max_suppression
+    rs = np.random.RandomState(5)
+    boxes = _synth.rois_log_uniform(rs, 1, 100000, image=4096, lo=8, hi=256)[0]
+    scores = rs.random_sample(100000).astype(f32)
+    keep = host(non_max_suppression(cu(boxes), cu(scores), 100000, 0.5))
+    want = oracle.nms(boxes, scores, 100000, 0.5)
+    assert np.array_equal(keep, want)
+    # idempotence: NMS of the survivors keeps all of them, in the same order
+    again = host(non_max_suppression(cu(boxes[keep]), cu(scores[keep]), keep.shape[0], 0.5))
+    assert np.array_equal(again, np.arange(keep.shape[0]))
+
+
+# ------------------------------------------------------------------ ProposalLayer
+def _check_proposals(P, probs, bbox, anchors, conf, training=False):
+    N = conf.POST_NMS_ROIS_TRAINING if training else conf.POST_NMS_ROIS_INFERENCE
+    want, dbg = oracle.proposal_forward(probs, bbox, anchors, conf.RPN_BBOX_STDDEV, conf.PRE_NMS_ROIS_COUNT, N,
+                                        conf.RPN_NMS_THRESHOLD, debug=True)
+    bbox_delta, ix, scores, anc, anchor_delta = P.debug_outputs()
+    assert np.array_equal(host(ix), dbg["ix"])
+    assert_bits(host(scores), dbg["scores"], "scores")
+    assert_bits(host(bbox_delta), dbg["bbox_delta"], "bbox_delta")
+    assert_bits(host(anc), dbg["anchors"], "anchors")
+    assert_bits(host(anchor_delta), dbg["anchor_delta"], "anchor_delta")
+    assert np.allclose(host(anchor_delta), dbg["anchor_delta"], rtol=1e-5, equal_nan=True)
+    assert_bits(host(P.get_anchors_delta_clipped()), dbg["anchor_delta_clipped"], "clipped")
+    assert np.array_equal(host(P.num_kept), dbg["num_kept"])
+    assert np.array_equal(host(P.keep_idx), dbg["keep_idx"])
+    assert_bits(host(P.get_proposals()), want, "proposals")
+    return want
+
+
+def test_proposals_debug_recipe():
+    """proposals_tf.py:331-345: seed 325, (1,4092,{2,4,4}) uniform inputs, COCO config."""
+    from objectdetection_b200 import Proposals
+    np.random.seed(325)
+    probs = np.array(np.random.random((1, 4092, 2)), dtype="float32")
+    bbox = np.array(np.random.random((1, 4092, 4)), dtype="float32")
+    anchors = np.array(np.random.random((1, 4092, 4)), dtype="float32")
+    conf = Conf()
+    P = Proposals(conf, batch_size=1, DEBUG=True)
+    out = P.run(probs, bbox, anchors)                     # host numpy in, like the reference's feed_dict
+    assert tuple(out.shape) == (1, 1000, 4)
+    _check_proposals(P, probs, bbox, anchors, conf)
+    g = P.get_proposal_graph()
+    assert set(g) == {"rpn_class_probs", "rpn_bbox", "input_anchors", "proposals"}
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_proposals_coco_shape(training):
+    """BASELINE config 2: 1024^2, 261,888 anchors, 6000 pre-NMS -> 1000 (2000 training), batch 2."""
+    from objectdetection_b200 import Proposals, utils
+    conf = Conf()
+    rs = np.random.RandomState(1234)
+    shapes = utils.get_resnet_stage_shapes(conf, conf.IMAGE_SHAPE)
+    anchors = oracle.gen_anchors(conf.IMAGE_SHAPE, 2, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes,
+                                 conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE)
+    probs, bbox = _synth.rpn_outputs(rs, 2, anchors.shape[1])
+    P = Proposals(conf, 2, cu(probs), cu(bbox), cu(anchors), training=training, DEBUG=True)
+    want = _check_proposals(P, probs, bbox, anchors, conf, training)
+    # same result when the decode kernel regenerates the anchors from their index (fused anchor generation)
+    spec = utils.anchor_spec(conf.IMAGE_SHAPE, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes,
+                             conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE)
+    P2 = Proposals(conf, 2, cu(probs), cu(bbox), None, training=training, anchor_spec=spec)
+    assert_bits(host(P2.get_proposals()), want, "proposals (fused anchors)")
+    # properties: inside [0,1], zero rows only at the tail
+    p = host(P.get_proposals())
+    assert p.min() >= 0 and p.max() <= 1
+    nz = np.abs(p).sum(-1) != 0
+    for b in range(2):
+        assert not nz[b, int(host(P.num_kept)[b]):].any()
+
+
+def test_proposals_toy_config_with_padding():
+    """BASELINE config 1 (shapes.py): 128x128, 4092 anchors, K = min(6000, 4092); low threshold -> zero padded rows."""
+    from objectdetection_b200 import Proposals, utils
+    conf = ShapesConfig()
+    conf.RPN_NMS_THRESHOLD = 0.05
+    rs = np.random.RandomState(5)
+    shapes = utils.get_resnet_stage_shapes(conf, conf.IMAGE_SHAPE)
+    anchors = oracle.gen_anchors(conf.IMAGE_SHAPE, 8, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes,
+                                 conf.RESNET_STRIDES, 1)
+    probs, bbox = _synth.rpn_outputs(rs, 8, 4092)
+    P = Proposals(conf, 8, cu(probs), cu(bbox), cu(anchors), DEBUG=True)
+    want = _check_proposals(P, probs, bbox, anchors, conf)
+    assert (np.abs(want).sum(-1) == 0).any()
+
+
+# ------------------------------------------------------------------ PyramidROIAlign
+def _roi_align_check(fmaps, props, image, pool):
+    from objectdetection_b200 import MaskRCNN
+    m = MaskRCNN(image_shape=[image, image, 3], pool_shape=pool, num_classes=4, levels=[2, 3, 4, 5],
+                 proposals=cu(props), feature_maps=[cu(f) for f in fmaps], type='keras', DEBUG=True)
+    got = host(m.get_pooled_rois())
+    want, wlv = oracle.pyramid_roi_align(fmaps, props, image, image, pool[0], pool[1])
+    assert got.shape == want.shape == (1, props.shape[0] * props.shape[1], pool[0], pool[1], fmaps[0].shape[-1])
+    assert np.array_equal(host(m.debug_outputs()[0]), wlv)                      # roi_level bit-exact
+    assert np.allclose(got, want, rtol=1e-4, atol=0)                             # north-star tolerance
+    frac = (got.view(np.uint32) == want.view(np.uint32)).mean()
+    assert frac == 1.0, f"only {frac:.6f} of the pooled values are bit-identical"
+    return got
+
+
+@pytest.mark.parametrize("pool", [[7, 7], [14, 14]])
+def test_roi_pooling_debug_recipe(pool):
+    """maskrcnn.py:327-345: seed 255, P2..P5 (2,{256,128,64,32}^2,256), proposals (2,1000,4) uniform."""
+    np.random.seed(255)
+    fmaps = [np.array(np.random.random((2, s, s, 256)), dtype="float32") for s in (256, 128, 64, 32)]
+    props = np.array(np.random.random((2, 1000, 4)), dtype="float32")
+    _roi_align_check(fmaps, props, 1024, pool)
+
+
+def test_roi_pooling_realistic_rois_and_degenerates():
+    rs = np.random.RandomState(1234)
+    fmaps = _synth.pyramid(rs, 2, D=64)
+    props = _synth.rois_log_uniform(rs, 2, 400)
+    props[1, 350:] = 0                                                        # zero padded proposals -> level 2
+    props[0, 0] = [0, 0, 1, 1]
+    props[0, 1] = [0.3, 0.3, 0.3, 0.3]
+    props[0, 2] = [0.25, 0.5, 1.0, 1.0]                                       # touches the far edge
+    props[0, 3] = [-0.1, -0.2, 0.4, 0.5]                                      # partly outside -> extrapolation 0
+    props[0, 4] = [0.5, 0.5, 1.2, 1.3]
+    for pool in ([7, 7], [14, 14], [1, 1], [3, 5]):
+        got = _roi_align_check(fmaps, props, 1024, pool)
+    lv = oracle.roi_level(props, 1024, 1024)
+    assert set(np.unique(lv)) == {2, 3, 4, 5}
+
+
+def test_roi_align_properties_full_size():
+    """Size-independent properties at the BASELINE size (2 x 1000 ROIs x 7x7 x 256): linearity in the feature maps
+    and exactness on a constant pyramid."""
+    from objectdetection_b200.maskrcnn import pyramid_roi_align
+    rs = np.random.RandomState(7)
+    props = cu(_synth.rois_log_uniform(rs, 2, 1000))
+    f1 = [torch.rand((2, s, s, 256), device="cuda") for s in (256, 128, 64, 32)]
+    f2 = [torch.rand((2, s, s, 256), device="cuda") for s in (256, 128, 64, 32)]
+    a = pyramid_roi_align(f1, props, [1024, 1024], [7, 7])
+    b = pyramid_roi_align(f2, props, [1024, 1024], [7, 7])
+    c = pyramid_roi_align([2 * x + y for x, y in zip(f1, f2)], props, [1024, 1024], [7, 7])
+    assert torch.allclose(c, 2 * a + b, rtol=1e-4, atol=1e-5)
+    const = pyramid_roi_align([torch.full_like(x, 3.25) for x in f1], props, [1024, 1024], [7, 7])
+    assert bool(((const == 3.25) | (const == 0)).all()) and float((const == 3.25).float().mean()) > 0.99
+
+
+def test_crop_and_resize_generic():
+    from objectdetection_b200.maskrcnn import crop_and_resize
+    rs = np.random.RandomState(2)
+    img = rs.random_sample((2, 9, 11, 8)).astype(f32)
+    boxes = np.array([[0, 0, 1, 1], [0.1, 0.2, 0.7, 0.9], [0.3, 0.3, 0.3, 0.3], [-0.2, -0.1, 0.5, 0.5],
+                      [0.5, 0.5, 1.3, 1.2], [0.9, 0.8, 0.1, 0.2], [0, 0, 0, 0], [0.25, 0.5, 0.75, 1.0]], f32)
+    bi = np.array([0, 1, 0, 1, 0, 1, 0, 5], np.int32)
+    for crop in ((7, 7), (14, 14), (1, 1), (1, 3), (2, 2)):
+        got = host(crop_and_resize(cu(img), cu(boxes), cu(bi), crop, extrapolation_value=0.5))
+        want = oracle.crop_and_resize(img, boxes, bi, crop[0], crop[1], extrapolation=0.5)
+        assert_bits(got, want, f"crop {crop}")
+
+
+# ------------------------------------------------------------------ DetectionTargetLayer
+def _check_targets(conf, props, cls, gt, pp, pn):
+    from objectdetection_b200 import BuildDetectionTargets
+    B = props.shape[0]
+    t = BuildDetectionTargets(conf, cu(props), cu(cls), cu(gt), DEBUG=True, perm_pos=cu(pp), perm_neg=cu(pn))
+    rois, rcls, deltas = (host(x) for x in t.get_target_rois())
+    d = {k: host(v) for k, v in t.debug_outputs().items()}
+    R = conf.MRCNN_TRAIN_ROIS_PER_IMAGE
+    assert rois.shape == (B, R, 4) and rcls.shape == (B, R) and deltas.shape == (B, R, 4)
+    for b in range(B):
+        w_rois, w_cls, w_deltas, wd = oracle.detection_targets(props[b], cls[b], gt[b], pp[b], pn[b], R, conf.BBOX_STD_DEV)
+        assert np.array_equal(d["counts"][b], wd["counts"]), (b, d["counts"][b], wd["counts"])
+        n_prop, n_gt = wd["counts"][:2]
+        assert np.array_equal(d["pos_indices"][b], wd["pos_indices"])            # bit-exact index lists
+        assert np.array_equal(d["neg_indices"][b], wd["neg_indices"])
+        assert np.array_equal(d["sampled_pos"][b], wd["sampled_pos"])
+        assert np.array_equal(d["sampled_neg"][b], wd["sampled_neg"])
+        assert np.array_equal(d["gt_assignment"][b], wd["gt_assignment"])
+        assert_bits(d["iou"][b][:n_prop, :n_gt], wd["iou"][:n_prop, :n_gt], "iou")
+        assert_bits(d["roi_iou_max"][b][:n_prop], wd["roi_iou_max"][:n_prop], "iou max")
+        assert_bits(rois[b], w_rois, "rois")
+        assert np.array_equal(rcls[b], w_cls[0])
+        assert_bits(deltas[b], w_deltas, "deltas")
+        assert np.allclose(deltas[b], w_deltas, rtol=1e-5, equal_nan=True)
+    return d
+
+
+def test_detection_targets_training_config():
+    """BASELINE config 3: 2000 proposals, 100 GT, 200 sampled ROIs (33% positive), batch 8."""
+    rs = np.random.RandomState(77)
+    conf = Conf()
+    d = _check_targets(conf, *_synth.target_inputs(rs, 8, 2000, 100))
+    assert (d["counts"][:, 4] > 0).all() and (d["counts"][:, 4] <= 66).all()
+
+
+def test_detection_targets_edge_cases():
+    rs = np.random.RandomState(3)
+    conf = ShapesConfig()
+    props, cls, gt, pp, pn = _synth.target_inputs(rs, 4, 300, 10, n_pad=40)
+    cls[1] = 0                                   # image without GT -> all zero targets
+    props[2, 5] = 0                              # a zero row in the middle: compacted indices hit the un-compacted tensor
+    props[3, :250] = 0                           # almost everything padded
+    d = _check_targets(conf, props, cls, gt, pp, pn)
+    assert d["counts"][1, 4] == 0 and d["counts"][1, 5] == 0
+
+
+def test_detection_targets_per_image_signature():
+    """The reference calls BuildDetectionTargets per image (training.py:71-73): [N,4], [G], [G,4] -> [R,4], [1,R], [R,4]."""
+    from objectdetection_b200 import BuildDetectionTargets
+    rs = np.random.RandomState(8)
+    conf = ShapesConfig()
+    props, cls, gt, pp, pn = _synth.target_inputs(rs, 1, 120, 6, n_pad=20)
+    t = BuildDetectionTargets(conf, props[0], cls[0], gt[0], perm_pos=pp[0], perm_neg=pn[0])
+    rois, rcls, deltas = t.get_target_rois()
+    assert tuple(rois.shape) == (32, 4) and tuple(rcls.shape) == (1, 32) and tuple(deltas.shape) == (32, 4)
+    w_rois, w_cls, w_deltas, _ = oracle.detection_targets(props[0], cls[0], gt[0], pp[0], pn[0], 32, conf.BBOX_STD_DEV)
+    assert_bits(host(rois), w_rois, "rois")
+    assert np.array_equal(host(rcls), w_cls)
+    # unseeded path: counts only
+    t2 = BuildDetectionTargets(conf, props[0], cls[0], gt[0], DEBUG=True)
+    assert int(t2.debug_outputs()["counts"][0, 4]) == int((w_cls > 0).sum())
+
+
+# ------------------------------------------------------------------ DetectionLayer
+def _check_detection(conf, window_px, image_shape, props, probs, bbox):
+    from objectdetection_b200 import DetectionLayer
+    D = DetectionLayer(conf, image_shape, props.shape[0], window_px, cu(props), cu(probs), cu(bbox), DEBUG=True)
+    win = oracle.norm_boxes(window_px, image_shape[:2])
+    want, wd = oracle.detection_forward(props, probs, bbox, win, conf.BBOX_STD_DEV, conf.DETECTION_MIN_THRESHOLD,
+                                        conf.DETECTION_NMS_THRESHOLD, conf.DETECTION_POST_NMS_INSTANCES, debug=True)
+    assert np.array_equal(host(D.class_ids), wd["class_ids"])
+    assert_bits(host(D.class_scores), wd["class_scores"], "class_scores")
+    assert_bits(host(D.refined_proposals), wd["refined_proposals"], "refined")
+    assert np.allclose(host(D.refined_proposals), wd["refined_proposals"], rtol=1e-5, equal_nan=True)
+    assert_bits(host(D.clipped_proposals), wd["clipped_proposals"], "clipped")
+    assert np.array_equal(host(D.keep_mask), wd["keep_mask"])
+    assert np.array_equal(host(D.nms_keep_mask), wd["nms_keep_mask"])
+    got = host(D.get_detections())
+    assert_bits(got, want, "detections")
+    return got
+
+
+def test_detection_debug_recipe():
+    """detection.py:285-310: seed 863, (1,8,4) / (1,8,4) / (1,8,4,4), window [131,0,893,1024]."""
+    np.random.seed(863)
+    props = np.array(np.random.random((1, 8, 4)), dtype="float32")
+    probs = np.array(np.random.random((1, 8, 4)), dtype="float32")
+    bbox = np.array(np.random.random((1, 8, 4, 4)), dtype="float32")
+    det = _check_detection(Conf(), np.array([[131, 0, 893, 1024]], "int32"), [1024, 1024, 3], props, probs, bbox)
+    assert det.shape == (1, 100, 6)
+
+
+def test_detection_coco_shape():
+    """BASELINE config 2: [2,1000,81] head outputs, window [131,0,893,1024]."""
+    rs = np.random.RandomState(1234)
+    props = _synth.rois_log_uniform(rs, 2, 1000)
+    props[1, 900:] = 0
+    probs, bbox = _synth.head_outputs(rs, 2, 1000, 81)
+    win = np.array([[131, 0, 893, 1024], [0, 0, 1024, 1024]], "int32")
+    det = _check_detection(Conf(), win, [1024, 1024, 3], props, probs, bbox)
+    assert (det[:, :, 4] > 0).sum() > 50
+    from objectdetection_b200.detection import unmold_detection
+    b, c, s = unmold_detection((600, 800, 3), (1024, 1024, 3), det[0], win[0])
+    wb, wc, ws_ = oracle.unmold_detection((600, 800, 3), (1024, 1024, 3), det[0], win[0])
+    assert np.array_equal(b, wb) and np.array_equal(c, wc) and np.array_equal(s, ws_)
+
+
+def test_detection_ties_caps_and_empty():
+    rs = np.random.RandomState(9)
+    B, N, C = 2, 400, 6
+    props = _synth.random_boxes(rs, B * N).reshape(B, N, 4)
+    probs, bbox = _synth.head_outputs(rs, B, N, C, boosted=0.9)
+    probs = (np.round(probs * 64) / 64).astype(f32)                 # quantised -> score ties
+    conf = Conf()
+    conf.DETECTION_POST_NMS_INSTANCES = 40                          # per-class cap and final cap both bind
+    win = np.array([[100, 0, 900, 1024], [0, 0, 1024, 1024]], "int32")
+    det = _check_detection(conf, win, [1024, 1024, 3], props, probs, bbox)
+    assert np.all(np.diff(det[:, :, 5], axis=1) <= 0)
+    empty = _check_detection(conf, win, [1024, 1024, 3], props, np.full_like(probs, 1.0 / C), bbox)
+    assert not empty.any()
+
+
+# ------------------------------------------------------------------ Faster R-CNN
+def test_frcnn_proposals_and_roi_pool(golden):
+    """BASELINE config 4: 600x1000, stride 16 (38x63 -> 21,546 anchors), 12000 -> 2000; thr 0.7 and the reference's 0.2."""
+    from objectdetection_b200 import fasterrcnn
+    rs = np.random.RandomState(9)
+    h, w, na = 38, 63, 9
+    probs = rs.random_sample((1, h, w, 2 * na))
+    bbox = rs.normal(0, 0.5, size=(1, h, w, 4 * na))
+    for thr in (0.7, 0.2):
+        P = fasterrcnn.Proposals('train', probs, bbox, image_shape=(600, 1000, 3), nms_threshold=thr)
+        got = host(P.get_proposals())
+        want = oracle.frcnn_proposals(probs, bbox, 600, 1000, 12000, 2000, thr)
+        assert got.shape == want.shape and np.all(got[:, 0] == 0)
+        assert np.allclose(got, want, rtol=1e-6, atol=1e-4)
+    assert np.array_equal(fasterrcnn.get_anchors(), golden["frcnn_base_anchors"])
+    # golden: the reference's own decode -> clip -> filter -> NMS on the small 6x9 case
+    gp = np.zeros((1, 6, 9, 18))
+    gp[0, :, :, :9] = golden["frcnn_scores_all"].reshape(6, 9, 9)
+    gb = golden["frcnn_deltas"].reshape(1, 6, 9, 36)
+    for thr in (0.2, 0.7):
+        P = fasterrcnn.Proposals('test', gp, gb, image_shape=(96, 144, 3), nms_threshold=thr, pre_nms_top_n=10 ** 9 // 2,
+                                 post_nms_top_n=50)
+        ref = golden[f"frcnn_nms_out_thr{int(thr * 10)}"].astype(f32)
+        assert np.allclose(host(P.get_proposals())[:, 1:], ref, rtol=1e-6, atol=1e-4)
+    fmap = rs.random_sample((1, h, w, 512)).astype(f32)
+    pooled = host(fasterrcnn.roi_pool(cu(fmap), cu(want[:300]), (600, 1000, 3)))
+    wp = oracle.roi_pool(fmap, want[:300], 600.0, 1000.0)
+    assert pooled.shape == (300, 7, 7, 512)
+    assert_bits(pooled, wp, "roi_pool")
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_are_loud():
+    from objectdetection_b200 import _lib
+    from objectdetection_b200.proposals import apply_box_deltas, top_k
+    with pytest.raises(ValueError):
+        apply_box_deltas(cu(np.zeros((1, 4, 4), f32)), cu(np.zeros((1, 5, 4), f32)))
+    with pytest.raises(ValueError):
+        top_k(cu(np.zeros((1, 4), f32)), 9)
+    L = _lib.lib()
+    dl = _lib.DL()
+    cpu_t = torch.zeros((1, 4, 4))
+    rc = L.od_apply_box_deltas(dl(cpu_t), dl(cpu_t), dl(cpu_t), None)
+    assert rc == -4 and b"CPU" in L.od_last_error_detail()
