@@ -83,6 +83,8 @@ typedef enum {
 int od_version(void);                       /* 10000*major + 100*minor + patch */
 const char* od_strerror(int status);
 const char* od_last_error_detail(void);     /* thread-local, never NULL */
+/* Kernels launched by this library in this process so far (statistics only; a relaxed atomic counter). */
+int64_t od_launch_count(void);
 
 /* ---- anchors (utils.py:230-369) ------------------------------------------- */
 #define OD_MAX_LEVELS 8

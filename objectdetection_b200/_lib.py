@@ -78,6 +78,7 @@ SIGNATURES = {
     "od_version": (c_int, []),
     "od_strerror": (c_char_p, [c_int]),
     "od_last_error_detail": (c_char_p, []),
+    "od_launch_count": (c_int64, []),
     "od_anchor_count": (c_int64, [POINTER(AnchorSpec)]),
     "od_gen_anchors": (c_int, [POINTER(AnchorSpec), c_int, _P, _P]),
     "od_apply_box_deltas": (c_int, [_P, _P, _P, _P]),

@@ -41,10 +41,18 @@ void set_error_detail(const char* fmt, ...);
     cudaError_t _e = (expr);                                                                  \
     if (_e != cudaSuccess) OD_FAIL(OD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));     \
   } while (0)
-#define OD_LAUNCH_CHECK(name)                                                                 \
+// Kernel-launch statistics (od_launch_count): one relaxed atomic add per launch, no other global state.
+void count_launches(int n);
+#define OD_LAUNCH_CHECK_NC(name)                                                              \
   do {                                                                                        \
     cudaError_t _e = cudaGetLastError();                                                      \
     if (_e != cudaSuccess) OD_FAIL(OD_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+// after exactly ONE kernel launch (loops of launches call count_launches themselves + OD_LAUNCH_CHECK_NC)
+#define OD_LAUNCH_CHECK(name)                                                                 \
+  do {                                                                                        \
+    od::count_launches(1);                                                                    \
+    OD_LAUNCH_CHECK_NC(name);                                                                 \
   } while (0)
 
 // ----------------------------------------------------------------------------- DLPack checks

@@ -4,6 +4,9 @@
 namespace od {
 
 static thread_local char g_detail[512] = "";
+static unsigned long long g_launches = 0;
+
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error_detail(const char* fmt, ...) {
   va_list ap;
@@ -66,5 +69,7 @@ const char* od_strerror(int status) {
 }
 
 const char* od_last_error_detail(void) { return od::g_detail; }
+
+int64_t od_launch_count(void) { return (int64_t)__atomic_load_n(&od::g_launches, __ATOMIC_RELAXED); }
 
 }  // extern "C"

@@ -249,8 +249,11 @@ int od_frcnn_proposal_forward(const DLTensor* rpn_box_class_prob, const DLTensor
   {
     const unsigned g = (unsigned)((n_pow2 / 2 + 255) / 256);
     for (int64_t k = 2; k <= n_pow2; k <<= 1)
-      for (int64_t j = k >> 1; j > 0; j >>= 1) bitonic_step_k128_kernel<<<g ? g : 1, 256, 0, st>>>(f.keys, n_pow2, k, j);
-    OD_LAUNCH_CHECK("bitonic_step_k128_kernel");
+      for (int64_t j = k >> 1; j > 0; j >>= 1) {
+        bitonic_step_k128_kernel<<<g ? g : 1, 256, 0, st>>>(f.keys, n_pow2, k, j);
+        count_launches(1);
+      }
+    OD_LAUNCH_CHECK_NC("bitonic_step_k128_kernel");
   }
   const int W = (int)((K + 63) / 64);
   if (K > 0) {

@@ -374,6 +374,7 @@ int od_roi_pool_forward(const DLTensor* feature_map, const DLTensor* proposals, 
       image_w, meta);
   OD_LAUNCH_CHECK("crop_meta_kernel");
   crop_pool2_rows_kernel<<<(unsigned)(n * 7), kCropThreads, 0, st>>>(meta, 14, 14, (int32_t)(D / 4), dptr<float4>(out));
+  count_launches(1);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(meta, st);
   if (e != cudaSuccess) OD_FAIL(OD_ERR_CUDA, "launch crop_pool2_rows_kernel: %s", cudaGetErrorString(e));

@@ -224,8 +224,11 @@ int sort_u64_desc_launch(unsigned long long* keys, int64_t rows, int64_t n_pow2,
   }
   const dim3 grid((unsigned)((n_pow2 / 2 + 255) / 256), (unsigned)rows);
   for (int64_t k = 2; k <= n_pow2; k <<= 1)
-    for (int64_t j = k >> 1; j > 0; j >>= 1) bitonic_step_global_kernel<<<grid, 256, 0, st>>>(keys, n_pow2, k, j);
-  OD_LAUNCH_CHECK("bitonic_step_global_kernel");
+    for (int64_t j = k >> 1; j > 0; j >>= 1) {
+      bitonic_step_global_kernel<<<grid, 256, 0, st>>>(keys, n_pow2, k, j);
+      count_launches(1);
+    }
+  OD_LAUNCH_CHECK_NC("bitonic_step_global_kernel");
   return OD_OK;
 }
 
@@ -270,9 +273,10 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
       shift -= bits;
       topk_hist_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, shift, bits, first, (int)k,
                                                      states, hist);
+      count_launches(1);
       first = 0;
     }
-    OD_LAUNCH_CHECK("topk_hist_kernel");
+    OD_LAUNCH_CHECK_NC("topk_hist_kernel");
   }
   topk_collect_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, take_all, n_pow2, states, buf);
   OD_LAUNCH_CHECK("topk_collect_kernel");
