@@ -8,9 +8,14 @@
 // warp reads/writes 512 contiguous bytes. The reference's per-level where/gather, concat and
 // re-sort (maskrcnn.py:127-173) are not reproduced: each ROI writes straight to out[b*N+n].
 //
-//   1. *_meta_kernel : one thread per ROI -> RoiMeta (level base pointer + sampling grid origin/step)
-//   2. crop_rows_kernel : one CTA per (ROI, output row); x-sample table in shared memory;
-//      each thread keeps 4 bins x 4 taps of 16-byte loads in flight before blending.
+//   crop_bins_kernel : the output is one flat array of bins (roi, y, x), each D*4 contiguous bytes. A CTA owns
+//      kBinsPerCta consecutive bins (every CTA does the same amount of work, ROI boundaries are irrelevant). Its
+//      first threads build a per-bin table in shared memory: level assignment + crop_and_resize grid of the bin's
+//      ROI -> image base pointer, the four tap offsets (in 16-byte units), the two lerp weights and a validity
+//      flag. The main loop then is table lookup + 4 unconditional 16-byte loads per output quad (kUnroll quads,
+//      i.e. 4*kUnroll loads in flight per thread), 3 lerps on packed fp32 pairs (FADD2) and one streaming
+//      16-byte store. No meta kernel, no per-call allocation.
+//   crop_pool2_rows_kernel (+ crop_meta_kernel) : FasterRCNN roi_pool = crop 14x14 fused with 2x2 max-pool.
 #include "common.cuh"
 
 namespace od {
@@ -60,23 +65,6 @@ __device__ __forceinline__ void fill_grid(RoiMeta& m, float4 box, int32_t ph, in
     m.ws = 0.0f;
     m.in_x0 = (float)(0.5 * (double)(x1 + x2) * (double)(m.W - 1));
   }
-}
-
-__global__ void pyramid_meta_kernel(LevelTable lt, const float4* __restrict__ rois, int64_t total, int32_t N, int32_t D,
-                                    int32_t image_h, int32_t image_w, int32_t min_level, int32_t num_levels,
-                                    int32_t ph, int32_t pw, RoiMeta* __restrict__ meta, int32_t* __restrict__ level_out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const float4 r = rois[i];
-  const int32_t level = roi_level_of(r, image_h, image_w, min_level, min_level + num_levels - 1);
-  const int32_t l = level - min_level;
-  RoiMeta m;
-  m.H = lt.H[l];
-  m.W = lt.W[l];
-  m.base = lt.ptr[l] + (int64_t)(i / N) * m.H * m.W * D;
-  fill_grid(m, r, ph, pw);
-  meta[i] = m;
-  if (level_out) level_out[i] = level;
 }
 
 // Generic tf.image.crop_and_resize meta. frcnn != 0: boxes are [n,5] (batch,x1,y1,x2,y2) pixels divided by
@@ -134,65 +122,154 @@ __device__ __forceinline__ void build_xsamples(const RoiMeta& m, int32_t pw, XSa
   }
 }
 
-// One CTA per (roi, output row y). out row is pw*D4 contiguous float4.
-__global__ void __launch_bounds__(kCropThreads)
-crop_rows_kernel(const RoiMeta* __restrict__ meta, int32_t ph, int32_t pw, int32_t D4, float extrap,
-                 float4* __restrict__ out) {
-  __shared__ XSample xs[kMaxPoolW];
-  const int64_t item = blockIdx.x;
-  const int64_t roi = item / ph;
-  const int32_t y = (int32_t)(item - roi * ph);
-  const RoiMeta m = meta[roi];
-  if (m.base == nullptr) return;
-  build_xsamples(m, pw, xs);
-  __syncthreads();
+// ----------------------------------------------------------------------------- crop_bins_kernel
+// Where a ROI comes from: mode 0 = PyramidROIAlign (level from the box, batch = roi / rois_per_image),
+// mode 1 = tf.image.crop_and_resize (explicit box_ind, one image tensor in lt slot 0).
+struct RoiSource {
+  int32_t mode;
+  int32_t rois_per_image;
+  int32_t image_h, image_w, min_level, num_levels;
+  int32_t batch;
+  LevelTable lt;
+  const float4* boxes;
+  const int32_t* box_ind;
+};
 
-  float4* orow = out + (roi * ph + y) * (int64_t)pw * D4;
-  const int32_t total = pw * D4;
-  const float in_y = m.in_y0 + (float)y * m.hs;
-  const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
-  if (!(in_y >= 0.0f) || !(in_y <= (float)(m.H - 1))) {
-    for (int32_t e = threadIdx.x; e < total; e += kCropThreads) stg_cs_f4(orow + e, ext4);
-    return;
-  }
-  const float fl = floorf(in_y);
-  const int32_t top = (int32_t)fl, bot = (int32_t)ceilf(in_y);
-  const float yl = in_y - fl;
-  const float4* __restrict__ rtop = reinterpret_cast<const float4*>(m.base) + (int64_t)top * m.W * D4;
-  const float4* __restrict__ rbot = reinterpret_cast<const float4*>(m.base) + (int64_t)bot * m.W * D4;
+struct __align__(16) BinTaps {  // tap offsets from the image base, in 16-byte units
+  uint32_t tl, tr, bl, br;
+};
+struct __align__(16) BinInfo {  // base pointer (16-byte aligned) | flag in the low bits
+  uintptr_t base_flag;
+  float xl, yl;
+};
+constexpr uintptr_t kBinSample = 0, kBinExtrapolate = 1, kBinSkip = 2;
+constexpr int kBinThreads = 256;
 
-  for (int32_t e0 = threadIdx.x; e0 < total; e0 += kCropThreads * kCropUnroll) {
-    float4 tl[kCropUnroll], tr[kCropUnroll], bl[kCropUnroll], br[kCropUnroll];
-    float xl[kCropUnroll];
-    int32_t ok[kCropUnroll];
-#pragma unroll
-    for (int u = 0; u < kCropUnroll; ++u) {
-      const int32_t e = e0 + u * kCropThreads;
-      ok[u] = 0;
-      if (e < total) {
-        const int32_t x = e / D4, c = e - x * D4;
-        const XSample s = xs[x];
-        ok[u] = s.valid ? 1 : 2;
-        xl[u] = s.lerp;
-        if (s.valid) {
-          const int32_t lo = s.left * D4 + c, ro = s.right * D4 + c;
-          tl[u] = ldg_f4(rtop + lo);
-          tr[u] = ldg_f4(rtop + ro);
-          bl[u] = ldg_f4(rbot + lo);
-          br[u] = ldg_f4(rbot + ro);
-        }
+// packed fp32 pairs (sm_100 FADD2): IEEE add/sub on both halves, so results equal two scalar ops
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+__device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+// a + (b - a) * t per component, every operation individually rounded (the multiply stays scalar: ptxas would
+// contract mul.f32x2 + add.f32x2 into FFMA2)
+__device__ __forceinline__ float4 lerp4p(float4 a, float4 b, float t) {
+  float4 d, r;
+  sub2(d.x, d.y, b.x, b.y, a.x, a.y);
+  sub2(d.z, d.w, b.z, b.w, a.z, a.w);
+  d.x = __fmul_rn(d.x, t);
+  d.y = __fmul_rn(d.y, t);
+  d.z = __fmul_rn(d.z, t);
+  d.w = __fmul_rn(d.w, t);
+  add2(r.x, r.y, a.x, a.y, d.x, d.y);
+  add2(r.z, r.w, a.z, a.w, d.z, d.w);
+  return r;
+}
+
+template <int BINS, int UNROLL, bool POW2>
+__global__ void __launch_bounds__(kBinThreads)
+crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_t ph, int32_t pw, int32_t D4,
+                 int32_t lgD4, float extrap, float4* __restrict__ out, int32_t* __restrict__ level_out) {
+  __shared__ BinTaps s_taps[BINS];
+  __shared__ BinInfo s_info[BINS];
+  const int32_t t = threadIdx.x;
+  const int64_t bin0 = (int64_t)blockIdx.x * BINS;
+  const int32_t nb = (int32_t)min((int64_t)BINS, total_bins - bin0);
+
+  for (int32_t i = t; i < nb; i += kBinThreads) {
+    const int64_t fb = bin0 + i;
+    const int64_t roi = fb / bins_per_roi;
+    const int32_t bin = (int32_t)(fb - roi * bins_per_roi);
+    const int32_t y = bin / pw, x = bin - y * pw;
+    const float4 box = __ldg(&src.boxes[roi]);
+    RoiMeta m;
+    uintptr_t flag = kBinSample;
+    if (src.mode == 0) {
+      const int32_t level = roi_level_of(box, src.image_h, src.image_w, src.min_level, src.min_level + src.num_levels - 1);
+      const int32_t l = level - src.min_level;
+      m.H = src.lt.H[l];
+      m.W = src.lt.W[l];
+      m.base = src.lt.ptr[l] + (roi / src.rois_per_image) * ((int64_t)m.H * m.W * D4 * 4);
+      if (level_out && bin == 0) level_out[roi] = level;
+    } else {
+      const int32_t b = __ldg(&src.box_ind[roi]);
+      m.H = src.lt.H[0];
+      m.W = src.lt.W[0];
+      if (b >= 0 && b < src.batch) {
+        m.base = src.lt.ptr[0] + (int64_t)b * ((int64_t)m.H * m.W * D4 * 4);
+      } else {  // box_ind out of range: TF skips the crop, the output rows are left untouched
+        m.base = src.lt.ptr[0];
+        flag = kBinSkip;
       }
     }
+    fill_grid(m, box, ph, pw);
+    const float in_y = m.in_y0 + (float)y * m.hs;
+    const float in_x = m.in_x0 + (float)x * m.ws;
+    const bool ok = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1)) && (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
+    BinTaps tp = {0u, 0u, 0u, 0u};
+    BinInfo bi;
+    bi.xl = 0.0f;
+    bi.yl = 0.0f;
+    if (ok) {
+      const float fy = floorf(in_y), fx = floorf(in_x);
+      const uint32_t top = (uint32_t)fy, bot = (uint32_t)ceilf(in_y);
+      const uint32_t left = (uint32_t)fx, right = (uint32_t)ceilf(in_x);
+      const uint32_t W = (uint32_t)m.W, d4 = (uint32_t)D4;
+      tp.tl = (top * W + left) * d4;
+      tp.tr = (top * W + right) * d4;
+      tp.bl = (bot * W + left) * d4;
+      tp.br = (bot * W + right) * d4;
+      bi.xl = in_x - fx;
+      bi.yl = in_y - fy;
+    } else if (flag == kBinSample) {
+      flag = kBinExtrapolate;
+    }
+    bi.base_flag = reinterpret_cast<uintptr_t>(m.base) | flag;
+    s_taps[i] = tp;
+    s_info[i] = bi;
+  }
+  __syncthreads();
+
+  const int32_t total = nb * D4;
+  float4* __restrict__ o = out + bin0 * D4;
+  const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
+  for (int32_t e0 = t; e0 < total; e0 += kBinThreads * UNROLL) {
+    float4 tl[UNROLL], tr[UNROLL], bl[UNROLL], br[UNROLL];
+    float xl[UNROLL], yl[UNROLL];
+    uint32_t fl[UNROLL];
 #pragma unroll
-    for (int u = 0; u < kCropUnroll; ++u) {
-      const int32_t e = e0 + u * kCropThreads;
-      if (ok[u] == 1) {
-        const float4 t = lerp4(tl[u], tr[u], xl[u]);
-        const float4 b = lerp4(bl[u], br[u], xl[u]);
-        stg_cs_f4(orow + e, lerp4(t, b, yl));
-      } else if (ok[u] == 2) {
-        stg_cs_f4(orow + e, ext4);
-      }
+    for (int u = 0; u < UNROLL; ++u) {
+      const int32_t e = min(e0 + u * kBinThreads, total - 1);  // clamped: loads are unconditional
+      const int32_t bin = POW2 ? (e >> lgD4) : (e / D4);
+      const uint32_t c = (uint32_t)(POW2 ? (e & (D4 - 1)) : (e - bin * D4));
+      const BinTaps tp = s_taps[bin];
+      const BinInfo bi = s_info[bin];
+      const float4* __restrict__ base = reinterpret_cast<const float4*>(bi.base_flag & ~(uintptr_t)15);
+      fl[u] = (uint32_t)(bi.base_flag & 3u);
+      xl[u] = bi.xl;
+      yl[u] = bi.yl;
+      tl[u] = ldg_f4(base + (tp.tl + c));
+      tr[u] = ldg_f4(base + (tp.tr + c));
+      bl[u] = ldg_f4(base + (tp.bl + c));
+      br[u] = ldg_f4(base + (tp.br + c));
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int32_t e = e0 + u * kBinThreads;
+      const float4 top = lerp4p(tl[u], tr[u], xl[u]);
+      const float4 bot = lerp4p(bl[u], br[u], xl[u]);
+      float4 v = lerp4p(top, bot, yl[u]);
+      if (fl[u] == (uint32_t)kBinExtrapolate) v = ext4;
+      if (e < total && fl[u] != (uint32_t)kBinSkip) stg_cs_f4(o + e, v);
     }
   }
 }
@@ -254,13 +331,42 @@ crop_pool2_rows_kernel(const RoiMeta* __restrict__ meta, int32_t ph, int32_t pw,
 }
 
 // ----------------------------------------------------------------------------- host side
-static int launch_crop_rows(const RoiMeta* meta, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
-                            float* out, cudaStream_t st) {
+static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
+                            float* out, int32_t* level_out, cudaStream_t st) {
   if (n_rois == 0) return OD_OK;
-  const int64_t items = n_rois * ph;
-  if (items > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many (roi,row) items: %lld", (long long)items);
-  crop_rows_kernel<<<(unsigned)items, kCropThreads, 0, st>>>(meta, ph, pw, D / 4, extrap, reinterpret_cast<float4*>(out));
-  OD_LAUNCH_CHECK("crop_rows_kernel");
+  const int32_t D4 = D / 4;
+  const int64_t bins_per_roi = (int64_t)ph * pw;
+  if (bins_per_roi > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "pool shape %dx%d too large", ph, pw);
+  const int64_t total_bins = n_rois * bins_per_roi;
+  for (int l = 0; l < (src.mode == 0 ? src.num_levels : 1); ++l)
+    if ((int64_t)src.lt.H[l] * src.lt.W[l] * D4 > 0xFFFFFFFFll)
+      OD_FAIL(OD_ERR_PARAM, "one image of level %d exceeds 2^32 16-byte units", l);
+  int32_t lg = -1;
+  if ((D4 & (D4 - 1)) == 0) {
+    lg = 0;
+    while ((1 << lg) < D4) ++lg;
+  }
+  if (lg >= 0 && D4 >= 16) {
+    constexpr int BINS = 64;
+    if ((int64_t)BINS * D4 > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "depth %d too large", D);
+    const int64_t grid = (total_bins + BINS - 1) / BINS;
+    if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
+    crop_bins_kernel<BINS, 4, true><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw, D4,
+                                                                         lg, extrap, reinterpret_cast<float4*>(out), level_out);
+  } else {
+    // thin or non-power-of-two depth: more bins per CTA so that the table build is amortised
+    constexpr int BINS = 512;
+    if ((int64_t)BINS * D4 > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "depth %d too large", D);
+    const int64_t grid = (total_bins + BINS - 1) / BINS;
+    if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
+    if (lg >= 0)
+      crop_bins_kernel<BINS, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw,
+                                                                           D4, lg, extrap, reinterpret_cast<float4*>(out), level_out);
+    else
+      crop_bins_kernel<BINS, 2, false><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw,
+                                                                            D4, lg, extrap, reinterpret_cast<float4*>(out), level_out);
+  }
+  OD_LAUNCH_CHECK("crop_bins_kernel");
   return OD_OK;
 }
 
@@ -270,16 +376,13 @@ using namespace od;
 
 extern "C" {
 
-// The RoiMeta table lives at the tail of `pooled`? No: callers do not pass a workspace for this entry
-// (the reference API has none), so the table is carved from a small per-call device allocation made with
-// cudaMallocAsync on `stream` (stream-ordered, no synchronisation).
 int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
                                  const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t pool_h,
                                  int32_t pool_w, DLTensor* pooled, DLTensor* roi_level, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!fmaps) OD_FAIL(OD_ERR_NULL, "fmaps is NULL");
   if (num_levels < 1 || num_levels > OD_MAX_LEVELS) OD_FAIL(OD_ERR_PARAM, "num_levels %d not in [1,%d]", num_levels, OD_MAX_LEVELS);
-  if (pool_h < 1 || pool_w < 1 || pool_w > kMaxPoolW) OD_FAIL(OD_ERR_PARAM, "pool shape %dx%d unsupported (w <= %d)", pool_h, pool_w, kMaxPoolW);
+  if (pool_h < 1 || pool_w < 1) OD_FAIL(OD_ERR_PARAM, "pool shape %dx%d unsupported", pool_h, pool_w);
   int dev = -1;
   OD_CHECK(check_tensor(rois, "rois", F32, 3, true, &dev));
   if (rois->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "rois must be [B,N,4]");
@@ -311,15 +414,19 @@ int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_level
   }
   const int64_t total = B * N;
   if (total == 0) return OD_OK;
-  RoiMeta* meta = nullptr;
-  OD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&meta), sizeof(RoiMeta) * (size_t)total, st));
-  pyramid_meta_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-      lt, dptr<float4>(rois), total, (int32_t)N, (int32_t)D, image_h, image_w, min_level, num_levels, pool_h, pool_w,
-      meta, dptr<int32_t>(roi_level));
-  OD_LAUNCH_CHECK("pyramid_meta_kernel");
-  int rc = launch_crop_rows(meta, total, pool_h, pool_w, (int32_t)D, 0.0f, dptr<float>(pooled), st);
-  cudaFreeAsync(meta, st);
-  return rc;
+  if (reinterpret_cast<uintptr_t>(dptr<float>(rois)) % 16) OD_FAIL(OD_ERR_LAYOUT, "rois not 16-byte aligned");
+  RoiSource src;
+  memset(&src, 0, sizeof(src));
+  src.mode = 0;
+  src.rois_per_image = (int32_t)N;
+  src.image_h = image_h;
+  src.image_w = image_w;
+  src.min_level = min_level;
+  src.num_levels = num_levels;
+  src.batch = (int32_t)B;
+  src.lt = lt;
+  src.boxes = dptr<float4>(rois);
+  return launch_crop_bins(src, total, pool_h, pool_w, (int32_t)D, 0.0f, dptr<float>(pooled), dptr<int32_t>(roi_level), st);
 }
 
 int od_crop_and_resize(const DLTensor* image, const DLTensor* boxes, const DLTensor* box_ind, int32_t crop_h,
@@ -330,7 +437,7 @@ int od_crop_and_resize(const DLTensor* image, const DLTensor* boxes, const DLTen
   OD_CHECK(check_tensor(boxes, "boxes", F32, 2, true, &dev));
   OD_CHECK(check_tensor(box_ind, "box_ind", I32, 1, true, &dev));
   OD_CHECK(check_tensor(out, "out", F32, 4, true, &dev));
-  if (crop_h < 1 || crop_w < 1 || crop_w > kMaxPoolW) OD_FAIL(OD_ERR_PARAM, "crop size %dx%d unsupported", crop_h, crop_w);
+  if (crop_h < 1 || crop_w < 1) OD_FAIL(OD_ERR_PARAM, "crop size %dx%d unsupported", crop_h, crop_w);
   const int64_t n = boxes->shape[0], D = image->shape[3];
   if (boxes->shape[1] != 4 || box_ind->shape[0] != n) OD_FAIL(OD_ERR_SHAPE, "boxes [n,4] / box_ind [n] mismatch");
   if (out->shape[0] != n || out->shape[1] != crop_h || out->shape[2] != crop_w || out->shape[3] != D)
@@ -340,15 +447,16 @@ int od_crop_and_resize(const DLTensor* image, const DLTensor* boxes, const DLTen
       reinterpret_cast<uintptr_t>(dptr<float>(boxes)) % 16)
     OD_FAIL(OD_ERR_LAYOUT, "image/boxes/out must be 16-byte aligned");
   if (n == 0) return OD_OK;
-  RoiMeta* meta = nullptr;
-  OD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&meta), sizeof(RoiMeta) * (size_t)n, st));
-  crop_meta_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(
-      dptr<float>(image), (int32_t)image->shape[0], (int32_t)image->shape[1], (int32_t)image->shape[2], (int32_t)D,
-      dptr<float>(boxes), dptr<int32_t>(box_ind), (int32_t)n, crop_h, crop_w, 0, 1.f, 1.f, meta);
-  OD_LAUNCH_CHECK("crop_meta_kernel");
-  int rc = launch_crop_rows(meta, n, crop_h, crop_w, (int32_t)D, extrapolation_value, dptr<float>(out), st);
-  cudaFreeAsync(meta, st);
-  return rc;
+  RoiSource src;
+  memset(&src, 0, sizeof(src));
+  src.mode = 1;
+  src.batch = (int32_t)image->shape[0];
+  src.lt.ptr[0] = dptr<float>(image);
+  src.lt.H[0] = (int32_t)image->shape[1];
+  src.lt.W[0] = (int32_t)image->shape[2];
+  src.boxes = dptr<float4>(boxes);
+  src.box_ind = dptr<int32_t>(box_ind);
+  return launch_crop_bins(src, n, crop_h, crop_w, (int32_t)D, extrapolation_value, dptr<float>(out), nullptr, st);
 }
 
 int od_roi_pool_forward(const DLTensor* feature_map, const DLTensor* proposals, float image_h, float image_w,
