@@ -263,7 +263,7 @@ int od_frcnn_proposal_forward(const DLTensor* rpn_box_class_prob, const DLTensor
     frcnn_mask_kernel<<<grid, 64, 0, st>>>(f.sorted, f.counters, (int)K, W, params->nms_threshold, f.mask, f.diagT);
     OD_LAUNCH_CHECK("frcnn_mask_kernel");
   }
-  OD_CHECK(nms_scan_launch(f.mask, f.diagT, f.counters + 1, 1, K, post_n, f.keep_pos, f.counters + 2, nullptr, st));
+  OD_CHECK(nms_scan_launch(f.mask, f.diagT, f.counters + 1, 1, K, (K + 63) / 64, post_n, f.keep_pos, f.counters + 2, nullptr, st));
   frcnn_emit_kernel<<<(unsigned)((post_n + 255) / 256), 256, 0, st>>>(f.sorted, f.keep_pos, f.counters + 2, (int)post_n,
                                                                      dptr<float>(proposals), dptr<int32_t>(num_out));
   OD_LAUNCH_CHECK("frcnn_emit_kernel");

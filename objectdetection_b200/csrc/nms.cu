@@ -1,14 +1,18 @@
 // nms.cu — greedy hard NMS with tf.image.non_max_suppression semantics as a bitmask-IoU kernel
 // plus a single-CTA keep scan. Call sites replaced: proposals_tf.py:234, detection.py:177.
 //
-//   mask kernel : 64x64 IoU tiles over the upper triangle; thread t of a tile owns row i and builds the
-//                 64-bit word "which later boxes j does i suppress" (fp32 IoU in TF's operation order,
-//                 IEEE division, `> thr`). Diagonal tiles also emit their transpose with warp ballots
-//                 (word j = which earlier boxes of the tile suppress j) for the scan.
-//   scan kernel : one CTA per image walks the 64-box chunks in order. Inside a chunk the greedy
-//                 recurrence kept_j = cand_j && !(sup_j & kept) is solved by warp-ballot fixed-point
-//                 iteration (bit j is final after j+1 rounds; typically 2-4 rounds), then the rows of the
-//                 kept boxes are OR-ed into the running `removed` bitmap in shared memory. Stops as soon
+//   mask kernel : 64x64 IoU tiles over the upper triangle only (linear tile index -> (row, col) tile); thread t
+//                 of a tile owns row i and builds the 64-bit word "which later boxes j does i suppress". The
+//                 pair test is TF's IoU in TF's operation order, but the IEEE division only runs when the
+//                 intersection is positive (inter == 0 gives IoU 0 or NaN, never > thr for thr >= 0), which
+//                 is the rare case. Diagonal tiles also emit their transpose with warp ballots (word j =
+//                 which earlier boxes of the tile suppress j) for the scan.
+//   scan kernel : one CTA per image walks the 64-box chunks in order. Inside a chunk the greedy recurrence
+//                 kept_j = cand_j && !(sup_j & kept) is solved by warp-ballot fixed-point iteration (bit j is
+//                 final after j+1 rounds; typically 2-4 rounds), then the mask rows of the kept boxes are
+//                 OR-ed into the running `removed` bitmap in shared memory. The 64 mask rows of chunk c+1
+//                 and its transposed diagonal tile are prefetched (cp.async into a double buffer / registers)
+//                 while chunk c is resolved, so the per-chunk critical path never waits on L2. Stops as soon
 //                 as max_out boxes are kept.
 #include "nms.cuh"
 #include "topk.cuh"
@@ -17,22 +21,39 @@ namespace od {
 
 constexpr int kScanThreads = 512;
 
+// Upper-triangle tile t -> (rb, cb), cb >= rb, rows of W, W-1, ... tiles.
+__device__ __forceinline__ void tile_of(int64_t t, int W, int& rb, int& cb) {
+  // rows before rb hold  rb*W - rb*(rb-1)/2  tiles
+  const double Wd = (double)W + 0.5;
+  int r = (int)(Wd - sqrt(Wd * Wd - 2.0 * (double)t));
+  r = max(0, min(r, W - 1));
+  while (r > 0 && (int64_t)r * W - (int64_t)r * (r - 1) / 2 > t) --r;
+  while ((int64_t)(r + 1) * W - (int64_t)(r + 1) * r / 2 <= t) ++r;
+  rb = r;
+  cb = r + (int)(t - ((int64_t)r * W - (int64_t)r * (r - 1) / 2));
+}
+
+template <bool FAST>  // FAST: thr >= 0, division skipped when the intersection is not positive
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ num_valid,
-                const int32_t* __restrict__ group, int K, int W, float thr,
+                const int32_t* __restrict__ group, int K, int W, int Ws, float thr,
                 unsigned long long* __restrict__ mask, uint32_t* __restrict__ diagT) {
-  const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
-  if (cb < rb) return;
+  int rb, cb;
+  tile_of(blockIdx.x, W, rb, cb);
+  const int b = blockIdx.y;
   const int n = num_valid ? min(num_valid[b], K) : K;
-  if (rb * 64 >= n || cb * 64 >= n) return;
-  __shared__ CBox cbox[64];
+  if (cb * 64 >= n) return;  // (rb <= cb)
+  __shared__ float4 cbox[64];   // canonical corners
+  __shared__ float carea[64];
   __shared__ int32_t cgrp[64];
   const int t = threadIdx.x;
   const float4* bx = boxes + (int64_t)b * K;
   {
     const int j = cb * 64 + t;
     const float4 v = (j < n) ? bx[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-    cbox[t] = canon_box(v);
+    const CBox c = canon_box(v);
+    cbox[t] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+    carea[t] = c.area;
     cgrp[t] = (group && j < n) ? group[(int64_t)b * K + j] : 0;
   }
   __syncthreads();
@@ -41,13 +62,30 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
   if (i < n) {
     const CBox my = canon_box(bx[i]);
     const int32_t g = group ? group[(int64_t)b * K + i] : 0;
-#pragma unroll 8
-    for (int jj = 0; jj < 64; ++jj) {
-      const int j = cb * 64 + jj;
-      const bool hit = (j > i) && (j < n) && (tf_iou(my, cbox[jj]) > thr) && (g == cgrp[jj]);
+    const int jmax = min(64, n - cb * 64);
+    const int jmin = (cb == rb) ? t + 1 : 0;   // only j > i
+#pragma unroll 4
+    for (int jj = jmin; jj < jmax; ++jj) {
+      const float4 c = cbox[jj];
+      bool hit;
+      if (FAST) {
+        const float ih = f_min(my.ymax, c.z) - f_max(my.ymin, c.x);
+        const float iw = f_min(my.xmax, c.w) - f_max(my.xmin, c.y);
+        const float inter = f_max(ih, 0.0f) * f_max(iw, 0.0f);
+        hit = false;
+        if (inter > 0.0f) {
+          const float aj = carea[jj];
+          // inter > 0 implies both areas > 0 (inter <= area under monotone rounding)
+          hit = (inter / (my.area + aj - inter) > thr) && (g == cgrp[jj]);
+        }
+      } else {
+        CBox o;
+        o.ymin = c.x; o.xmin = c.y; o.ymax = c.z; o.xmax = c.w; o.area = carea[jj];
+        hit = (tf_iou(my, o) > thr) && (g == cgrp[jj]);
+      }
       bits |= (unsigned long long)hit << jj;
     }
-    mask[((int64_t)b * K + i) * W + cb] = bits;
+    mask[((int64_t)b * K + i) * Ws + cb] = bits;
   }
   if (cb == rb) {
     // transpose of the diagonal tile: word jj, bit t = "box t of this chunk suppresses box jj"
@@ -61,28 +99,80 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// NBUF >= 2: staged scan — Ws is even and NBUF buffers of (64 mask rows + the transposed diagonal tile) fit in shared
+// memory; chunk c+NBUF-1 is prefetched with cp.async while chunk c is resolved. NBUF == 0: direct global loads.
+template <int NBUF>
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __restrict__ diagT,
-                const int32_t* __restrict__ num_valid, int K, int W, int max_out, int32_t* __restrict__ keep_pos,
+                const int32_t* __restrict__ num_valid, int K, int W, int Ws, int max_out, int32_t* __restrict__ keep_pos,
                 int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
-  extern __shared__ unsigned long long removed[];  // [W]
+  constexpr bool STAGED = NBUF >= 2;
+  constexpr int DIST = STAGED ? NBUF - 1 : 1;
+  extern __shared__ __align__(16) unsigned long long smem_u64[];
+  unsigned long long* removed = smem_u64;       // [Ws]
+  unsigned long long* stage = smem_u64 + Ws;    // [NBUF][64*Ws + 64] when STAGED
+  const size_t buf_words = (size_t)64 * Ws + 64;
   __shared__ unsigned long long kept_word;
   const int b = blockIdx.x;
   const int n = num_valid ? min(num_valid[b], K) : K;
   const int Wn = (n + 63) / 64;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int w = tid; w < W; w += kScanThreads) removed[w] = 0ull;
+  for (int w = tid; w < Ws; w += kScanThreads) removed[w] = 0ull;
   if (keep_flag)
     for (int i = tid; i < K; i += kScanThreads) keep_flag[(int64_t)b * K + i] = 0;
   int kept_total = 0;
-  const unsigned long long* mrow = mask + (int64_t)b * K * W;
-  for (int c = 0; c < Wn && kept_total < max_out; ++c) {
-    __syncthreads();
+  const unsigned long long* mrow = mask + (int64_t)b * K * Ws;
+  const uint32_t* dbase = diagT + (int64_t)b * W * 128;
+
+  // chunk c -> stage[c % NBUF]: its 64 mask rows, 16-byte units [(c+1)/2, ceil(Wn/2)), and its diagonal tile
+  auto prefetch = [&](int c) {
+    if (STAGED && c < Wn) {
+      unsigned long long* dst = stage + (size_t)(c % (STAGED ? NBUF : 1)) * buf_words;
+      const int u0 = (c + 1) >> 1, u1 = (Wn + 1) >> 1;
+      const int r = tid >> 3;
+      const int row = c * 64 + r;
+      if (row < n)
+        for (int u = u0 + (tid & 7); u < u1; u += 8)
+          cp_async16(dst + (size_t)r * Ws + 2 * u, mrow + (size_t)row * Ws + 2 * u);
+      if (tid < 32) cp_async16(dst + (size_t)64 * Ws + 2 * tid, dbase + (size_t)c * 128 + 4 * tid);
+    }
+    cp_async_commit();
+  };
+  unsigned long long sup0 = 0ull, sup1 = 0ull;   // !STAGED: warp 0 holds the diagonal tile of the current chunk
+  auto load_diag = [&](int c, unsigned long long& s0, unsigned long long& s1) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(dbase + (size_t)c * 128) + lane);
+    const uint2 d = __ldg(reinterpret_cast<const uint2*>(dbase + (size_t)c * 128) + lane + 32);
+    s0 = ((unsigned long long)a.y << 32) | a.x;
+    s1 = ((unsigned long long)d.y << 32) | d.x;
+  };
+  if (STAGED) {
+#pragma unroll
+    for (int c = 0; c < DIST; ++c) prefetch(c);
+  } else if (warp == 0 && Wn > 0) {
+    load_diag(0, sup0, sup1);
+  }
+
+  for (int c = 0; c < Wn; ++c) {
+    if (STAGED) cp_async_wait<DIST - 1>();   // this thread's share of chunk c has landed
+    __syncthreads();                         // everyone's share; removed[c] is final; buffer (c-1)%NBUF is free
+    if (STAGED) prefetch(c + DIST);
+    unsigned long long nsup0 = 0ull, nsup1 = 0ull;
+    if (!STAGED && warp == 0 && c + 1 < Wn) load_diag(c + 1, nsup0, nsup1);
+    const unsigned long long* buf = stage + (size_t)(c % (STAGED ? NBUF : 1)) * buf_words;
     if (warp == 0) {
+      if (STAGED) {
+        sup0 = buf[(size_t)64 * Ws + lane];
+        sup1 = buf[(size_t)64 * Ws + lane + 32];
+      }
       const unsigned long long word = removed[c];
-      const uint32_t* dt = diagT + ((int64_t)b * W + c) * 128;
-      const unsigned long long sup0 = ((unsigned long long)dt[lane * 2 + 1] << 32) | dt[lane * 2];
-      const unsigned long long sup1 = ((unsigned long long)dt[(lane + 32) * 2 + 1] << 32) | dt[(lane + 32) * 2];
       const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
       const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
       unsigned long long kept = (unsigned long long)__ballot_sync(0xffffffffu, cand0) |
@@ -96,35 +186,53 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __r
         kept = nk;
       }
       // respect max_out: drop the highest set bits beyond the allowance
-      int allow = max_out - kept_total;
+      const int allow = max_out - kept_total;
       while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
       if (lane == 0) kept_word = kept;
+      if (!STAGED) {
+        sup0 = nsup0;
+        sup1 = nsup1;
+      }
     }
     __syncthreads();
     const unsigned long long kept = kept_word;
-    if (kept == 0ull) continue;
-    if (tid < 64 && ((kept >> tid) & 1ull)) {
-      const int pos = kept_total + __popcll(kept & ((1ull << tid) - 1ull));
-      if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = c * 64 + tid;
-      if (keep_flag) keep_flag[(int64_t)b * K + c * 64 + tid] = 1;
-    }
-    kept_total += __popcll(kept);
-    if (kept_total >= max_out) break;
-    // OR the rows of the kept boxes into removed[c+1 .. Wn): 128 word lanes x 4 row groups
-    const int rg = tid >> 7, wl = tid & 127;
-    for (int w = c + 1 + wl; w < Wn; w += 128) {
-      unsigned long long acc = 0ull;
-      int rank = 0;
+    if (kept != 0ull) {
+      if (tid < 64 && ((kept >> tid) & 1ull)) {
+        const int pos = kept_total + __popcll(kept & ((1ull << tid) - 1ull));
+        if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = c * 64 + tid;
+        if (keep_flag) keep_flag[(int64_t)b * K + c * 64 + tid] = 1;
+      }
+      kept_total += __popcll(kept);
+      if (kept_total >= max_out) break;
+      // OR the rows of the kept boxes into removed[c+1 .. Wn)
+      if (STAGED) {
+        for (int w = c + 1 + tid; w < Wn; w += kScanThreads) {   // one thread per word, rows from shared memory
+          unsigned long long acc = 0ull;
 #pragma unroll 8
-      for (int bit = 0; bit < 64; ++bit) {
-        if ((kept >> bit) & 1ull) {
-          if ((rank & 3) == rg) acc |= __ldg(&mrow[((int64_t)c * 64 + bit) * W + w]);
-          ++rank;
+          for (int bit = 0; bit < 64; ++bit)
+            if ((kept >> bit) & 1ull) acc |= buf[(size_t)bit * Ws + w];
+          removed[w] |= acc;
+        }
+      } else {
+        // unconditional, fully pipelined global loads: 8 row groups x 64 word lanes
+        const int rg = tid >> 6, wl = tid & 63;
+        for (int w = c + 1 + wl; w < Wn; w += 64) {
+          unsigned long long v[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int row = min(c * 64 + rg * 8 + r, K - 1);
+            v[r] = __ldg(&mrow[(size_t)row * Ws + w]);
+          }
+          unsigned long long acc = 0ull;
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if ((kept >> (rg * 8 + r)) & 1ull) acc |= v[r];
+          if (acc) atomicOr(&removed[w], acc);
         }
       }
-      if (acc) atomicOr(&removed[w], acc);
     }
   }
+  if (STAGED) cp_async_wait<0>();
   __syncthreads();
   if (keep_pos)
     for (int j = kept_total + tid; j < max_out; j += kScanThreads) keep_pos[(int64_t)b * max_out + j] = -1;
@@ -132,9 +240,9 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __r
 }
 
 size_t nms_sorted_workspace_bytes(int64_t B, int64_t K) {
-  const int64_t W = (K + 63) / 64;
+  const int64_t W = (K + 63) / 64, Ws = nms_mask_stride(K);
   Workspace w(nullptr, 0);
-  w.take<unsigned long long>((size_t)(B * K * W));
+  w.take<unsigned long long>((size_t)(B * K * Ws));
   w.take<uint32_t>((size_t)(B * W * 128));
   return w.off + 256;
 }
@@ -145,29 +253,47 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
   if (B == 0) return OD_OK;
   if (B > 65535) OD_FAIL(OD_ERR_PARAM, "NMS batch %lld > 65535", (long long)B);
   if (K >= (1 << 22)) OD_FAIL(OD_ERR_PARAM, "NMS supports < 4M boxes per image");
-  const int W = (int)((K + 63) / 64);
+  const int W = (int)((K + 63) / 64), Ws = (int)nms_mask_stride(K);
   Workspace w(ws, ws_bytes);
-  unsigned long long* mask = w.take<unsigned long long>((size_t)(B * K * W));
+  unsigned long long* mask = w.take<unsigned long long>((size_t)(B * K * Ws));
   uint32_t* diagT = w.take<uint32_t>((size_t)(B * W * 128));
   if (!ws || !w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "NMS workspace %zu < %zu bytes", ws_bytes, w.off);
   if (K > 0) {
-    if (W > 65535) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
-    const dim3 grid((unsigned)W, (unsigned)W, (unsigned)B);
-    nms_mask_kernel<<<grid, 64, 0, st>>>(boxes, num_valid, group, (int)K, W, thr, mask, diagT);
+    const int64_t tiles = (int64_t)W * (W + 1) / 2;
+    if (tiles > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
+    const dim3 grid((unsigned)tiles, (unsigned)B, 1);
+    if (thr >= 0.0f)
+      nms_mask_kernel<true><<<grid, 64, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
+    else
+      nms_mask_kernel<false><<<grid, 64, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
     OD_LAUNCH_CHECK("nms_mask_kernel");
   }
-  return nms_scan_launch(mask, diagT, num_valid, B, K, max_out, keep_pos, num_kept, keep_flag, st);
+  return nms_scan_launch(mask, diagT, num_valid, B, K, Ws, max_out, keep_pos, num_kept, keep_flag, st);
 }
 
 int nms_scan_launch(const unsigned long long* mask, const uint32_t* diagT, const int32_t* num_valid, int64_t B,
-                    int64_t K, int64_t max_out, int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag,
-                    cudaStream_t st) {
-  const int W = (int)((K + 63) / 64);
-  const size_t smem = (size_t)(W > 0 ? W : 1) * sizeof(unsigned long long);
-  if (smem > 48 * 1024)
-    OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_scan_kernel<<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, (int)max_out, keep_pos,
-                                                           num_kept, keep_flag);
+                    int64_t K, int64_t mask_stride, int64_t max_out, int32_t* keep_pos, int32_t* num_kept,
+                    int32_t* keep_flag, cudaStream_t st) {
+  const int W = (int)((K + 63) / 64), Ws = (int)mask_stride;
+  if (Ws < W) OD_FAIL(OD_ERR_PARAM, "NMS mask stride %d < %d words", Ws, W);
+  const size_t plain = (size_t)(Ws > 0 ? Ws : 1) * sizeof(unsigned long long);
+  const size_t per_buf = ((size_t)64 * Ws + 64) * sizeof(unsigned long long);
+  const bool aligned = (Ws % 2 == 0) && (reinterpret_cast<uintptr_t>(mask) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(diagT) % 16 == 0);
+  const size_t kSmemBudget = 200 * 1024;
+  const int nbuf = !aligned ? 0 : (plain + 3 * per_buf <= kSmemBudget ? 3 : (plain + 2 * per_buf <= kSmemBudget ? 2 : 0));
+  const size_t smem = plain + (size_t)nbuf * per_buf;
+#define OD_SCAN_LAUNCH(NB)                                                                                          \
+  do {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                           \
+      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    nms_scan_kernel<NB><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, (int)max_out, \
+                                                                 keep_pos, num_kept, keep_flag);                    \
+  } while (0)
+  if (nbuf == 3) OD_SCAN_LAUNCH(3);
+  else if (nbuf == 2) OD_SCAN_LAUNCH(2);
+  else OD_SCAN_LAUNCH(0);
+#undef OD_SCAN_LAUNCH
   OD_LAUNCH_CHECK("nms_scan_kernel");
   return OD_OK;
 }

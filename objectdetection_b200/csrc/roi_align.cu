@@ -100,7 +100,6 @@ struct XSample {
 };
 constexpr int kMaxPoolW = 64;
 constexpr int kCropThreads = 128;
-constexpr int kCropUnroll = 4;
 
 __device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
   return make_float4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t);

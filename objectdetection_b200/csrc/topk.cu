@@ -19,6 +19,7 @@ constexpr int kBins = 1 << kDigitBits;
 constexpr int kSelThreads = 256;
 constexpr int kSortThreads = 1024;
 constexpr int64_t kSmemSortMax = 16384;
+constexpr int64_t kRankSortMaxK = 8192;   // above this the k^2 rank sort loses to the bitonic networks
 
 struct __align__(16) SelState {
   unsigned long long prefix;  // determined high bits of the k-th key (low `shift` bits are zero)
@@ -176,6 +177,44 @@ topk_sort_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_st
   }
 }
 
+// Rank sort + emit: keys are unique, so the position of a key in descending order is the number of keys greater
+// than it. grid (ceil(k/64), rows); a CTA owns 64 keys, its 4 thread groups each count over a quarter of every
+// 1024-key tile staged in shared memory (k^2 compares spread over the whole GPU instead of one CTA's bitonic
+// network: 36 M compares per row at k = 6000).
+constexpr int kRankThreads = 256;
+constexpr int kRankMine = 64;
+constexpr int kRankTile = 1024;
+__global__ void __launch_bounds__(kRankThreads)
+topk_rank_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int k, int ib,
+                      const float* __restrict__ scores, int64_t row_stride, int64_t col_stride,
+                      int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  __shared__ unsigned long long tile[kRankTile];
+  __shared__ int32_t partial[kRankThreads];
+  const int row = blockIdx.y;
+  const unsigned long long* in = buf + (int64_t)row * buf_stride;
+  const int me = blockIdx.x * kRankMine + (threadIdx.x & (kRankMine - 1));
+  const int part = threadIdx.x >> 6;
+  const unsigned long long mine = (me < k) ? in[me] : ~0ull;
+  int rank = 0;
+  for (int t0 = 0; t0 < k; t0 += kRankTile) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRankTile; i += kRankThreads) tile[i] = (t0 + i < k) ? in[t0 + i] : 0ull;
+    __syncthreads();
+    const unsigned long long* tp = tile + part * (kRankTile / 4);
+#pragma unroll 16
+    for (int j = 0; j < kRankTile / 4; ++j) rank += (tp[j] > mine) ? 1 : 0;
+  }
+  partial[threadIdx.x] = rank;
+  __syncthreads();
+  if (part == 0 && me < k) {
+    rank += partial[threadIdx.x + 64] + partial[threadIdx.x + 128] + partial[threadIdx.x + 192];
+    const uint32_t imask = (1u << ib) - 1u;
+    const uint32_t idx = imask - (uint32_t)(mine & imask);
+    idx_out[(int64_t)row * k + rank] = (int32_t)idx;
+    if (val_out) val_out[(int64_t)row * k + rank] = scores[(int64_t)row * row_stride + (int64_t)idx * col_stride];
+  }
+}
+
 // ---- generic descending sort of uint64 segments (shared-memory when it fits, global bitonic otherwise)
 __global__ void __launch_bounds__(kSortThreads)
 sort_u64_smem_kernel(unsigned long long* __restrict__ keys, int n_pow2) {
@@ -280,7 +319,11 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
   }
   topk_collect_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, take_all, n_pow2, states, buf);
   OD_LAUNCH_CHECK("topk_collect_kernel");
-  if (n_pow2 <= kSmemSortMax) {
+  if (k <= kRankSortMaxK) {
+    const dim3 g((unsigned)((k + kRankMine - 1) / kRankMine), (unsigned)rows);
+    topk_rank_emit_kernel<<<g, kRankThreads, 0, st>>>(buf, n_pow2, (int)k, ib, scores, row_stride, col_stride, idx_out, val_out);
+    OD_LAUNCH_CHECK("topk_rank_emit_kernel");
+  } else if (n_pow2 <= kSmemSortMax) {
     const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
     OD_CUDA(cudaFuncSetAttribute(topk_sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_sort_emit_kernel<<<(unsigned)rows, kSortThreads, smem, st>>>(buf, n_pow2, k, (int)n_pow2, ib, scores, row_stride,
