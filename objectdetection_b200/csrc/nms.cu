@@ -1,8 +1,9 @@
 // nms.cu — greedy hard NMS with tf.image.non_max_suppression semantics as a bitmask-IoU kernel
 // plus a single-CTA keep scan. Call sites replaced: proposals_tf.py:234, detection.py:177.
 //
-//   mask kernel : 64x64 IoU tiles over the upper triangle only (linear tile index -> (row, col) tile); thread t
-//                 of a tile owns row i and builds the 64-bit word "which later boxes j does i suppress". The
+//   mask kernel : 64x64 IoU tiles over the upper triangle; a CTA owns 64 rows x 4 column tiles whose canonical boxes
+//                 sit in shared memory; a thread owns row i and builds the 64-bit words "which later boxes j does
+//                 i suppress" of two tiles. The
 //                 pair test is TF's IoU in TF's operation order, but the IEEE division only runs when the
 //                 intersection is positive (inter == 0 gives IoU 0 or NaN, never > thr for thr >= 0), which
 //                 is the rare case. Diagonal tiles also emit their transpose with warp ballots (word j =
@@ -21,80 +22,76 @@ namespace od {
 
 constexpr int kScanThreads = 512;
 
-// Upper-triangle tile t -> (rb, cb), cb >= rb, rows of W, W-1, ... tiles.
-__device__ __forceinline__ void tile_of(int64_t t, int W, int& rb, int& cb) {
-  // rows before rb hold  rb*W - rb*(rb-1)/2  tiles
-  const double Wd = (double)W + 0.5;
-  int r = (int)(Wd - sqrt(Wd * Wd - 2.0 * (double)t));
-  r = max(0, min(r, W - 1));
-  while (r > 0 && (int64_t)r * W - (int64_t)r * (r - 1) / 2 > t) --r;
-  while ((int64_t)(r + 1) * W - (int64_t)(r + 1) * r / 2 <= t) ++r;
-  rb = r;
-  cb = r + (int)(t - ((int64_t)r * W - (int64_t)r * (r - 1) / 2));
-}
+constexpr int kMaskColTiles = 4;   // column tiles (of 64 boxes) per CTA
+constexpr int kMaskThreads = 128;  // 64 rows x 2 halves; half h owns column tiles h, h+2 of the CTA's span
 
 template <bool FAST>  // FAST: thr >= 0, division skipped when the intersection is not positive
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ num_valid,
                 const int32_t* __restrict__ group, int K, int W, int Ws, float thr,
                 unsigned long long* __restrict__ mask, uint32_t* __restrict__ diagT) {
-  int rb, cb;
-  tile_of(blockIdx.x, W, rb, cb);
-  const int b = blockIdx.y;
+  const int rb = blockIdx.y, b = blockIdx.z;
+  const int cb0 = rb + blockIdx.x * kMaskColTiles;
   const int n = num_valid ? min(num_valid[b], K) : K;
-  if (cb * 64 >= n) return;  // (rb <= cb)
-  __shared__ float4 cbox[64];   // canonical corners
-  __shared__ float carea[64];
-  __shared__ int32_t cgrp[64];
+  if (cb0 * 64 >= n) return;  // rb <= cb0: nothing valid in this span
+  __shared__ float4 cbox[kMaskColTiles * 64];   // canonical corners; boxes >= n are zero-area (never hit)
+  __shared__ float carea[kMaskColTiles * 64];
+  __shared__ int32_t cgrp[kMaskColTiles * 64];
   const int t = threadIdx.x;
   const float4* bx = boxes + (int64_t)b * K;
-  {
-    const int j = cb * 64 + t;
+  for (int q = t; q < kMaskColTiles * 64; q += kMaskThreads) {
+    const int j = cb0 * 64 + q;
     const float4 v = (j < n) ? bx[j] : make_float4(0.f, 0.f, 0.f, 0.f);
     const CBox c = canon_box(v);
-    cbox[t] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
-    carea[t] = c.area;
-    cgrp[t] = (group && j < n) ? group[(int64_t)b * K + j] : 0;
+    cbox[q] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+    carea[q] = c.area;
+    cgrp[q] = (group && j < n) ? group[(int64_t)b * K + j] : -1;
   }
   __syncthreads();
-  const int i = rb * 64 + t;
-  unsigned long long bits = 0ull;
-  if (i < n) {
-    const CBox my = canon_box(bx[i]);
-    const int32_t g = group ? group[(int64_t)b * K + i] : 0;
-    const int jmax = min(64, n - cb * 64);
-    const int jmin = (cb == rb) ? t + 1 : 0;   // only j > i
-#pragma unroll 4
-    for (int jj = jmin; jj < jmax; ++jj) {
-      const float4 c = cbox[jj];
+  const int r = t & 63, half = t >> 6;
+  const int i = rb * 64 + r;
+  const bool row_ok = i < n;
+  const CBox my = canon_box(row_ok ? bx[i] : make_float4(0.f, 0.f, 0.f, 0.f));
+  const int32_t g = (group && row_ok) ? group[(int64_t)b * K + i] : 0;
+#pragma unroll
+  for (int ct = 0; ct < kMaskColTiles / 2; ++ct) {
+    const int tile = half + 2 * ct;
+    const int cb = cb0 + tile;
+    if (cb * 64 >= n) break;   // uniform per half (two warps)
+    unsigned long long bits = 0ull;
+    const float4* cbp = cbox + tile * 64;
+    const float* cap = carea + tile * 64;
+    const int32_t* cgp = cgrp + tile * 64;
+#pragma unroll 16
+    for (int jj = 0; jj < 64; ++jj) {
+      const float4 c = cbp[jj];
       bool hit;
       if (FAST) {
         const float ih = f_min(my.ymax, c.z) - f_max(my.ymin, c.x);
         const float iw = f_min(my.xmax, c.w) - f_max(my.xmin, c.y);
         const float inter = f_max(ih, 0.0f) * f_max(iw, 0.0f);
         hit = false;
-        if (inter > 0.0f) {
-          const float aj = carea[jj];
-          // inter > 0 implies both areas > 0 (inter <= area under monotone rounding)
-          hit = (inter / (my.area + aj - inter) > thr) && (g == cgrp[jj]);
-        }
+        if (inter > 0.0f)  // implies both areas > 0 (inter <= area under monotone rounding)
+          hit = (inter / (my.area + cap[jj] - inter) > thr) && (!group || g == cgp[jj]);
       } else {
         CBox o;
-        o.ymin = c.x; o.xmin = c.y; o.ymax = c.z; o.xmax = c.w; o.area = carea[jj];
-        hit = (tf_iou(my, o) > thr) && (g == cgrp[jj]);
+        o.ymin = c.x; o.xmin = c.y; o.ymax = c.z; o.xmax = c.w; o.area = cap[jj];
+        hit = (cb * 64 + jj < n) && (tf_iou(my, o) > thr) && (!group || g == cgp[jj]);
       }
       bits |= (unsigned long long)hit << jj;
     }
-    mask[((int64_t)b * K + i) * Ws + cb] = bits;
-  }
-  if (cb == rb) {
-    // transpose of the diagonal tile: word jj, bit t = "box t of this chunk suppresses box jj"
-    uint32_t* dt = diagT + ((int64_t)b * W + cb) * 128;
-    const int warp = t >> 5, lane = t & 31;
+    if (cb == rb) bits &= (r == 63) ? 0ull : ~((2ull << r) - 1ull);   // only j > i
+    if (!row_ok) bits = 0ull;
+    if (row_ok) mask[((int64_t)b * K + i) * Ws + cb] = bits;
+    if (cb == rb) {
+      // transpose of the diagonal tile: word jj, bit r = "box r of this chunk suppresses box jj"
+      uint32_t* dt = diagT + ((int64_t)b * W + cb) * 128;
+      const int warp = (t >> 5) & 1, lane = t & 31;
 #pragma unroll 8
-    for (int jj = 0; jj < 64; ++jj) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (bits >> jj) & 1ull);
-      if (lane == 0) dt[jj * 2 + warp] = bal;
+      for (int jj = 0; jj < 64; ++jj) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (bits >> jj) & 1ull);
+        if (lane == 0) dt[jj * 2 + warp] = bal;
+      }
     }
   }
 }
@@ -206,13 +203,20 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __r
       if (kept_total >= max_out) break;
       // OR the rows of the kept boxes into removed[c+1 .. Wn)
       if (STAGED) {
-        for (int w = c + 1 + tid; w < Wn; w += kScanThreads) {   // one thread per word, rows from shared memory
-          unsigned long long acc = 0ull;
-#pragma unroll 8
-          for (int bit = 0; bit < 64; ++bit)
-            if ((kept >> bit) & 1ull) acc |= buf[(size_t)bit * Ws + w];
-          removed[w] |= acc;
-        }
+        // 8 row groups x 64 word lanes, rows from shared memory (unconditional loads, select by kept bit)
+        const int rg = tid >> 6, wl = tid & 63;
+        const unsigned int kbits = (unsigned int)(kept >> (rg * 8)) & 0xFFu;
+        if (kbits)
+          for (int w = c + 1 + wl; w < Wn; w += 64) {
+            const unsigned long long* col = buf + (size_t)(rg * 8) * Ws + w;
+            unsigned long long acc = 0ull;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const unsigned long long v = col[(size_t)r * Ws];
+              acc |= ((kbits >> r) & 1u) ? v : 0ull;
+            }
+            if (acc) atomicOr(&removed[w], acc);
+          }
       } else {
         // unconditional, fully pipelined global loads: 8 row groups x 64 word lanes
         const int rg = tid >> 6, wl = tid & 63;
@@ -259,13 +263,12 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
   uint32_t* diagT = w.take<uint32_t>((size_t)(B * W * 128));
   if (!ws || !w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "NMS workspace %zu < %zu bytes", ws_bytes, w.off);
   if (K > 0) {
-    const int64_t tiles = (int64_t)W * (W + 1) / 2;
-    if (tiles > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
-    const dim3 grid((unsigned)tiles, (unsigned)B, 1);
+    if (W > 65535) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
+    const dim3 grid((unsigned)((W + kMaskColTiles - 1) / kMaskColTiles), (unsigned)W, (unsigned)B);
     if (thr >= 0.0f)
-      nms_mask_kernel<true><<<grid, 64, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
+      nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
     else
-      nms_mask_kernel<false><<<grid, 64, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
+      nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
     OD_LAUNCH_CHECK("nms_mask_kernel");
   }
   return nms_scan_launch(mask, diagT, num_valid, B, K, Ws, max_out, keep_pos, num_kept, keep_flag, st);

@@ -178,11 +178,11 @@ topk_sort_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_st
 }
 
 // Rank sort + emit: keys are unique, so the position of a key in descending order is the number of keys greater
-// than it. grid (ceil(k/64), rows); a CTA owns 64 keys, its 4 thread groups each count over a quarter of every
+// than it. grid (ceil(k/16), rows); a CTA owns 16 keys, its 16 thread groups each count over a 16th of every
 // 1024-key tile staged in shared memory (k^2 compares spread over the whole GPU instead of one CTA's bitonic
 // network: 36 M compares per row at k = 6000).
 constexpr int kRankThreads = 256;
-constexpr int kRankMine = 64;
+constexpr int kRankMine = 16;
 constexpr int kRankTile = 1024;
 __global__ void __launch_bounds__(kRankThreads)
 topk_rank_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int k, int ib,
@@ -193,21 +193,23 @@ topk_rank_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_st
   const int row = blockIdx.y;
   const unsigned long long* in = buf + (int64_t)row * buf_stride;
   const int me = blockIdx.x * kRankMine + (threadIdx.x & (kRankMine - 1));
-  const int part = threadIdx.x >> 6;
+  constexpr int kParts = kRankThreads / kRankMine;
+  const int part = threadIdx.x / kRankMine;
   const unsigned long long mine = (me < k) ? in[me] : ~0ull;
   int rank = 0;
   for (int t0 = 0; t0 < k; t0 += kRankTile) {
     __syncthreads();
     for (int i = threadIdx.x; i < kRankTile; i += kRankThreads) tile[i] = (t0 + i < k) ? in[t0 + i] : 0ull;
     __syncthreads();
-    const unsigned long long* tp = tile + part * (kRankTile / 4);
+    const unsigned long long* tp = tile + part * (kRankTile / kParts);
 #pragma unroll 16
-    for (int j = 0; j < kRankTile / 4; ++j) rank += (tp[j] > mine) ? 1 : 0;
+    for (int j = 0; j < kRankTile / kParts; ++j) rank += (tp[j] > mine) ? 1 : 0;
   }
   partial[threadIdx.x] = rank;
   __syncthreads();
   if (part == 0 && me < k) {
-    rank += partial[threadIdx.x + 64] + partial[threadIdx.x + 128] + partial[threadIdx.x + 192];
+#pragma unroll
+    for (int q = 1; q < kParts; ++q) rank += partial[threadIdx.x + q * kRankMine];
     const uint32_t imask = (1u << ib) - 1u;
     const uint32_t idx = imask - (uint32_t)(mine & imask);
     idx_out[(int64_t)row * k + rank] = (int32_t)idx;
