@@ -337,6 +337,24 @@ def run_ours(args):
         step(dev_sets[i % NSETS])
     torch.cuda.synchronize()
 
+    if args.kernel_times:
+        # developer aid (not a bench number): per-kernel device times of a few live steps via CUPTI
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(4):
+                step(dev_sets[i % NSETS])
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type is not None and "cuda" in str(ev.device_type).lower():
+                a = agg.setdefault(ev.name[:70], [0, 0.0])
+                a[0] += 1
+                a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        tot = sum(v[1] for v in agg.values()) / 4
+        for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{us / 4:9.1f} us/step  x{cnt / 4:4.1f}  {name}", file=sys.stderr)
+        print(f"{tot:9.1f} us/step  total kernel time", file=sys.stderr)
+
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
     if rank == 0:
@@ -452,6 +470,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-times", action="store_true", help="print per-kernel device times (CUPTI) to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -62,23 +62,45 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
     const float4* cbp = cbox + tile * 64;
     const float* cap = carea + tile * 64;
     const int32_t* cgp = cgrp + tile * 64;
-#pragma unroll 16
-    for (int jj = 0; jj < 64; ++jj) {
-      const float4 c = cbp[jj];
-      bool hit;
-      if (FAST) {
+    if (FAST) {
+      // pass 1, branch-free: candidates = pairs whose intersection has positive height and width. Everything else
+      // has inter == 0 (or NaN) in TF's arithmetic and can never exceed a threshold >= 0.
+      uint32_t cand_lo = 0u, cand_hi = 0u;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const float4 c = cbp[jj];
+        const bool p = (fminf(my.ymax, c.z) > fmaxf(my.ymin, c.x)) && (fminf(my.xmax, c.w) > fmaxf(my.xmin, c.y));
+        cand_lo |= p ? (1u << jj) : 0u;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const float4 c = cbp[32 + jj];
+        const bool p = (fminf(my.ymax, c.z) > fmaxf(my.ymin, c.x)) && (fminf(my.xmax, c.w) > fmaxf(my.xmin, c.y));
+        cand_hi |= p ? (1u << jj) : 0u;
+      }
+      unsigned long long m = ((unsigned long long)cand_hi << 32) | cand_lo;
+      if (cb == rb) m &= (r == 63) ? 0ull : ~((2ull << r) - 1ull);   // only j > i
+      // pass 2, rare: the exact TF IoU (operation order, IEEE division) of the candidates
+      while (m) {
+        const int jj = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        const float4 c = cbp[jj];
         const float ih = f_min(my.ymax, c.z) - f_max(my.ymin, c.x);
         const float iw = f_min(my.xmax, c.w) - f_max(my.xmin, c.y);
         const float inter = f_max(ih, 0.0f) * f_max(iw, 0.0f);
-        hit = false;
-        if (inter > 0.0f)  // implies both areas > 0 (inter <= area under monotone rounding)
-          hit = (inter / (my.area + cap[jj] - inter) > thr) && (!group || g == cgp[jj]);
-      } else {
+        // inter > 0 implies both areas > 0 (inter <= area under monotone rounding), TF's area guard is moot
+        const bool hit = (inter > 0.0f) && (inter / (my.area + cap[jj] - inter) > thr) && (!group || g == cgp[jj]);
+        bits |= (unsigned long long)hit << jj;
+      }
+    } else {
+#pragma unroll 8
+      for (int jj = 0; jj < 64; ++jj) {
+        const float4 c = cbp[jj];
         CBox o;
         o.ymin = c.x; o.xmin = c.y; o.ymax = c.z; o.xmax = c.w; o.area = cap[jj];
-        hit = (cb * 64 + jj < n) && (tf_iou(my, o) > thr) && (!group || g == cgp[jj]);
+        const bool hit = (cb * 64 + jj < n) && (tf_iou(my, o) > thr) && (!group || g == cgp[jj]);
+        bits |= (unsigned long long)hit << jj;
       }
-      bits |= (unsigned long long)hit << jj;
     }
     if (cb == rb) bits &= (r == 63) ? 0ull : ~((2ull << r) - 1ull);   // only j > i
     if (!row_ok) bits = 0ull;
