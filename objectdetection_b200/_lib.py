@@ -197,6 +197,24 @@ def as_cuda(x, dtype, device=None) -> torch.Tensor:
     return t.contiguous()
 
 
+_const_cache = {}
+
+
+def const_cuda(arr, dtype, device) -> torch.Tensor:
+    """Small host constants (e.g. a normalised window) as CUDA tensors, cached by content, so that repeated calls
+    with the same values issue no H2D copy (and the call can be captured in a CUDA graph after one eager run)."""
+    import numpy as np
+    a = np.ascontiguousarray(arr)
+    key = (torch.device(device).index, str(dtype), a.dtype.str, a.shape, a.tobytes())
+    t = _const_cache.get(key)
+    if t is None:
+        if len(_const_cache) > 256:
+            _const_cache.clear()
+        t = torch.from_numpy(a.copy()).to(device).to(dtype).contiguous()
+        _const_cache[key] = t
+    return t
+
+
 def make_anchor_spec(image_shape, scales, ratios, feature_map_shapes, feature_map_strides, anchor_stride) -> AnchorSpec:
     s = AnchorSpec()
     if len(scales) > OD_MAX_LEVELS or len(ratios) > OD_MAX_RATIOS:

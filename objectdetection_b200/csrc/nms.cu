@@ -63,20 +63,25 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
     const float* cap = carea + tile * 64;
     const int32_t* cgp = cgrp + tile * 64;
     if (FAST) {
-      // pass 1, branch-free: candidates = pairs whose intersection has positive height and width. Everything else
-      // has inter == 0 (or NaN) in TF's arithmetic and can never exceed a threshold >= 0.
+      // pass 1, branch-free: candidates = a superset of the pairs whose intersection has positive height and width.
+      // Everything else has inter == 0 (or NaN) in TF's arithmetic and can never exceed a threshold >= 0.
+      // (min(a,b) > max(c,d) needs a > d and b > c; a > c / b > d are the boxes' own validity, which pass 2 settles.)
+      // The four differences run on the FMA pipe; a pair is a candidate iff all four are negative, i.e. the AND of
+      // their sign bits is set, which one funnel shift appends to the word (bit jj ends up at position jj).
       uint32_t cand_lo = 0u, cand_hi = 0u;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
+      for (int jj = 31; jj >= 0; --jj) {
         const float4 c = cbp[jj];
-        const bool p = (fminf(my.ymax, c.z) > fmaxf(my.ymin, c.x)) && (fminf(my.xmax, c.w) > fmaxf(my.xmin, c.y));
-        cand_lo |= p ? (1u << jj) : 0u;
+        const uint32_t sgn = __float_as_uint(c.x - my.ymax) & __float_as_uint(my.ymin - c.z) &
+                             __float_as_uint(c.y - my.xmax) & __float_as_uint(my.xmin - c.w);
+        cand_lo = __funnelshift_l(sgn, cand_lo, 1);
       }
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
+      for (int jj = 31; jj >= 0; --jj) {
         const float4 c = cbp[32 + jj];
-        const bool p = (fminf(my.ymax, c.z) > fmaxf(my.ymin, c.x)) && (fminf(my.xmax, c.w) > fmaxf(my.xmin, c.y));
-        cand_hi |= p ? (1u << jj) : 0u;
+        const uint32_t sgn = __float_as_uint(c.x - my.ymax) & __float_as_uint(my.ymin - c.z) &
+                             __float_as_uint(c.y - my.xmax) & __float_as_uint(my.xmin - c.w);
+        cand_hi = __funnelshift_l(sgn, cand_hi, 1);
       }
       unsigned long long m = ((unsigned long long)cand_hi << 32) | cand_lo;
       if (cb == rb) m &= (r == 63) ? 0ull : ~((2ull << r) - 1ull);   // only j > i

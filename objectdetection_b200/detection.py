@@ -62,7 +62,7 @@ class DetectionLayer():
         dev = props.device
         probs = _lib.as_cuda(mrcnn_class_probs, torch.float32, dev)
         bbox = _lib.as_cuda(mrcnn_bbox, torch.float32, dev)
-        win = _lib.as_cuda(np.asarray(window, np.float32).reshape(-1, 4), torch.float32, dev)
+        win = _lib.const_cuda(np.asarray(window, np.float32).reshape(-1, 4), torch.float32, dev)
         B, N, C = probs.shape
         if B != self.num_batches:
             raise ValueError(f"num_batches={self.num_batches} but mrcnn_class_probs has batch {B}")
