@@ -8,18 +8,14 @@
 // warp reads/writes 512 contiguous bytes. The reference's per-level where/gather, concat and
 // re-sort (maskrcnn.py:127-173) are not reproduced: each ROI writes straight to out[b*N+n].
 //
-//   crop_cols_kernel : pool sizes <= 32 (the 7x7 / 14x14 / 28x28 cases): separable walk down the output rows, see
-//      the comment at the kernel. crop_bins_kernel below is the general fallback.
 //   crop_bins_kernel : the output is one flat array of bins (roi, y, x), each D*4 contiguous bytes. A CTA owns
 //      kBinsPerCta consecutive bins (every CTA does the same amount of work, ROI boundaries are irrelevant). Its
 //      first threads build a per-bin table in shared memory: level assignment + crop_and_resize grid of the bin's
 //      ROI -> image base pointer, the four tap offsets (in 16-byte units), the two lerp weights and a validity
-//      flag. The main loop then is table lookup + 4 unconditional 16-byte loads per output quad (kUnroll quads,
-//      i.e. 4*kUnroll loads in flight per thread), 3 lerps on packed fp32 pairs (FADD2) and one streaming
+//      flag. The main loop then is table lookup + 4 unconditional 16-byte loads per output quad (2 quads,
+//      i.e. 8 loads in flight per thread), 3 lerps on packed fp32 pairs (FADD2) and one streaming
 //      16-byte store. No meta kernel, no per-call allocation.
 //   crop_pool2_rows_kernel (+ crop_meta_kernel) : FasterRCNN roi_pool = crop 14x14 fused with 2x2 max-pool.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace od {
@@ -178,14 +174,8 @@ __device__ __forceinline__ float4 lerp4p(float4 a, float4 b, float t) {
   return r;
 }
 
-__device__ __forceinline__ float4 ldg_f4_ordered(const float4* p) {   // asm volatile: issued in program order
-  float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-
-template <int BINS, int UNROLL, bool POW2, bool ORDERED = false, int MINB = 1>
-__global__ void __launch_bounds__(kBinThreads, MINB)
+template <int BINS, int UNROLL, bool POW2>
+__global__ void __launch_bounds__(kBinThreads)
 crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_t ph, int32_t pw, int32_t D4,
                  int32_t lgD4, float extrap, float4* __restrict__ out, int32_t* __restrict__ level_out) {
   __shared__ BinTaps s_taps[BINS];
@@ -266,24 +256,10 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
       fl[u] = (uint32_t)(bi.base_flag & 3u);
       xl[u] = bi.xl;
       yl[u] = bi.yl;
-      if (ORDERED) {
-        tl[u] = ldg_f4_ordered(base + (tp.tl + c));
-        tr[u] = ldg_f4_ordered(base + (tp.tr + c));
-        bl[u] = ldg_f4_ordered(base + (tp.bl + c));
-        br[u] = ldg_f4_ordered(base + (tp.br + c));
-      } else {
-        tl[u] = ldg_f4(base + (tp.tl + c));
-        tr[u] = ldg_f4(base + (tp.tr + c));
-        bl[u] = ldg_f4(base + (tp.bl + c));
-        br[u] = ldg_f4(base + (tp.br + c));
-      }
-    }
-    if (ORDERED) {   // every load result is "used" here, so all 4*UNROLL loads are in flight before the first lerp
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u)
-        asm volatile("" ::"f"(tl[u].x), "f"(tl[u].y), "f"(tl[u].z), "f"(tl[u].w), "f"(tr[u].x), "f"(tr[u].y), "f"(tr[u].z),
-                     "f"(tr[u].w), "f"(bl[u].x), "f"(bl[u].y), "f"(bl[u].z), "f"(bl[u].w), "f"(br[u].x), "f"(br[u].y),
-                     "f"(br[u].z), "f"(br[u].w));
+      tl[u] = ldg_f4(base + (tp.tl + c));
+      tr[u] = ldg_f4(base + (tp.tr + c));
+      bl[u] = ldg_f4(base + (tp.bl + c));
+      br[u] = ldg_f4(base + (tp.br + c));
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -293,140 +269,6 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
       float4 v = lerp4p(top, bot, yl[u]);
       if (fl[u] == (uint32_t)kBinExtrapolate) v = ext4;
       if (e < total && fl[u] != (uint32_t)kBinSkip) stg_cs_f4(o + e, v);
-    }
-  }
-}
-
-// ----------------------------------------------------------------------------- crop_cols_kernel
-// Separable form of the same arithmetic for pool sizes <= 32: TF's  top = tl + (tr-tl)*xl  only depends on
-// (feature row, x bin), so a thread that owns one (roi, x bin, channel quad) column and walks down the output rows
-// needs each distinct feature row of the ROI once: 2 loads + 1 lerp per distinct row, 1 lerp + 1 store per output.
-// For the typical up-sampled ROI (8 feature rows -> 14 output rows) that is 1.3 loads per output instead of 4.
-// The per-ROI plan (distinct feature rows in sampling order and how many outputs each one completes) is built by one
-// thread into shared memory; every branch of the main loop is uniform over the CTA.
-constexpr int kColMaxP = 32;
-struct ColPlan {
-  const float4* base;                 // image (level, batch) base; nullptr -> crop skipped
-  uint32_t row_off[2 * kColMaxP];     // distinct feature rows in visiting order: row * W * D4 (16-byte units)
-  uint8_t n_topprev[2 * kColMaxP];    // outputs with (top, bottom) = (previous distinct row, this row)
-  uint8_t n_same[2 * kColMaxP];       // outputs with top == bottom == this row (integral sample position)
-  uint8_t y_of[kColMaxP];             // output row of visit index i (in-range rows, increasing sample position)
-  float yl[kColMaxP];                 // y lerp weight of visit index i
-  uint8_t y_ext[kColMaxP];            // output rows whose sample position is out of range
-  int32_t n_rows, n_valid, n_ext;
-  int32_t W;
-  float in_x0, ws;
-};
-
-__global__ void __launch_bounds__(512)
-crop_cols_kernel(RoiSource src, int32_t ph, int32_t pw, int32_t D4, int32_t xg, int32_t dq, int32_t ngroups,
-                 float extrap, float4* __restrict__ out, int32_t* __restrict__ level_out) {
-  __shared__ ColPlan P;
-  const int64_t roi = blockIdx.x / ngroups;
-  const int32_t grp = blockIdx.x - (int32_t)roi * ngroups;
-  if (threadIdx.x == 0) {
-    const float4 box = __ldg(&src.boxes[roi]);
-    RoiMeta m;
-    m.base = nullptr;
-    if (src.mode == 0) {
-      const int32_t level = roi_level_of(box, src.image_h, src.image_w, src.min_level, src.min_level + src.num_levels - 1);
-      const int32_t l = level - src.min_level;
-      m.H = src.lt.H[l];
-      m.W = src.lt.W[l];
-      m.base = src.lt.ptr[l] + (roi / src.rois_per_image) * ((int64_t)m.H * m.W * D4 * 4);
-      if (level_out && grp == 0) level_out[roi] = level;
-    } else {
-      const int32_t b = __ldg(&src.box_ind[roi]);
-      m.H = src.lt.H[0];
-      m.W = src.lt.W[0];
-      if (b >= 0 && b < src.batch) m.base = src.lt.ptr[0] + (int64_t)b * ((int64_t)m.H * m.W * D4 * 4);
-    }
-    fill_grid(m, box, ph, pw);
-    P.base = reinterpret_cast<const float4*>(m.base);
-    P.W = m.W;
-    P.in_x0 = m.in_x0;
-    P.ws = m.ws;
-    // visit the output rows by increasing sample position (reverse order for a flipped box)
-    const bool rev = m.hs < 0.0f;
-    const uint32_t row_stride = (uint32_t)m.W * (uint32_t)D4;
-    int32_t nr = 0, nv = 0, ne = 0, last = -1;
-    for (int32_t i = 0; i < ph; ++i) {
-      const int32_t y = rev ? ph - 1 - i : i;
-      const float in_y = m.in_y0 + (float)y * m.hs;
-      if (!((in_y >= 0.0f) && (in_y <= (float)(m.H - 1)))) {
-        P.y_ext[ne++] = (uint8_t)y;
-        continue;
-      }
-      const float fl = floorf(in_y);
-      const int32_t T = (int32_t)fl, Bt = (int32_t)ceilf(in_y);
-      P.y_of[nv] = (uint8_t)y;
-      P.yl[nv] = in_y - fl;
-      ++nv;
-      if (last < T) {  // a new top row
-        P.row_off[nr] = (uint32_t)T * row_stride;
-        P.n_topprev[nr] = 0;
-        P.n_same[nr] = 0;
-        ++nr;
-        last = T;
-      }
-      if (Bt == T) {          // last == T here (T was appended now or is the most recent row)
-        ++P.n_same[nr - 1];
-      } else if (last == Bt) {  // (T, T+1) with T+1 already the most recent row
-        ++P.n_topprev[nr - 1];
-      } else {                // last == T: append the bottom row
-        P.row_off[nr] = (uint32_t)Bt * row_stride;
-        P.n_topprev[nr] = 1;
-        P.n_same[nr] = 0;
-        ++nr;
-        last = Bt;
-      }
-    }
-    P.n_rows = nr;
-    P.n_valid = nv;
-    P.n_ext = ne;
-  }
-  __syncthreads();
-  const float4* __restrict__ base = P.base;
-  if (base == nullptr) return;
-  const int32_t xi = threadIdx.x / dq, q = threadIdx.x - xi * dq;
-  const int32_t x = grp * xg + xi;
-  if (xi >= xg || x >= pw) return;
-  const float in_x = P.in_x0 + (float)x * P.ws;
-  const bool xok = (in_x >= 0.0f) && (in_x <= (float)(P.W - 1));
-  const float fx = floorf(in_x);
-  const uint32_t left = xok ? (uint32_t)fx : 0u, right = xok ? (uint32_t)ceilf(in_x) : 0u;
-  const float xl = in_x - fx;
-  const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
-  const int64_t ystride = (int64_t)pw * D4;
-  const int32_t n_rows = P.n_rows, n_valid = P.n_valid, n_ext = P.n_ext;
-  for (int32_t c4 = q; c4 < D4; c4 += dq) {
-    float4* __restrict__ o = out + ((int64_t)roi * ph * pw + x) * D4 + c4;
-    for (int32_t i = 0; i < n_ext; ++i) stg_cs_f4(o + P.y_ext[i] * ystride, ext4);
-    if (!xok) {
-      for (int32_t i = 0; i < n_valid; ++i) stg_cs_f4(o + P.y_of[i] * ystride, ext4);
-      continue;
-    }
-    const float4* __restrict__ pl = base + (left * (uint32_t)D4 + (uint32_t)c4);
-    const float4* __restrict__ pr = base + (right * (uint32_t)D4 + (uint32_t)c4);
-    float4 L = make_float4(0.f, 0.f, 0.f, 0.f), R = L, cur = L, prev = L;
-    if (n_rows > 0) {
-      L = ldg_f4(pl + P.row_off[0]);
-      R = ldg_f4(pr + P.row_off[0]);
-    }
-    int32_t yi = 0;
-    for (int32_t k = 0; k < n_rows; ++k) {
-      float4 Ln = L, Rn = R;
-      if (k + 1 < n_rows) {   // prefetch the next distinct row while this one is consumed
-        Ln = ldg_f4(pl + P.row_off[k + 1]);
-        Rn = ldg_f4(pr + P.row_off[k + 1]);
-      }
-      prev = cur;
-      cur = lerp4p(L, R, xl);
-      const int32_t n1 = P.n_topprev[k], n2 = P.n_same[k];
-      for (int32_t j = 0; j < n1; ++j, ++yi) stg_cs_f4(o + P.y_of[yi] * ystride, lerp4p(prev, cur, P.yl[yi]));
-      for (int32_t j = 0; j < n2; ++j, ++yi) stg_cs_f4(o + P.y_of[yi] * ystride, lerp4p(cur, cur, P.yl[yi]));
-      L = Ln;
-      R = Rn;
     }
   }
 }
@@ -498,21 +340,6 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
   for (int l = 0; l < (src.mode == 0 ? src.num_levels : 1); ++l)
     if ((int64_t)src.lt.H[l] * src.lt.W[l] * D4 > 0xFFFFFFFFll)
       OD_FAIL(OD_ERR_PARAM, "one image of level %d exceeds 2^32 16-byte units", l);
-  static const int variant = getenv("ODHEAD_CROP_VARIANT") ? atoi(getenv("ODHEAD_CROP_VARIANT")) : 0;   // dev knob
-  if (variant == 5 && ph <= kColMaxP && pw <= kColMaxP) {
-    // column kernel: CTA = one ROI x xg x-bins x dq channel quads
-    int32_t dq = D4 < 64 ? D4 : 64;
-    int32_t ngroups = (pw * dq + 511) / 512;
-    int32_t xg = (pw + ngroups - 1) / ngroups;
-    ngroups = (pw + xg - 1) / xg;
-    const int64_t grid = n_rois * ngroups;
-    if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many ROIs: %lld", (long long)n_rois);
-    int32_t threads = ((xg * dq + 31) / 32) * 32;
-    crop_cols_kernel<<<(unsigned)grid, threads, 0, st>>>(src, ph, pw, D4, xg, dq, ngroups, extrap,
-                                                        reinterpret_cast<float4*>(out), level_out);
-    OD_LAUNCH_CHECK("crop_cols_kernel");
-    return OD_OK;
-  }
   int32_t lg = -1;
   if ((D4 & (D4 - 1)) == 0) {
     lg = 0;
@@ -520,24 +347,12 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
   }
   if (lg >= 0 && D4 >= 16) {
     if ((int64_t)64 * D4 > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "depth %d too large", D);
-    const int bins = (variant == 2 || variant == 3) ? 32 : ((variant == 9 || variant == 11) ? 128 : 64);
-    const int64_t grid = (total_bins + bins - 1) / bins;
+    constexpr int BINS = 64;
+    const int64_t grid = (total_bins + BINS - 1) / BINS;
     if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
-#define OD_CROP_ARGS src, total_bins, (int32_t)bins_per_roi, ph, pw, D4, lg, extrap, reinterpret_cast<float4*>(out), level_out
-    switch (variant) {
-      case 1: crop_bins_kernel<64, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 2: crop_bins_kernel<32, 4, true><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 3: crop_bins_kernel<32, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 4: crop_bins_kernel<64, 4, true, true, 2><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 6: crop_bins_kernel<64, 4, true, true, 3><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 7: crop_bins_kernel<64, 8, true, true, 2><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 8: crop_bins_kernel<64, 1, true><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 9: crop_bins_kernel<128, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 10: crop_bins_kernel<64, 2, true, true, 4><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      case 11: crop_bins_kernel<128, 1, true><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-      default: crop_bins_kernel<64, 4, true><<<(unsigned)grid, kBinThreads, 0, st>>>(OD_CROP_ARGS); break;
-    }
-#undef OD_CROP_ARGS
+    // 64 bins x 2 quads in flight per thread: best of the {32,64,128} x {1,2,4,8} sweep (profiles/r1_crop_variants.md)
+    crop_bins_kernel<BINS, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw, D4,
+                                                                         lg, extrap, reinterpret_cast<float4*>(out), level_out);
   } else {
     // thin or non-power-of-two depth: more bins per CTA so that the table build is amortised
     constexpr int BINS = 512;
