@@ -269,6 +269,7 @@ def run_ours(args):
 
     from objectdetection_b200 import DetectionLayer, Proposals, _lib, utils
     from objectdetection_b200.config import config
+    from objectdetection_b200.distributed import gather_detections
     from objectdetection_b200.maskrcnn import pyramid_roi_align
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,7 +304,6 @@ def run_ours(args):
     h2d_bytes = sum(t.numel() * 4 for k, v in host_sets[0].items() for t in (v if isinstance(v, list) else [v]))
     pooled7 = torch.empty((1, B * N_ROIS, 7, 7, DEPTH), dtype=torch.float32, device=dev)
     pooled14 = torch.empty((1, B * N_ROIS, 14, 14, DEPTH), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world * B, conf.DETECTION_POST_NMS_INSTANCES, 6), dtype=torch.float32, device=dev) if world > 1 else None
     roi_ev = []
 
     def front(inp):
@@ -349,8 +349,7 @@ def run_ours(args):
             e1.record()
             roi_ev.append((e0, e1))
         if world > 1:
-            dist.all_gather_into_tensor(gathered, det)
-            return gathered, proposals
+            return gather_detections(det, batch=world * B), proposals     # the path's only collective
         return det, proposals
 
     def barrier():
@@ -438,7 +437,7 @@ def run_ours(args):
             else:
                 d_[k_].copy_(v, non_blocking=True)
         d, _ = step(s_)
-        return d[:B].cpu() if world > 1 else d.cpu()   # D2H of this rank's detections (synchronises)
+        return d[rank * B:(rank + 1) * B].cpu()       # D2H of this rank's detections (synchronises)
 
     for i in range(2):
         e2e_step(i % NSETS)

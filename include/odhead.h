@@ -185,6 +185,9 @@ typedef struct od_target_params {
   int32_t rois_per_image;   /* MRCNN_TRAIN_ROIS_PER_IMAGE = R */
   float bbox_stddev[4];     /* BBOX_STD_DEV as float32 */
   int32_t mask_h, mask_w;   /* mask target size (28,28); only read when gt_masks != NULL */
+  int32_t use_mini_mask;    /* != 0: gt_masks are mini masks cropped to their GT box (USE_MINI_MASK, config.py:57-58):
+                               the ROI is re-expressed in the GT box's frame before the crop */
+  int32_t mask_layout_hwg;  /* 0: gt_masks [B,G,Mh,Mw]; != 0: [B,Mh,Mw,G] (batch_gt_masks, data_processor.py:386) */
 } od_target_params;
 
 /* Optional intermediates (data_processor.py:629-652); members may be NULL. */
@@ -205,7 +208,10 @@ size_t od_detection_target_workspace_bytes(int64_t batch, int64_t num_proposals,
  * (data_processor.py:587,:597): the j-th entry of the shuffled list is
  * list[q_j] where q = (p for p in perm if p < len(list)), in perm order.
  * rois [B,R,4] f32, roi_gt_class_ids [B,R] i32, roi_gt_box_deltas [B,R,4] f32.
- * gt_masks [B,G,Mh,Mw] f32 and mask_targets [B,R,mask_h,mask_w] f32 are optional (both NULL or both set). */
+ * gt_masks [B,G,Mh,Mw] (or [B,Mh,Mw,G], see mask_layout_hwg) f32 and mask_targets [B,R,mask_h,mask_w] f32 are optional
+ * (both NULL or both set): target[r] = round(crop_and_resize(gt_mask[assigned GT of r], box_r, [mask_h,mask_w])) for
+ * the sampled positives, zero rows elsewhere (north-star extension: the reference prepares the masks but its mask
+ * head is commented out; semantics of the model it re-writes). */
 int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_class_ids,
                                 const DLTensor* gt_boxes, const DLTensor* perm_pos, const DLTensor* perm_neg,
                                 const od_target_params* params,

@@ -48,7 +48,8 @@ class ProposalDebug(ctypes.Structure):
 
 
 class TargetParams(ctypes.Structure):
-    _fields_ = [("rois_per_image", c_int32), ("bbox_stddev", c_float * 4), ("mask_h", c_int32), ("mask_w", c_int32)]
+    _fields_ = [("rois_per_image", c_int32), ("bbox_stddev", c_float * 4), ("mask_h", c_int32), ("mask_w", c_int32),
+                ("use_mini_mask", c_int32), ("mask_layout_hwg", c_int32)]
 
 
 class TargetDebug(ctypes.Structure):

@@ -78,7 +78,8 @@ detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __r
                         const float4* __restrict__ gt_boxes, const int32_t* __restrict__ perm_pos,
                         const int32_t* __restrict__ perm_neg, int N, int G, int R, float4 stddev,
                         float4* __restrict__ rois, int32_t* __restrict__ roi_cls, float4* __restrict__ roi_deltas,
-                        int32_t* __restrict__ ws_i32, float* __restrict__ ws_f32, TargetDebugPtrs dbg) {
+                        int32_t* __restrict__ ws_i32, float* __restrict__ ws_f32, int32_t* __restrict__ mask_src,
+                        TargetDebugPtrs dbg) {
   extern __shared__ float4 s_gt[];                        // [G] compacted GT boxes
   int32_t* s_gt_src = reinterpret_cast<int32_t*>(s_gt + G);  // [G] original GT row of compacted j
   __shared__ int scratch[40];
@@ -163,6 +164,7 @@ detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __r
       o_cls[t] = 0;
       o_del[t] = z4;
     }
+    if (mask_src) mask_src[(int64_t)b * R + t] = -1;
     if (dbg.sampled_pos) dbg.sampled_pos[(int64_t)b * R + t] = -1;
     if (dbg.sampled_neg) dbg.sampled_neg[(int64_t)b * R + t] = -1;
     if (dbg.gt_assignment) dbg.gt_assignment[(int64_t)b * R + t] = -1;
@@ -187,6 +189,7 @@ detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __r
         o_rois[r] = box;
         o_cls[r] = gcls[g];
         o_del[r] = refine_box(box, gbox[g], stddev);
+        if (mask_src) mask_src[(int64_t)b * R + r] = g;
         if (dbg.sampled_pos) dbg.sampled_pos[(int64_t)b * R + r] = idx;
         if (dbg.gt_assignment) dbg.gt_assignment[(int64_t)b * R + r] = a;
       },
@@ -204,6 +207,56 @@ detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __r
         if (dbg.sampled_neg) dbg.sampled_neg[(int64_t)b * R + r] = idx;
       },
       scratch);
+}
+
+// Mask targets (north-star extension; the reference prepares batch_gt_masks at data_processor.py:386,399 but never
+// consumes them because its mask head is commented out, masking.py:1-67). Semantics restated from the model this
+// file re-writes (matterport Mask_RCNN detection_targets_graph): for every sampled positive ROI
+//   box = roi                                   (full-size masks), or
+//   box = (roi - gt_box.y1x1y1x1) / (gt_h, gt_w, gt_h, gt_w)        (mini masks: ROI in the GT box's frame)
+//   target = round(crop_and_resize(gt_mask[assigned GT], box, [mask_h, mask_w]))   round = half to even
+// rows of non-positive ROIs are zero. One CTA per (roi slot, image); D = 1 channel, so plain 4-byte taps.
+__global__ void __launch_bounds__(256)
+mask_target_kernel(const float4* __restrict__ rois, const float4* __restrict__ gt_boxes, const int32_t* __restrict__ mask_src,
+                   const float* __restrict__ gt_masks, int R, int G, int Mh, int Mw, int hwg_layout, int use_mini_mask,
+                   int mh, int mw, float* __restrict__ targets) {
+  const int r = blockIdx.x, b = blockIdx.y;
+  float* o = targets + ((int64_t)b * R + r) * mh * mw;
+  const int g = mask_src[(int64_t)b * R + r];
+  const int total = mh * mw;
+  if (g < 0) {
+    for (int e = threadIdx.x; e < total; e += blockDim.x) o[e] = 0.0f;
+    return;
+  }
+  float4 box = rois[(int64_t)b * R + r];
+  if (use_mini_mask) {
+    const float4 gt = gt_boxes[(int64_t)b * G + g];
+    const float gt_h = gt.z - gt.x, gt_w = gt.w - gt.y;
+    box = make_float4((box.x - gt.x) / gt_h, (box.y - gt.y) / gt_w, (box.z - gt.x) / gt_h, (box.w - gt.y) / gt_w);
+  }
+  // element (y, x) of GT mask g: [B,G,Mh,Mw] or the reference's [B,Mh,Mw,G]
+  const float* img = gt_masks + (int64_t)b * G * Mh * Mw + (hwg_layout ? (int64_t)g : (int64_t)g * Mh * Mw);
+  const int64_t sy = hwg_layout ? (int64_t)Mw * G : Mw, sx = hwg_layout ? G : 1;
+  const float Hm1 = (float)(Mh - 1), Wm1 = (float)(Mw - 1);
+  const float hs = (mh > 1) ? (box.z - box.x) * Hm1 / (float)(mh - 1) : 0.0f;
+  const float ws = (mw > 1) ? (box.w - box.y) * Wm1 / (float)(mw - 1) : 0.0f;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int y = e / mw, x = e - y * mw;
+    const float in_y = (mh > 1) ? box.x * Hm1 + (float)y * hs : (float)(0.5 * (double)(box.x + box.z) * (double)(Mh - 1));
+    const float in_x = (mw > 1) ? box.y * Wm1 + (float)x * ws : (float)(0.5 * (double)(box.y + box.w) * (double)(Mw - 1));
+    float v = 0.0f;   // extrapolation_value = 0
+    if ((in_y >= 0.0f) && (in_y <= Hm1) && (in_x >= 0.0f) && (in_x <= Wm1)) {
+      const float fy = floorf(in_y), fx = floorf(in_x);
+      const int64_t top = (int64_t)fy, bot = (int64_t)ceilf(in_y), left = (int64_t)fx, right = (int64_t)ceilf(in_x);
+      const float yl = in_y - fy, xl = in_x - fx;
+      const float tl = __ldg(img + top * sy + left * sx), tr = __ldg(img + top * sy + right * sx);
+      const float bl = __ldg(img + bot * sy + left * sx), br = __ldg(img + bot * sy + right * sx);
+      const float t = tl + (tr - tl) * xl;
+      const float bt = bl + (br - bl) * xl;
+      v = t + (bt - t) * yl;
+    }
+    o[e] = rintf(v);
+  }
 }
 
 static int check_opt_nd(const DLTensor* t, const char* name, DType dt, int* dev, std::initializer_list<int64_t> shape) {
@@ -227,6 +280,7 @@ size_t od_detection_target_workspace_bytes(int64_t batch, int64_t num_proposals,
   Workspace w(nullptr, 0);
   w.take<int32_t>((size_t)(batch * 4 * num_proposals));
   w.take<float>((size_t)(batch * num_proposals));
+  w.take<int32_t>((size_t)(batch * 4096));   // GT row of every sampled positive (mask targets), R <= 4096
   return w.off + 256;
 }
 
@@ -256,7 +310,24 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
       roi_gt_class_ids->shape[1] != R || roi_gt_box_deltas->shape[0] != B || roi_gt_box_deltas->shape[1] != R ||
       roi_gt_box_deltas->shape[2] != 4)
     OD_FAIL(OD_ERR_SHAPE, "outputs must be rois [B,R,4], roi_gt_class_ids [B,R], roi_gt_box_deltas [B,R,4]");
-  if (gt_masks || mask_targets) OD_FAIL(OD_ERR_PARAM, "mask targets are not built in this version (pass NULL)");
+  if ((gt_masks == nullptr) != (mask_targets == nullptr)) OD_FAIL(OD_ERR_NULL, "gt_masks and mask_targets go together");
+  int64_t Mh = 0, Mw = 0;
+  if (gt_masks) {
+    OD_CHECK(check_tensor(gt_masks, "gt_masks", F32, 4, true, &dev));
+    OD_CHECK(check_tensor(mask_targets, "mask_targets", F32, 4, true, &dev));
+    if (params->mask_layout_hwg) {
+      Mh = gt_masks->shape[1]; Mw = gt_masks->shape[2];
+      if (gt_masks->shape[0] != B || gt_masks->shape[3] != G) OD_FAIL(OD_ERR_SHAPE, "gt_masks must be [B,Mh,Mw,G]");
+    } else {
+      Mh = gt_masks->shape[2]; Mw = gt_masks->shape[3];
+      if (gt_masks->shape[0] != B || gt_masks->shape[1] != G) OD_FAIL(OD_ERR_SHAPE, "gt_masks must be [B,G,Mh,Mw]");
+    }
+    if (params->mask_h < 1 || params->mask_w < 1 || Mh < 1 || Mw < 1) OD_FAIL(OD_ERR_PARAM, "mask sizes must be positive");
+    if (mask_targets->shape[0] != B || mask_targets->shape[1] != R || mask_targets->shape[2] != params->mask_h ||
+        mask_targets->shape[3] != params->mask_w)
+      OD_FAIL(OD_ERR_SHAPE, "mask_targets must be [B,R,mask_h,mask_w]");
+    if (R > 4096) OD_FAIL(OD_ERR_PARAM, "mask targets support rois_per_image <= 4096");
+  }
   if (G > 8192) OD_FAIL(OD_ERR_PARAM, "at most 8192 GT boxes per image");
   if (N >= (1 << 30)) OD_FAIL(OD_ERR_PARAM, "too many proposals");
   // pos_count + neg_count must fit R for every reachable pos_count (data_processor.py:586-594 arithmetic)
@@ -284,6 +355,7 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
   Workspace w(ws, ws_bytes);
   int32_t* ws_i32 = w.take<int32_t>((size_t)(B * 4 * N));
   float* ws_f32 = w.take<float>((size_t)(B * N));
+  int32_t* mask_src = w.take<int32_t>((size_t)(B * 4096));
   if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, w.off);
   TargetDebugPtrs dp;
   dp.iou = dptr<float>(dbg.iou);
@@ -301,8 +373,16 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
   detection_target_kernel<<<(unsigned)B, kTgtThreads, smem, st>>>(
       dptr<float4>(proposals), dptr<int32_t>(gt_class_ids), dptr<float4>(gt_boxes), dptr<int32_t>(perm_pos),
       dptr<int32_t>(perm_neg), (int)N, (int)G, (int)R, sd, dptr<float4>(rois), dptr<int32_t>(roi_gt_class_ids),
-      dptr<float4>(roi_gt_box_deltas), ws_i32, ws_f32, dp);
+      dptr<float4>(roi_gt_box_deltas), ws_i32, ws_f32, gt_masks ? mask_src : nullptr, dp);
   OD_LAUNCH_CHECK("detection_target_kernel");
+  if (gt_masks) {
+    const dim3 grid((unsigned)R, (unsigned)B);
+    mask_target_kernel<<<grid, 256, 0, st>>>(dptr<float4>(rois), dptr<float4>(gt_boxes), mask_src, dptr<float>(gt_masks), (int)R,
+                                             (int)G, (int)Mh, (int)Mw, params->mask_layout_hwg ? 1 : 0,
+                                             params->use_mini_mask ? 1 : 0, params->mask_h, params->mask_w,
+                                             dptr<float>(mask_targets));
+    OD_LAUNCH_CHECK("mask_target_kernel");
+  }
   return OD_OK;
 }
 

@@ -24,13 +24,17 @@ class BuildDetectionTargets():
     """
 
     def __init__(self, conf, proposals, gt_class_ids, gt_bboxes, DEBUG=False, perm_pos=None, perm_neg=None,
-                 generator=None):
+                 generator=None, gt_masks=None):
         self.train_rois_per_image = conf.MRCNN_TRAIN_ROIS_PER_IMAGE
         self.box_stddev = conf.BBOX_STD_DEV
+        self.mask_shape = tuple(getattr(conf, "MASK_SHAPE", (28, 28)))
+        self.use_mini_mask = bool(getattr(conf, "USE_MINI_MASK", True))
         self.DEBUG = bool(DEBUG)
-        self.build_detection_target(proposals, gt_class_ids, gt_bboxes, perm_pos, perm_neg, generator)
+        self.roi_gt_masks = None
+        self.build_detection_target(proposals, gt_class_ids, gt_bboxes, perm_pos, perm_neg, generator, gt_masks)
 
-    def build_detection_target(self, proposals, gt_class_ids, gt_bboxes, perm_pos=None, perm_neg=None, generator=None):
+    def build_detection_target(self, proposals, gt_class_ids, gt_bboxes, perm_pos=None, perm_neg=None, generator=None,
+                               gt_masks=None):
         L = _lib.lib()
         props = _lib.as_cuda(proposals, torch.float32)
         dev = props.device
@@ -53,7 +57,18 @@ class BuildDetectionTargets():
         rois = torch.empty((B, R, 4), dtype=torch.float32, device=dev)
         rcls = torch.empty((B, R), dtype=torch.int32, device=dev)
         deltas = torch.empty((B, R, 4), dtype=torch.float32, device=dev)
-        params = _lib.TargetParams(R, _stddev4(self.box_stddev), 28, 28)
+        # optional mask targets: gt_masks in the reference's batch layout [B,Mh,Mw,G] ([Mh,Mw,G] per image,
+        # data_processor.py:386,399); MINI_MASK_SHAPE masks cropped to their GT box when conf.USE_MINI_MASK
+        masks = mtargets = None
+        if gt_masks is not None:
+            masks = _lib.as_cuda(gt_masks, torch.float32, dev)
+            if single:
+                masks = masks[None]
+            if masks.dim() != 4 or masks.shape[0] != B or masks.shape[3] != G:
+                raise ValueError("gt_masks must be [batch, mask_h, mask_w, max_gt_objects]")
+            mtargets = torch.empty((B, R, int(self.mask_shape[0]), int(self.mask_shape[1])), dtype=torch.float32, device=dev)
+        params = _lib.TargetParams(R, _stddev4(self.box_stddev), int(self.mask_shape[0]), int(self.mask_shape[1]),
+                                   1 if self.use_mini_mask else 0, 1)
         dl = _lib.DL()
         dbg = _lib.TargetDebug()
         if self.DEBUG:
@@ -70,9 +85,11 @@ class BuildDetectionTargets():
             self.debug_dict = d
         ws = _lib.workspace(L.od_detection_target_workspace_bytes(B, N, G), dev)
         _lib.check(L.od_detection_target_forward(dl(props), dl(cls), dl(gtb), dl(pp), dl(pn), ctypes.byref(params),
-                                                 dl(rois), dl(rcls), dl(deltas), None, None, ctypes.byref(dbg),
+                                                 dl(rois), dl(rcls), dl(deltas), dl(masks), dl(mtargets), ctypes.byref(dbg),
                                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
                    "od_detection_target_forward")
+        if mtargets is not None:
+            self.roi_gt_masks = mtargets[0] if single else mtargets
         if single:
             self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas = rois[0], rcls, deltas[0]   # cls is [1,R] (:627)
         else:
@@ -80,6 +97,11 @@ class BuildDetectionTargets():
 
     def get_target_rois(self):
         return self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas
+
+    def get_target_masks(self):
+        """[R,mask_h,mask_w] ([B,R,...] batched) mask targets of the sampled positives (zero rows elsewhere); only
+        built when ``gt_masks`` was given. North-star extension - the reference never builds them."""
+        return self.roi_gt_masks
 
     def debug_outputs(self):
         return self.debug_dict

@@ -213,6 +213,37 @@ def detection_targets(proposals, gt_class_ids, gt_boxes, perm_pos, perm_neg, roi
     return rois, cls[None], deltas, dbg
 
 
+def mask_targets(rois, gt_class_ids, gt_boxes, gt_masks_hwg, dbg, mask_shape=(28, 28), use_mini_mask=True):
+    """Mask targets of ONE image's sampled positives (north-star extension; **parity unpinned**: absent from the
+    reference, whose mask head is commented out - masking.py:1-67 - restated from the model it re-writes, matterport
+    Mask_RCNN ``detection_targets_graph``): ``round(crop_and_resize(gt_mask[assigned], box, mask_shape))`` with
+    ``box`` = the ROI, re-expressed in the GT box's frame for mini masks. ``rois`` [R,4] and ``dbg`` come from
+    ``detection_targets``; ``gt_masks_hwg`` is [Mh,Mw,G] (batch_gt_masks layout, data_processor.py:386).
+    Returns [R,mh,mw] float32 (zero rows for non-positives)."""
+    rois, gt_boxes = _f32(rois), _f32(gt_boxes)
+    masks = _f32(gt_masks_hwg)
+    R = rois.shape[0]
+    mh, mw = int(mask_shape[0]), int(mask_shape[1])
+    out = np.zeros((R, mh, mw), np.float32)
+    pos_count = int(dbg["counts"][4])
+    if pos_count == 0:
+        return out
+    valid = np.nonzero(_i32(gt_class_ids) != 0)[0]
+    src = valid[dbg["gt_assignment"][:pos_count]]
+    boxes = rois[:pos_count].copy()
+    if use_mini_mask:
+        gt = gt_boxes[src]
+        gt_h = gt[:, 2] - gt[:, 0]
+        gt_w = gt[:, 3] - gt[:, 1]
+        with np.errstate(all="ignore"):
+            boxes = np.stack([(boxes[:, 0] - gt[:, 0]) / gt_h, (boxes[:, 1] - gt[:, 1]) / gt_w,
+                              (boxes[:, 2] - gt[:, 0]) / gt_h, (boxes[:, 3] - gt[:, 1]) / gt_w], axis=1).astype(np.float32)
+    roi_masks = np.ascontiguousarray(np.transpose(masks, (2, 0, 1))[src][..., None])     # [n,Mh,Mw,1]
+    crops = crop_and_resize(roi_masks, boxes, np.arange(pos_count, dtype=np.int32), mh, mw)
+    out[:pos_count] = np.round(crops[..., 0])     # tf.round: half to even
+    return out
+
+
 def detection_forward(proposals, probs, bbox, window_norm, stddev, min_conf: float, nms_thr: float,
                       max_instances: int, debug: bool = False):
     """DetectionLayer.build. Returns detections [B,M,6] (and intermediates if debug)."""

@@ -332,6 +332,40 @@ def test_detection_targets_training_config():
     assert (d["counts"][:, 4] > 0).all() and (d["counts"][:, 4] <= 66).all()
 
 
+@pytest.mark.parametrize("mini", [True, False])
+def test_detection_mask_targets(mini):
+    """28x28 mask-target crops (north-star extension): blob masks, mini-mask and full-image variants, batch 3."""
+    from objectdetection_b200 import BuildDetectionTargets
+    rs = np.random.RandomState(11)
+
+    class C(Conf):
+        USE_MINI_MASK = mini
+    conf = C()
+    B, N, G, M = 3, 600, 20, 56
+    props, cls, gt, pp, pn = _synth.target_inputs(rs, B, N, G, n_pad=100)
+    masks = np.zeros((B, M, M, G), f32)                      # reference layout [B,Mh,Mw,G]
+    yy, xx = np.mgrid[0:M, 0:M]
+    for b in range(B):
+        for g in range(G):
+            cy, cx, r = rs.uniform(10, 46), rs.uniform(10, 46), rs.uniform(6, 25)
+            masks[b, :, :, g] = ((yy - cy) ** 2 + (xx - cx) ** 2 < r * r).astype(f32)
+    t = BuildDetectionTargets(conf, cu(props), cu(cls), cu(gt), DEBUG=True, perm_pos=cu(pp), perm_neg=cu(pn),
+                              gt_masks=cu(masks))
+    got = host(t.get_target_masks())
+    rois = host(t.get_target_rois()[0])
+    R = conf.MRCNN_TRAIN_ROIS_PER_IMAGE
+    assert got.shape == (B, R, 28, 28)
+    n_pos_total = 0
+    for b in range(B):
+        w_rois, _, _, wd = oracle.detection_targets(props[b], cls[b], gt[b], pp[b], pn[b], R, conf.BBOX_STD_DEV)
+        assert_bits(rois[b], w_rois, "rois")
+        want = oracle.mask_targets(w_rois, cls[b], gt[b], masks[b], wd, (28, 28), mini)
+        assert np.array_equal(got[b], want), (b, np.abs(got[b] - want).sum())       # {0,1} values: exact
+        n_pos_total += int(wd["counts"][4])
+        assert not got[b, int(wd["counts"][4]):].any()
+    assert n_pos_total > 0 and got.any() and set(np.unique(got)) <= {0.0, 1.0}
+
+
 def test_detection_targets_edge_cases():
     rs = np.random.RandomState(3)
     conf = ShapesConfig()

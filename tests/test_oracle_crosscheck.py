@@ -276,3 +276,34 @@ def test_unmold_detection_golden(golden):
     assert boxes.dtype == np.int32 and np.array_equal(boxes, golden["unmold_boxes"])
     assert np.array_equal(cls, golden["unmold_class_ids"]) and np.array_equal(scores, golden["unmold_scores"])
     assert boxes.shape[0] < 37
+
+
+def test_mask_targets_oracle_properties():
+    """oracle.mask_targets (parity unpinned, matterport semantics): a full-ones GT mask gives an all-ones target for a
+    ROI inside the GT box; an ROI equal to the GT box reproduces the (bilinearly resampled, rounded) mini mask."""
+    import oracle
+    rs = np.random.RandomState(4)
+    N, G, R, M = 64, 4, 32, 56
+    gt = np.zeros((G, 4), np.float32)
+    gt[:2] = [[0.2, 0.2, 0.6, 0.7], [0.5, 0.1, 0.9, 0.5]]
+    cls = np.array([3, 7, 0, 0], np.int32)
+    props = np.zeros((N, 4), np.float32)
+    props[0] = gt[0]                               # IoU 1 with GT 0
+    props[1] = [0.25, 0.25, 0.55, 0.65]            # inside GT 0, IoU 0.6
+    props[2] = gt[1]
+    props[3:40] = rs.uniform(0, 0.1, (37, 4)).astype(np.float32) + np.array([0, 0, 0.05, 0.05], np.float32)
+    masks = np.zeros((M, M, G), np.float32)
+    masks[:, :, 0] = 1.0
+    masks[10:40, 5:30, 1] = 1.0
+    perm = np.arange(N, dtype=np.int32)
+    rois, rcls, deltas, dbg = oracle.detection_targets(props, cls, gt, perm, perm, R, [0.1, 0.1, 0.2, 0.2])
+    assert int(dbg["counts"][4]) == 3
+    t = oracle.mask_targets(rois, cls, gt, masks, dbg, (28, 28), True)
+    # (an ROI equal to its GT box may lose its last row/column to fp32 rounding: in = y*55/27 can exceed 55 - TF too)
+    assert t.shape == (R, 28, 28) and (t[0][:27, :27] == 1).all() and (t[1] == 1).all() and not t[3:].any()
+    # ROI == GT box 1: the target is the mini mask resampled 56 -> 28 (corner aligned), rounded
+    ys = np.round(np.linspace(0, M - 1, 28)).astype(int)
+    coarse = masks[:, :, 1][np.ix_(ys, ys)]
+    assert np.mean(t[2] == coarse) > 0.95
+    full = oracle.mask_targets(rois, cls, gt, masks, dbg, (28, 28), False)
+    assert full.shape == (R, 28, 28) and (full[0] == 1).all()     # ROI 0 in image coordinates lies inside the mask
