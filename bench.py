@@ -195,6 +195,12 @@ def cpu_setup(B):
     import oracle
     from objectdetection_b200.config import config
     oracle.build()
+    oracle.lib()
+    try:    # libgomp may already be initialised with torchrun's OMP_NUM_THREADS=1
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cpu_threads())
+    except OSError:
+        pass
     conf = config()
     shapes = oracle.get_resnet_stage_shapes(conf.RESNET_STRIDES, conf.IMAGE_SHAPE)
     anchors = oracle.gen_anchors(conf.IMAGE_SHAPE, B, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes,
@@ -213,6 +219,7 @@ def cpu_threads():
 
 def run_cpu_baseline(budget_s=12.0, max_reps=2000):
     """The oracle port on the same workload (batch 2 per step), repeated for ~budget_s seconds."""
+    os.environ.setdefault("OMP_NUM_THREADS", str(cpu_threads()))
     oracle, conf, inp, anchors, win = cpu_setup(B_PER_GPU)
     cpu_step(oracle, conf, inp, anchors, win)      # warm-up (page in, OpenMP pool)
     reps, t0 = 0, time.perf_counter()
@@ -229,6 +236,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host thread it can get
+    os.environ["OMP_NUM_THREADS"] = str(cpu_threads())
     B = B_PER_GPU
     oracle, conf, inp, anchors, win = cpu_setup(B)
     t = time.perf_counter()
@@ -427,32 +436,57 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": roi14_ms}
 
-    # ---- timed region 2: end to end through the same classes, inputs in pinned HOST memory
-    def e2e_step(s_):
-        h, d_ = host_sets[s_], dev_sets[s_]
-        for k_, v in h.items():          # H2D of every input of this step from pinned host memory
-            if isinstance(v, list):
-                for hv, dv in zip(v, d_[k_]):
-                    dv.copy_(hv, non_blocking=True)
-            else:
-                d_[k_].copy_(v, non_blocking=True)
-        d, _ = step(s_)
-        return d[rank * B:(rank + 1) * B].cpu()       # D2H of this rank's detections (synchronises)
+    # ---- timed region 2: end to end, inputs in pinned HOST memory. Every step copies all of its inputs H2D (into the
+    # buffers the layer classes read), runs the step and reads the detections back D2H. The copy of step i+1 runs on
+    # a second stream while step i computes (two input sets = double buffer); everything is inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    ready = [torch.cuda.Event() for _ in range(NSETS)]      # H2D of set s finished
+    consumed = [torch.cuda.Event() for _ in range(NSETS)]   # compute on set s finished (buffers may be overwritten)
+    det_host = [torch.empty((B, conf.DETECTION_POST_NMS_INSTANCES, 6), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
 
-    for i in range(2):
-        e2e_step(i % NSETS)
-    e2e_steps = max(3, min(args.steps, 20))
+    def h2d(s_):
+        h, d_ = host_sets[s_], dev_sets[s_]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s_])
+            for k_, v in h.items():
+                if isinstance(v, list):
+                    for hv, dv in zip(v, d_[k_]):
+                        dv.copy_(hv, non_blocking=True)
+                else:
+                    d_[k_].copy_(v, non_blocking=True)
+            ready[s_].record(copy_stream)
+
+    def e2e_loop(n):
+        for s_ in range(NSETS):
+            consumed[s_].record(main_stream)
+        h2d(0)
+        out = None
+        for i in range(n):
+            s_ = i % NSETS
+            if i + 1 < n:
+                h2d((i + 1) % NSETS)                 # overlaps with this step's kernels
+            main_stream.wait_event(ready[s_])
+            d, _ = step(s_)
+            det_host[s_].copy_(d[rank * B:(rank + 1) * B], non_blocking=True)   # D2H of this rank's detections
+            consumed[s_].record(main_stream)
+            main_stream.synchronize()                # the caller reads the result of every step
+            out = det_host[s_]
+        return out
+
+    e2e_loop(3)
+    e2e_steps = max(4, min(args.steps, 40))
     barrier(); torch.cuda.synchronize()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
-    for i in range(e2e_steps):
-        out = e2e_step(i % NSETS)
+    out = e2e_loop(e2e_steps)
     ev3.record()
     torch.cuda.synchronize(); barrier()
     e2e_ms = max_over_ranks(ev2.elapsed_time(ev3))
     d2h_bytes = out.numel() * 4
     e2e = {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
-           "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps}
+           "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           "note": "H2D of step i+1 overlaps the kernels of step i (2 streams); PCIe-bound"}
 
     # ---- stand-alone ROIAlign on the SURVEY §8d ROI recipe (seed 1234), L2 flushed between launches
     standalone = {}

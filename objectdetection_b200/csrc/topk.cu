@@ -3,13 +3,13 @@
 // detection.py:221; also the score ordering inside tf.image.non_max_suppression.
 //
 // Every element gets a unique orderable key  c = (score_key << ib) | (2^ib - 1 - index),  ib = ceil(log2(cols)),
-// so "k largest by (value desc, index asc)" is "k largest c". A most-significant-digit radix select
-// (12-bit digits) narrows a per-row prefix until the bucket that still straddles the k-th element is
-// fully taken (`done`), which for distinct scores happens after 2-3 digits; later passes exit at once.
-// Passes are one launch each: per-CTA shared-memory histograms -> global histogram (atomics) -> the
-// last CTA of the row (ticket counter) scans the 4096 buckets and advances the row's state.
-// Then one collect pass compacts the k winners and a single-CTA bitonic sort (shared memory, up to
-// 16384 keys; global-memory bitonic above that) orders them.
+// so "k largest by (value desc, index asc)" is "k largest c". Selection is a most-significant-digit radix select
+// (12-bit digits) in three launches: a histogram pass over the leading digit (per-CTA shared-memory histograms ->
+// global atomics -> the last CTA of the row, found with a ticket counter, scans the 4096 buckets), a split pass
+// (keys above the threshold bucket are winners, keys inside it become candidates) and a one-CTA-per-row tail
+// that resolves the remaining digits over the candidates in shared memory. The k winners are then ordered by a
+// rank sort spread over the whole GPU (k <= 8192), a single-CTA shared-memory bitonic sort (k <= 16384) or a
+// global-memory bitonic sort above that.
 #include "topk.cuh"
 
 namespace od {
@@ -27,8 +27,8 @@ struct __align__(16) SelState {
   int32_t k_rem;              // how many to take among the elements matching `prefix`
   int32_t done;               // every element matching `prefix` is selected
   uint32_t blocks_done;       // ticket counter for last-CTA detection
-  uint32_t out_count;         // slot counter of the collect pass
-  uint32_t pad;
+  uint32_t out_count;         // slot counter of the winners buffer
+  uint32_t cand_count;        // number of keys in the threshold bucket of the first digit (may exceed the buffer)
 };
 
 __device__ __forceinline__ unsigned long long topk_key(float s, uint32_t idx, int ib) {
@@ -177,6 +177,151 @@ topk_sort_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_st
   }
 }
 
+// ---- select = 3 launches: (1) topk_hist_kernel on the leading 12-bit digit -> the bucket b that holds the k-th key;
+// (2) topk_split_kernel re-reads the row once: keys above b are winners (-> buf), keys in b are candidates
+// (-> cand); (3) topk_tail_kernel, one CTA per row, resolves the remaining digits over the (few thousand)
+// candidates with shared-memory histograms and appends the winners among them. If the candidates overflow their
+// buffer (heavily clustered or tied scores), the tail falls back to scanning the original row: slow, still exact.
+constexpr int kTailThreads = 1024;
+
+__global__ void __launch_bounds__(kSelThreads)
+topk_split_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
+                  int64_t buf_stride, int64_t cand_cap, SelState* __restrict__ states, unsigned long long* __restrict__ buf,
+                  unsigned long long* __restrict__ cand) {
+  const int row = blockIdx.y;
+  SelState* st = states + row;
+  const int shift = st->shift;
+  const unsigned long long bucket = st->prefix >> shift;
+  const int take_bucket = st->done;   // the whole bucket is selected: no candidates left to resolve
+  const float* srow = scores + (int64_t)row * row_stride;
+  unsigned long long* out = buf + (int64_t)row * buf_stride;
+  unsigned long long* cnd = cand + (int64_t)row * cand_cap;
+  const RowChunk ch = row_chunk(cols);
+  const int lane = threadIdx.x & 31;
+  for (int64_t i0 = ch.begin; i0 < ch.end; i0 += kSelThreads) {
+    const int64_t i = i0 + threadIdx.x;
+    unsigned long long c = 0;
+    bool win = false, cd = false;
+    if (i < ch.end) {
+      c = topk_key(srow[i * col_stride], (uint32_t)i, ib);
+      const unsigned long long d = c >> shift;
+      win = (d > bucket) || (take_bucket && d == bucket);
+      cd = !take_bucket && (d == bucket);
+    }
+    const uint32_t bw = __ballot_sync(0xffffffffu, win);
+    if (bw) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&st->out_count, (uint32_t)__popc(bw));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (win) out[base + __popc(bw & ((1u << lane) - 1u))] = c;
+    }
+    const uint32_t bc = __ballot_sync(0xffffffffu, cd);
+    if (bc) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&st->cand_count, (uint32_t)__popc(bc));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const uint32_t slot = base + __popc(bc & ((1u << lane) - 1u));
+      if (cd && slot < (uint32_t)cand_cap) cnd[slot] = c;   // beyond the capacity only the count grows (overflow)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTailThreads)
+topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
+                 int64_t buf_stride, int64_t cand_cap, SelState* __restrict__ states, unsigned long long* __restrict__ buf,
+                 const unsigned long long* __restrict__ cand) {
+  __shared__ uint32_t sh[kBins];
+  __shared__ uint32_t warp_sums[kTailThreads / 32];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_krem, s_done;
+  const int row = blockIdx.x;
+  SelState* st = states + row;
+  if (st->done) return;   // the split pass already emitted everything
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int shift1 = st->shift;
+  unsigned long long prefix = st->prefix;
+  int k_rem = st->k_rem, done = 0, shift = shift1;
+  const uint32_t n_cand = st->cand_count;
+  const bool overflow = n_cand > (uint32_t)cand_cap;
+  const int64_t n_src = overflow ? cols : (int64_t)n_cand;
+  const float* srow = scores + (int64_t)row * row_stride;
+  const unsigned long long* cnd = cand + (int64_t)row * cand_cap;
+  auto key_at = [&](int64_t i) -> unsigned long long {
+    return overflow ? topk_key(srow[i * col_stride], (uint32_t)i, ib) : cnd[i];
+  };
+  while (shift > 0 && !done) {
+    const int bits = shift >= kDigitBits ? kDigitBits : shift;
+    const int new_shift = shift - bits;
+    const uint32_t mask = (1u << bits) - 1u;
+    for (int b = tid; b < kBins; b += kTailThreads) sh[b] = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < n_src; i += kTailThreads) {
+      const unsigned long long c = key_at(i);
+      if ((c >> shift) == (prefix >> shift)) atomicAdd(&sh[(uint32_t)(c >> new_shift) & mask], 1u);
+    }
+    __syncthreads();
+    // bucket holding the k_rem-th largest key; thread 0 owns the highest buckets
+    constexpr int kPer = kBins / kTailThreads;
+    const int top_bin = kBins - 1 - tid * kPer;
+    uint32_t local[kPer];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      local[q] = sh[top_bin - q];
+      sum += local[q];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0;
+    for (int w = 0; w < warp; ++w) warp_off += warp_sums[w];
+    const uint32_t before = warp_off + incl - sum;
+    if ((uint32_t)k_rem > before && (uint32_t)k_rem <= before + sum) {
+      uint32_t cum = before;
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        if ((uint32_t)k_rem > cum && (uint32_t)k_rem <= cum + local[q]) {
+          const int new_k = k_rem - (int)cum;
+          s_prefix = prefix | ((unsigned long long)(top_bin - q) << new_shift);
+          s_krem = new_k;
+          s_done = ((int)local[q] == new_k);
+        }
+        cum += local[q];
+      }
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    k_rem = s_krem;
+    done = s_done;
+    shift = new_shift;
+    __syncthreads();
+  }
+  // winners among the candidates: same leading digit, and (c >> shift) >= (prefix >> shift)
+  const unsigned long long thr = prefix >> shift;
+  unsigned long long* out = buf + (int64_t)row * buf_stride;
+  for (int64_t i0 = 0; i0 < n_src; i0 += kTailThreads) {
+    const int64_t i = i0 + tid;
+    unsigned long long c = 0;
+    bool sel = false;
+    if (i < n_src) {
+      c = key_at(i);
+      sel = ((c >> shift1) == (prefix >> shift1)) && ((c >> shift) >= thr);
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, sel);
+    if (ballot) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&st->out_count, (uint32_t)__popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (sel) out[base + __popc(ballot & ((1u << lane) - 1u))] = c;
+    }
+  }
+}
+
 // Rank sort + emit: keys are unique, so the position of a key in descending order is the number of keys greater
 // than it. grid (ceil(k/16), rows); a CTA owns 16 keys, its 16 thread groups each count over a 16th of every
 // 1024-key tile staged in shared memory (k^2 compares spread over the whole GPU instead of one CTA's bitonic
@@ -280,11 +425,19 @@ static int blocks_per_row(int64_t rows, int64_t cols) {
   return (int)(b < 1 ? 1 : b);
 }
 
+// Candidate buffer entries per row for the split/tail select.
+static int64_t cand_capacity(int64_t cols, int64_t k) {
+  int64_t cap = 4 * next_pow2(k > 0 ? k : 1);
+  if (cap < 16384) cap = 16384;
+  return cap < cols ? cap : cols;
+}
+
 size_t topk_workspace_bytes(int64_t rows, int64_t cols, int64_t k) {
   Workspace w(nullptr, 0);
   w.take<SelState>((size_t)rows);
   w.take<uint32_t>((size_t)rows * kBins);
   w.take<unsigned long long>((size_t)rows * (size_t)next_pow2(k > 0 ? k : 1));
+  w.take<unsigned long long>((size_t)rows * (size_t)cand_capacity(cols, k));
   return w.off + 256;
 }
 
@@ -299,6 +452,8 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
   SelState* states = w.take<SelState>((size_t)rows);
   uint32_t* hist = w.take<uint32_t>((size_t)rows * kBins);
   unsigned long long* buf = w.take<unsigned long long>((size_t)rows * (size_t)n_pow2);
+  const int64_t cap = cand_capacity(cols, k);
+  unsigned long long* cand = w.take<unsigned long long>((size_t)rows * (size_t)cap);
   if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "top-k workspace %zu < %zu bytes", ws_bytes, w.off);
   const int ib = index_bits(cols);
   const int total_bits = 32 + ib;
@@ -306,21 +461,19 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
   // state + histogram are contiguous at the head of the workspace
   OD_CUDA(cudaMemsetAsync(states, 0, (size_t)((char*)buf - (char*)states), st));
   const int take_all = (k == cols);
-  if (!take_all) {
-    int shift = total_bits;
-    int first = 1;
-    while (shift > 0) {
-      const int bits = shift >= kDigitBits ? kDigitBits : shift;
-      shift -= bits;
-      topk_hist_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, shift, bits, first, (int)k,
-                                                     states, hist);
-      count_launches(1);
-      first = 0;
-    }
-    OD_LAUNCH_CHECK_NC("topk_hist_kernel");
+  if (take_all) {
+    topk_collect_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, 1, n_pow2, states, buf);
+    OD_LAUNCH_CHECK("topk_collect_kernel");
+  } else {
+    const int bits = total_bits >= kDigitBits ? kDigitBits : total_bits;
+    topk_hist_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, total_bits - bits, bits, 1, (int)k,
+                                                   states, hist);
+    OD_LAUNCH_CHECK("topk_hist_kernel");
+    topk_split_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, n_pow2, cap, states, buf, cand);
+    OD_LAUNCH_CHECK("topk_split_kernel");
+    topk_tail_kernel<<<(unsigned)rows, kTailThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, n_pow2, cap, states, buf, cand);
+    OD_LAUNCH_CHECK("topk_tail_kernel");
   }
-  topk_collect_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, take_all, n_pow2, states, buf);
-  OD_LAUNCH_CHECK("topk_collect_kernel");
   if (k <= kRankSortMaxK) {
     const dim3 g((unsigned)((k + kRankMine - 1) / kRankMine), (unsigned)rows);
     topk_rank_emit_kernel<<<g, kRankThreads, 0, st>>>(buf, n_pow2, (int)k, ib, scores, row_stride, col_stride, idx_out, val_out);

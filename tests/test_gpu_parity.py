@@ -94,6 +94,22 @@ def test_topk_all_equal_scores():
     assert np.array_equal(host(i), np.tile(np.arange(777, dtype=np.int32), (2, 1)))
 
 
+def test_topk_candidate_overflow_and_clustered_scores():
+    """The split/tail select keeps the keys of the threshold bucket in a bounded candidate buffer; clustered or tied
+    scores overflow it and the tail falls back to the original row. Both must stay exact (ties -> lower index)."""
+    from objectdetection_b200.proposals import top_k
+    s = np.full((2, 100000), 0.5, f32)                      # one bucket holds everything: 100000 > capacity
+    s[1, ::3] = 0.75
+    v, i = top_k(cu(s), 1000)
+    wv, wi = oracle.topk(s, 1000)
+    assert np.array_equal(host(i), wi) and np.array_equal(host(v), wv)
+    rs = np.random.RandomState(8)
+    c = (0.9 + 0.0001 * rs.random_sample((3, 200000))).astype(f32)   # same exponent + top mantissa bits: one big bucket
+    v, i = top_k(cu(c), 6000)
+    wv, wi = oracle.topk(c, 6000)
+    assert np.array_equal(host(i), wi) and np.array_equal(host(v), wv)
+
+
 # ------------------------------------------------------------------ decode / clip
 def test_apply_box_deltas_and_clip():
     from objectdetection_b200.proposals import apply_box_deltas, clip_boxes_to_01
