@@ -26,7 +26,7 @@ struct __align__(16) SelState {
   int32_t shift;              // number of undetermined low bits
   int32_t k_rem;              // how many to take among the elements matching `prefix`
   int32_t done;               // every element matching `prefix` is selected
-  uint32_t blocks_done;       // ticket counter for last-CTA detection
+  uint32_t reserved;
   uint32_t out_count;         // slot counter of the winners buffer
   uint32_t cand_count;        // number of keys in the threshold bucket of the first digit (may exceed the buffer)
 };
@@ -44,86 +44,6 @@ __device__ __forceinline__ RowChunk row_chunk(int64_t cols) {
   c.begin = per * blockIdx.x;
   c.end = min(cols, c.begin + per);
   return c;
-}
-
-__global__ void __launch_bounds__(kSelThreads)
-topk_hist_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
-                 int shift, int bits, int first, int k, SelState* __restrict__ states, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t sh[kBins];
-  __shared__ uint32_t warp_sums[kSelThreads / 32];
-  __shared__ int is_last;
-  const int row = blockIdx.y;
-  SelState* st = states + row;
-  const int done = first ? 0 : st->done;
-  if (done) return;
-  const unsigned long long prefix = first ? 0ull : st->prefix;
-  const int k_rem = first ? k : st->k_rem;
-  const int total_bits = 32 + ib;
-  const int hi_shift = shift + bits;
-  const uint32_t mask = (1u << bits) - 1u;
-  for (int b = threadIdx.x; b < kBins; b += kSelThreads) sh[b] = 0;
-  __syncthreads();
-  const float* srow = scores + (int64_t)row * row_stride;
-  const RowChunk ch = row_chunk(cols);
-  for (int64_t i = ch.begin + threadIdx.x; i < ch.end; i += kSelThreads) {
-    const unsigned long long c = topk_key(srow[i * col_stride], (uint32_t)i, ib);
-    if (hi_shift >= total_bits || (c >> hi_shift) == (prefix >> hi_shift)) atomicAdd(&sh[(uint32_t)(c >> shift) & mask], 1u);
-  }
-  __syncthreads();
-  uint32_t* hrow = hist + (int64_t)row * kBins;
-  for (int b = threadIdx.x; b < kBins; b += kSelThreads) {
-    const uint32_t v = sh[b];
-    if (v) atomicAdd(&hrow[b], v);
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t t = atomicAdd(&st->blocks_done, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // ---- last CTA of this row: find the bucket holding the k_rem-th largest key
-  constexpr int kPer = kBins / kSelThreads;  // buckets per thread, walked from the top
-  const int top_bin = kBins - 1 - threadIdx.x * kPer;
-  uint32_t local[kPer];
-  uint32_t sum = 0;
-#pragma unroll
-  for (int q = 0; q < kPer; ++q) {
-    local[q] = __ldcg(&hrow[top_bin - q]);
-    hrow[top_bin - q] = 0;  // ready for the next pass
-    sum += local[q];
-  }
-  // inclusive scan of `sum` over threads (thread 0 owns the highest buckets)
-  uint32_t incl = sum;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  uint32_t warp_off = 0;
-  for (int w = 0; w < warp; ++w) warp_off += warp_sums[w];
-  const uint32_t before = warp_off + incl - sum;  // elements in buckets above this thread's range
-  if ((uint32_t)k_rem > before && (uint32_t)k_rem <= before + sum) {
-    uint32_t cum = before;
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      if ((uint32_t)k_rem > cum && (uint32_t)k_rem <= cum + local[q]) {
-        const int d = top_bin - q;
-        const int new_k = k_rem - (int)cum;
-        st->prefix = prefix | ((unsigned long long)d << shift);
-        st->shift = shift;
-        st->k_rem = new_k;
-        st->done = ((int)local[q] == new_k);
-      }
-      cum += local[q];
-    }
-  }
-  if (threadIdx.x == 0) st->blocks_done = 0;
 }
 
 // Selected <=> (c >> shift) >= (prefix >> shift). Exactly k elements qualify.
@@ -177,6 +97,107 @@ topk_sort_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_st
   }
 }
 
+// First-digit histogram only: per-CTA shared-memory histogram of the leading `bits` bits -> global histogram.
+// The consumers (split / tail) locate the threshold bucket themselves, so there is no last-CTA tail here.
+__global__ void __launch_bounds__(kSelThreads)
+topk_hist1_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
+                  int shift, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kBins];
+  const int row = blockIdx.y;
+  for (int b = threadIdx.x; b < kBins; b += kSelThreads) sh[b] = 0;
+  __syncthreads();
+  const float* srow = scores + (int64_t)row * row_stride;
+  const RowChunk ch = row_chunk(cols);
+  for (int64_t i0 = ch.begin + threadIdx.x; i0 < ch.end; i0 += 4 * kSelThreads) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * kSelThreads;
+      v[u] = (i < ch.end) ? __ldg(&srow[i * col_stride]) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * kSelThreads;
+      if (i < ch.end) atomicAdd(&sh[(uint32_t)(topk_key(v[u], (uint32_t)i, ib) >> shift)], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* hrow = hist + (int64_t)row * kBins;
+  for (int b = threadIdx.x; b < kBins; b += kSelThreads) {
+    const uint32_t v = sh[b];
+    if (v) atomicAdd(&hrow[b], v);
+  }
+}
+
+// Block-wide: bucket of a 4096-bin histogram (global or shared) that holds the k-th largest key, scanning from the
+// top; returns through shared memory (bucket, keys to take inside it, whether that is the whole bucket).
+struct BucketPick {
+  int bucket, k_rem, done;
+};
+template <int THREADS, typename Load>
+__device__ __forceinline__ BucketPick pick_bucket(Load load_bin, int k, uint32_t* warp_sums, BucketPick* s_pick) {
+  constexpr int kPer = kBins / THREADS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int top_bin = kBins - 1 - tid * kPer;   // thread 0 owns the highest buckets
+  uint32_t local[kPer];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    local[q] = load_bin(top_bin - q);
+    sum += local[q];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t warp_off = 0;
+  for (int w = 0; w < warp; ++w) warp_off += warp_sums[w];
+  const uint32_t before = warp_off + incl - sum;
+  if ((uint32_t)k > before && (uint32_t)k <= before + sum) {
+    uint32_t cum = before;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      if ((uint32_t)k > cum && (uint32_t)k <= cum + local[q]) {
+        s_pick->bucket = top_bin - q;
+        s_pick->k_rem = k - (int)cum;
+        s_pick->done = ((int)local[q] == k - (int)cum);
+      }
+      cum += local[q];
+    }
+  }
+  __syncthreads();
+  const BucketPick r = *s_pick;
+  __syncthreads();
+  return r;
+}
+
+// Block-wide exclusive prefix sum of one int per thread; returns (offset of this thread, block total).
+template <int THREADS>
+__device__ __forceinline__ int2 block_exclusive_scan(int v, uint32_t* warp_sums) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = (uint32_t)incl;
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) {
+    const int c = (int)warp_sums[w];
+    if (w < warp) off += c;
+    total += c;
+  }
+  __syncthreads();
+  return make_int2(off + incl - v, total);
+}
+
 // ---- select = 3 launches: (1) topk_hist_kernel on the leading 12-bit digit -> the bucket b that holds the k-th key;
 // (2) topk_split_kernel re-reads the row once: keys above b are winners (-> buf), keys in b are candidates
 // (-> cand); (3) topk_tail_kernel, one CTA per row, resolves the remaining digits over the (few thousand)
@@ -184,45 +205,65 @@ topk_sort_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_st
 // buffer (heavily clustered or tied scores), the tail falls back to scanning the original row: slow, still exact.
 constexpr int kTailThreads = 1024;
 
+constexpr int kSplitPer = 8;   // keys per thread and tile: one atomic per CTA, tile and list instead of one per warp
 __global__ void __launch_bounds__(kSelThreads)
-topk_split_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
-                  int64_t buf_stride, int64_t cand_cap, SelState* __restrict__ states, unsigned long long* __restrict__ buf,
-                  unsigned long long* __restrict__ cand) {
+topk_split_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib, int k,
+                  int shift, int64_t buf_stride, int64_t cand_cap, const uint32_t* __restrict__ hist,
+                  SelState* __restrict__ states, unsigned long long* __restrict__ buf, unsigned long long* __restrict__ cand) {
+  __shared__ uint32_t warp_sums[kSelThreads / 32];
+  __shared__ BucketPick s_pick;
+  __shared__ uint32_t s_base[2];
   const int row = blockIdx.y;
   SelState* st = states + row;
-  const int shift = st->shift;
-  const unsigned long long bucket = st->prefix >> shift;
-  const int take_bucket = st->done;   // the whole bucket is selected: no candidates left to resolve
+  const uint32_t* hrow = hist + (int64_t)row * kBins;
+  const BucketPick pk = pick_bucket<kSelThreads>([&](int b) { return __ldg(&hrow[b]); }, k, warp_sums, &s_pick);
+  const unsigned long long bucket = (unsigned long long)pk.bucket;
+  const int take_bucket = pk.done;   // the whole bucket is selected: no candidates left to resolve
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // for the tail kernel
+    st->prefix = bucket << shift;
+    st->shift = shift;
+    st->k_rem = pk.k_rem;
+    st->done = pk.done;
+  }
   const float* srow = scores + (int64_t)row * row_stride;
   unsigned long long* out = buf + (int64_t)row * buf_stride;
   unsigned long long* cnd = cand + (int64_t)row * cand_cap;
   const RowChunk ch = row_chunk(cols);
-  const int lane = threadIdx.x & 31;
-  for (int64_t i0 = ch.begin; i0 < ch.end; i0 += kSelThreads) {
-    const int64_t i = i0 + threadIdx.x;
-    unsigned long long c = 0;
-    bool win = false, cd = false;
-    if (i < ch.end) {
-      c = topk_key(srow[i * col_stride], (uint32_t)i, ib);
-      const unsigned long long d = c >> shift;
-      win = (d > bucket) || (take_bucket && d == bucket);
-      cd = !take_bucket && (d == bucket);
+  for (int64_t t0 = ch.begin; t0 < ch.end; t0 += (int64_t)kSplitPer * kSelThreads) {
+    float v[kSplitPer];
+#pragma unroll
+    for (int u = 0; u < kSplitPer; ++u) {
+      const int64_t i = t0 + u * kSelThreads + threadIdx.x;
+      v[u] = (i < ch.end) ? __ldg(&srow[i * col_stride]) : 0.0f;
     }
-    const uint32_t bw = __ballot_sync(0xffffffffu, win);
-    if (bw) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&st->out_count, (uint32_t)__popc(bw));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (win) out[base + __popc(bw & ((1u << lane) - 1u))] = c;
+    uint32_t wmask = 0, cmask = 0;
+#pragma unroll
+    for (int u = 0; u < kSplitPer; ++u) {
+      const int64_t i = t0 + u * kSelThreads + threadIdx.x;
+      if (i < ch.end) {
+        const unsigned long long d = topk_key(v[u], (uint32_t)i, ib) >> shift;
+        if ((d > bucket) || (take_bucket && d == bucket)) wmask |= 1u << u;
+        else if (d == bucket) cmask |= 1u << u;
+      }
     }
-    const uint32_t bc = __ballot_sync(0xffffffffu, cd);
-    if (bc) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&st->cand_count, (uint32_t)__popc(bc));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const uint32_t slot = base + __popc(bc & ((1u << lane) - 1u));
-      if (cd && slot < (uint32_t)cand_cap) cnd[slot] = c;   // beyond the capacity only the count grows (overflow)
+    const int2 ws = block_exclusive_scan<kSelThreads>(__popc(wmask), warp_sums);
+    const int2 cs = block_exclusive_scan<kSelThreads>(__popc(cmask), warp_sums);
+    if (threadIdx.x == 0) {
+      s_base[0] = ws.y ? atomicAdd(&st->out_count, (uint32_t)ws.y) : 0u;
+      s_base[1] = cs.y ? atomicAdd(&st->cand_count, (uint32_t)cs.y) : 0u;
     }
+    __syncthreads();
+    uint32_t wpos = s_base[0] + (uint32_t)ws.x, cpos = s_base[1] + (uint32_t)cs.x;
+#pragma unroll
+    for (int u = 0; u < kSplitPer; ++u) {
+      const int64_t i = t0 + u * kSelThreads + threadIdx.x;
+      if ((wmask >> u) & 1u) out[wpos++] = topk_key(v[u], (uint32_t)i, ib);
+      if ((cmask >> u) & 1u) {
+        if (cpos < (uint32_t)cand_cap) cnd[cpos] = topk_key(v[u], (uint32_t)i, ib);   // beyond the capacity only the count grows
+        ++cpos;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -232,12 +273,11 @@ topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_str
                  const unsigned long long* __restrict__ cand) {
   __shared__ uint32_t sh[kBins];
   __shared__ uint32_t warp_sums[kTailThreads / 32];
-  __shared__ unsigned long long s_prefix;
-  __shared__ int s_krem, s_done;
+  __shared__ BucketPick s_pick;
   const int row = blockIdx.x;
   SelState* st = states + row;
   if (st->done) return;   // the split pass already emitted everything
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int shift1 = st->shift;
   unsigned long long prefix = st->prefix;
   int k_rem = st->k_rem, done = 0, shift = shift1;
@@ -260,50 +300,17 @@ topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_str
       if ((c >> shift) == (prefix >> shift)) atomicAdd(&sh[(uint32_t)(c >> new_shift) & mask], 1u);
     }
     __syncthreads();
-    // bucket holding the k_rem-th largest key; thread 0 owns the highest buckets
-    constexpr int kPer = kBins / kTailThreads;
-    const int top_bin = kBins - 1 - tid * kPer;
-    uint32_t local[kPer];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      local[q] = sh[top_bin - q];
-      sum += local[q];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    uint32_t warp_off = 0;
-    for (int w = 0; w < warp; ++w) warp_off += warp_sums[w];
-    const uint32_t before = warp_off + incl - sum;
-    if ((uint32_t)k_rem > before && (uint32_t)k_rem <= before + sum) {
-      uint32_t cum = before;
-#pragma unroll
-      for (int q = 0; q < kPer; ++q) {
-        if ((uint32_t)k_rem > cum && (uint32_t)k_rem <= cum + local[q]) {
-          const int new_k = k_rem - (int)cum;
-          s_prefix = prefix | ((unsigned long long)(top_bin - q) << new_shift);
-          s_krem = new_k;
-          s_done = ((int)local[q] == new_k);
-        }
-        cum += local[q];
-      }
-    }
-    __syncthreads();
-    prefix = s_prefix;
-    k_rem = s_krem;
-    done = s_done;
+    const BucketPick pk = pick_bucket<kTailThreads>([&](int b) { return sh[b]; }, k_rem, warp_sums, &s_pick);
+    prefix |= (unsigned long long)pk.bucket << new_shift;
+    k_rem = pk.k_rem;
+    done = pk.done;
     shift = new_shift;
-    __syncthreads();
   }
-  // winners among the candidates: same leading digit, and (c >> shift) >= (prefix >> shift)
+  // winners among the candidates: same leading digit, and (c >> shift) >= (prefix >> shift). This CTA is the only
+  // writer of the row by now (the split kernel has finished), so the output offset is a plain running count.
   const unsigned long long thr = prefix >> shift;
   unsigned long long* out = buf + (int64_t)row * buf_stride;
+  uint32_t base = st->out_count;
   for (int64_t i0 = 0; i0 < n_src; i0 += kTailThreads) {
     const int64_t i = i0 + tid;
     unsigned long long c = 0;
@@ -312,13 +319,9 @@ topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_str
       c = key_at(i);
       sel = ((c >> shift1) == (prefix >> shift1)) && ((c >> shift) >= thr);
     }
-    const uint32_t ballot = __ballot_sync(0xffffffffu, sel);
-    if (ballot) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&st->out_count, (uint32_t)__popc(ballot));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (sel) out[base + __popc(ballot & ((1u << lane) - 1u))] = c;
-    }
+    const int2 sc = block_exclusive_scan<kTailThreads>(sel ? 1 : 0, warp_sums);
+    if (sel) out[base + (uint32_t)sc.x] = c;
+    base += (uint32_t)sc.y;
   }
 }
 
@@ -465,11 +468,11 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
     topk_collect_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, 1, n_pow2, states, buf);
     OD_LAUNCH_CHECK("topk_collect_kernel");
   } else {
-    const int bits = total_bits >= kDigitBits ? kDigitBits : total_bits;
-    topk_hist_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, total_bits - bits, bits, 1, (int)k,
-                                                   states, hist);
-    OD_LAUNCH_CHECK("topk_hist_kernel");
-    topk_split_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, n_pow2, cap, states, buf, cand);
+    const int shift1 = total_bits - kDigitBits;   // total_bits >= 33
+    topk_hist1_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, shift1, hist);
+    OD_LAUNCH_CHECK("topk_hist1_kernel");
+    topk_split_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, (int)k, shift1, n_pow2, cap, hist,
+                                                    states, buf, cand);
     OD_LAUNCH_CHECK("topk_split_kernel");
     topk_tail_kernel<<<(unsigned)rows, kTailThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, n_pow2, cap, states, buf, cand);
     OD_LAUNCH_CHECK("topk_tail_kernel");
