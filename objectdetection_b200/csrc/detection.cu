@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256)
 det_prepare_kernel(const float4* __restrict__ proposals, const float* __restrict__ probs,
                    const float4* __restrict__ bbox, const float4* __restrict__ window, int N, int C, int n_pow2,
                    float4 stddev, float min_conf, int32_t* __restrict__ cls_out, float* __restrict__ score_out,
-                   float4* __restrict__ clipped_out, unsigned long long* __restrict__ keys, DetDebugPtrs dbg) {
+                   float4* __restrict__ clipped_out, unsigned long long* __restrict__ keys,
+                   int32_t* __restrict__ num_valid, DetDebugPtrs dbg) {
   const int lane = threadIdx.x & 31;
   const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int b = blockIdx.y;
@@ -37,6 +38,7 @@ det_prepare_kernel(const float4* __restrict__ proposals, const float* __restrict
     if (lane == 0) keys[(int64_t)b * n_pow2 + slot] = 0ull;
     return;
   }
+  if (slot == 0 && lane == 0) num_valid[b] = 0;   // det_rank_gather_kernel raises it with atomicMax
   const int n = (int)slot;
   const int64_t r = (int64_t)b * N + n;
   const float* p = probs + r * C;
@@ -77,13 +79,55 @@ det_prepare_kernel(const float4* __restrict__ proposals, const float* __restrict
   keys[(int64_t)b * n_pow2 + n] =
       keep ? (((unsigned long long)(C - arg) << 48) | ((unsigned long long)score_key(score) << 16) |
               (unsigned long long)(0xFFFFu - (uint32_t)n))
-           : 0ull;
+           : (unsigned long long)(0xFFFFu - (uint32_t)n);   // dropped ROIs: class field 0, still unique (rank sort)
   if (dbg.class_ids) dbg.class_ids[r] = arg;
   if (dbg.class_scores) dbg.class_scores[r] = score;
   if (dbg.bbox_delta) dbg.bbox_delta[r] = d;
   if (dbg.refined) dbg.refined[r] = ref;
   if (dbg.clipped) dbg.clipped[r] = cl;
   if (dbg.keep_mask) dbg.keep_mask[r] = keep ? 1 : 0;
+}
+
+// Rank sort of the N keys of one image fused with the gather: keys are unique, the sorted position of a key is the
+// number of keys greater than it. grid (ceil(N/64), B); a CTA owns 64 keys, its 4 thread groups each count over a
+// quarter of every 1024-key tile in shared memory. Writes the sorted key, box and class of position `rank`, and
+// num_valid = number of kept ROIs (keys whose class field is non-zero sort first).
+constexpr int kDetRankThreads = 256;
+constexpr int kDetRankMine = 64;
+constexpr int kDetRankTile = 1024;
+__global__ void __launch_bounds__(kDetRankThreads)
+det_rank_gather_kernel(const unsigned long long* __restrict__ keys, const float4* __restrict__ clipped,
+                       const int32_t* __restrict__ cls, int N, int n_pow2, unsigned long long* __restrict__ sorted_keys,
+                       float4* __restrict__ sorted_boxes, int32_t* __restrict__ group, int32_t* __restrict__ num_valid) {
+  __shared__ unsigned long long tile[kDetRankTile];
+  __shared__ int32_t partial[kDetRankThreads];
+  const int b = blockIdx.y;
+  const unsigned long long* in = keys + (int64_t)b * n_pow2;
+  const int me = blockIdx.x * kDetRankMine + (threadIdx.x & (kDetRankMine - 1));
+  const int part = threadIdx.x / kDetRankMine;
+  constexpr int kParts = kDetRankThreads / kDetRankMine;
+  const unsigned long long mine = (me < N) ? in[me] : ~0ull;
+  int rank = 0;
+  for (int t0 = 0; t0 < N; t0 += kDetRankTile) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDetRankTile; i += kDetRankThreads) tile[i] = (t0 + i < N) ? in[t0 + i] : 0ull;
+    __syncthreads();
+    const unsigned long long* tp = tile + part * (kDetRankTile / kParts);
+#pragma unroll 16
+    for (int j = 0; j < kDetRankTile / kParts; ++j) rank += (tp[j] > mine) ? 1 : 0;
+  }
+  partial[threadIdx.x] = rank;
+  __syncthreads();
+  if (part == 0 && me < N) {
+#pragma unroll
+    for (int q = 1; q < kParts; ++q) rank += partial[threadIdx.x + q * kDetRankMine];
+    const bool valid = (mine >> 48) != 0ull;
+    const int n = (int)(0xFFFFu - (uint32_t)(mine & 0xFFFFull));
+    sorted_keys[(int64_t)b * n_pow2 + rank] = valid ? mine : 0ull;
+    sorted_boxes[(int64_t)b * N + rank] = valid ? clipped[(int64_t)b * N + n] : make_float4(0.f, 0.f, 0.f, 0.f);
+    group[(int64_t)b * N + rank] = valid ? cls[(int64_t)b * N + n] : -1;
+    if (valid) atomicMax(&num_valid[b], rank + 1);
+  }
 }
 
 // Sorted position -> box / class; also finds num_valid (keys are sorted descending, zeros last).
@@ -93,11 +137,12 @@ __global__ void det_gather_kernel(const unsigned long long* __restrict__ keys, c
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= N) return;
+  // kept ROIs carry a non-zero class field and sort first
   const unsigned long long k = keys[(int64_t)b * n_pow2 + i];
   const unsigned long long nxt = (i + 1 < n_pow2) ? keys[(int64_t)b * n_pow2 + i + 1] : 0ull;
-  if (i == 0 && k == 0ull) num_valid[b] = 0;
-  if (k != 0ull && (nxt == 0ull || i == N - 1)) num_valid[b] = i + 1;
-  if (k != 0ull) {
+  const bool valid = (k >> 48) != 0ull, next_valid = (nxt >> 48) != 0ull;
+  if (valid && (!next_valid || i == N - 1)) num_valid[b] = i + 1;   // (num_valid was reset to 0 by det_prepare_kernel)
+  if (valid) {
     const int n = (int)(0xFFFFu - (uint32_t)(k & 0xFFFFull));
     sorted_boxes[(int64_t)b * N + i] = clipped[(int64_t)b * N + n];
     group[(int64_t)b * N + i] = cls[(int64_t)b * N + n];
@@ -147,8 +192,10 @@ det_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* 
     if (tid == kFinThreads - 1) tile_base = off + incl;
     __syncthreads();
   }
-  // survivors of the per-class cap -> final ordering key (score desc, ROI index asc)
-  for (int i = tid; i < n_pow2; i += kFinThreads) {
+  // survivors of the per-class cap -> final ordering key (score desc, ROI index asc), compacted into fkeys[0..m)
+  int32_t m = 0;
+  for (int t0 = 0; t0 < nv; t0 += kFinThreads) {
+    const int i = t0 + tid;
     unsigned long long out = 0ull;
     if (i < nv && kf[i]) {
       const int g = grp[i];
@@ -168,23 +215,38 @@ det_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* 
         if (nms_keep_mask) nms_keep_mask[(int64_t)b * N + n] = 1;
       }
     }
-    fkeys[i] = out;
+    // stable block compaction of the non-zero keys
+    const uint32_t bal = __ballot_sync(0xffffffffu, out != 0ull);
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    int off = m, total = 0;
+    for (int w = 0; w < kFinThreads / 32; ++w) {
+      const int c = warp_sums[w];
+      if (w < warp) off += c;
+      total += c;
+    }
+    if (out != 0ull) fkeys[off + __popc(bal & ((1u << lane) - 1u))] = out;
+    m += total;
+    __syncthreads();
   }
-  __syncthreads();
-  block_bitonic_sort_desc(fkeys, n_pow2);
+  // rank of every survivor among the m survivors (keys are unique) = its output row; rows >= min(m, M) stay zero
   float* det = detections + (int64_t)b * M * 6;
-  for (int j = tid; j < M; j += kFinThreads) {
-    const unsigned long long k = (j < n_pow2) ? fkeys[j] : 0ull;
-    float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (k != 0ull) {
-      const int n = (int)composite_index(k);
+  for (int t = tid; t < m; t += kFinThreads) {
+    const unsigned long long mine = fkeys[t];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) rank += (fkeys[j] > mine) ? 1 : 0;
+    if (rank < M) {
+      const int n = (int)composite_index(mine);
       const float4 bx = clipped[(int64_t)b * N + n];
+      float* row = det + (int64_t)rank * 6;
       row[0] = bx.x; row[1] = bx.y; row[2] = bx.z; row[3] = bx.w;
       row[4] = (float)cls[(int64_t)b * N + n];
       row[5] = score[(int64_t)b * N + n];
     }
+  }
+  for (int j = min(m, M) + tid; j < M; j += kFinThreads) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) det[j * 6 + c] = row[c];
+    for (int c = 0; c < 6; ++c) det[j * 6 + c] = 0.0f;
   }
 }
 
@@ -193,6 +255,7 @@ struct DetWs {
   float* score;
   float4* clipped;
   unsigned long long* keys;
+  unsigned long long* sorted_keys;
   float4* sorted_boxes;
   int32_t* group;
   int32_t* num_valid;
@@ -207,6 +270,7 @@ static size_t carve_det_ws(Workspace& w, int64_t B, int64_t N, DetWs* out) {
   d.score = w.take<float>((size_t)(B * N));
   d.clipped = w.take<float4>((size_t)(B * N));
   d.keys = w.take<unsigned long long>((size_t)(B * n_pow2));
+  d.sorted_keys = w.take<unsigned long long>((size_t)(B * n_pow2));
   d.sorted_boxes = w.take<float4>((size_t)(B * N));
   d.group = w.take<int32_t>((size_t)(B * N));
   d.num_valid = w.take<int32_t>((size_t)B);
@@ -292,21 +356,28 @@ int od_detection_forward(const DLTensor* proposals, const DLTensor* mrcnn_class_
     const dim3 grid((unsigned)(((int64_t)n_pow2 * 32 + 255) / 256), (unsigned)B);
     det_prepare_kernel<<<grid, 256, 0, st>>>(dptr<float4>(proposals), dptr<float>(mrcnn_class_probs),
                                              dptr<float4>(mrcnn_bbox), dptr<float4>(window_norm), (int)N, (int)C, n_pow2,
-                                             sd, params->min_confidence, d.cls, d.score, d.clipped, d.keys, dp);
+                                             sd, params->min_confidence, d.cls, d.score, d.clipped, d.keys, d.num_valid, dp);
     OD_LAUNCH_CHECK("det_prepare_kernel");
   }
-  OD_CHECK(sort_u64_desc_launch(d.keys, B, n_pow2, st));
-  {
+  const unsigned long long* sorted_keys = d.sorted_keys;
+  if (N <= 4096) {
+    const dim3 grid((unsigned)((N + kDetRankMine - 1) / kDetRankMine), (unsigned)B);
+    det_rank_gather_kernel<<<grid, kDetRankThreads, 0, st>>>(d.keys, d.clipped, d.cls, (int)N, n_pow2, d.sorted_keys,
+                                                            d.sorted_boxes, d.group, d.num_valid);
+    OD_LAUNCH_CHECK("det_rank_gather_kernel");
+  } else {   // many ROIs: bitonic sort in place, then gather
+    OD_CHECK(sort_u64_desc_launch(d.keys, B, n_pow2, st));
     const dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
     det_gather_kernel<<<grid, 256, 0, st>>>(d.keys, d.clipped, d.cls, (int)N, n_pow2, d.sorted_boxes, d.group, d.num_valid);
     OD_LAUNCH_CHECK("det_gather_kernel");
+    sorted_keys = d.keys;
   }
   OD_CHECK(nms_sorted_launch(d.sorted_boxes, d.num_valid, d.group, B, N, params->nms_threshold, N, nullptr, nullptr,
                              d.keep_flag, d.nms_ws, d.nms_bytes, st));
   {
     const size_t smem = (size_t)n_pow2 * (sizeof(unsigned long long) + sizeof(int32_t));
     OD_CUDA(cudaFuncSetAttribute(det_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    det_finalize_kernel<<<(unsigned)B, kFinThreads, smem, st>>>(d.keys, d.keep_flag, d.group, d.num_valid, d.clipped, d.cls,
+    det_finalize_kernel<<<(unsigned)B, kFinThreads, smem, st>>>(sorted_keys, d.keep_flag, d.group, d.num_valid, d.clipped, d.cls,
                                                                 d.score, (int)N, n_pow2, (int)M, dptr<float>(detections),
                                                                 dptr<int32_t>(dbg.nms_keep_mask));
     OD_LAUNCH_CHECK("det_finalize_kernel");

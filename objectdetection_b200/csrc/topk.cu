@@ -26,7 +26,7 @@ struct __align__(16) SelState {
   int32_t shift;              // number of undetermined low bits
   int32_t k_rem;              // how many to take among the elements matching `prefix`
   int32_t done;               // every element matching `prefix` is selected
-  uint32_t reserved;
+  uint32_t reserved;          // number of winners above the threshold bucket (region boundary for the rank sort)
   uint32_t out_count;         // slot counter of the winners buffer
   uint32_t cand_count;        // number of keys in the threshold bucket of the first digit (may exceed the buffer)
 };
@@ -276,6 +276,9 @@ topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_str
   __shared__ BucketPick s_pick;
   const int row = blockIdx.x;
   SelState* st = states + row;
+  // keys written so far (by the split pass) are all greater than the ones this kernel appends: the rank sort
+  // uses that boundary to halve its compares
+  if (threadIdx.x == 0) st->reserved = st->out_count;
   if (st->done) return;   // the split pass already emitted everything
   const int tid = threadIdx.x;
   const int shift1 = st->shift;
@@ -334,20 +337,29 @@ constexpr int kRankMine = 16;
 constexpr int kRankTile = 1024;
 __global__ void __launch_bounds__(kRankThreads)
 topk_rank_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int k, int ib,
-                      const float* __restrict__ scores, int64_t row_stride, int64_t col_stride,
-                      int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+                      const SelState* __restrict__ states, const float* __restrict__ scores, int64_t row_stride,
+                      int64_t col_stride, int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
   __shared__ unsigned long long tile[kRankTile];
   __shared__ int32_t partial[kRankThreads];
   const int row = blockIdx.y;
   const unsigned long long* in = buf + (int64_t)row * buf_stride;
-  const int me = blockIdx.x * kRankMine + (threadIdx.x & (kRankMine - 1));
+  const int first = blockIdx.x * kRankMine;
+  const int me = first + (threadIdx.x & (kRankMine - 1));
   constexpr int kParts = kRankThreads / kRankMine;
   const int part = threadIdx.x / kRankMine;
   const unsigned long long mine = (me < k) ? in[me] : ~0ull;
-  int rank = 0;
-  for (int t0 = 0; t0 < k; t0 += kRankTile) {
+  // buf[0, n1) holds keys that are all greater than buf[n1, k): a CTA whose keys lie on one side only counts there
+  const int n1 = states ? min((int)states[row].reserved, k) : k;
+  const int last = min(first + kRankMine, k) - 1;
+  int lo = 0, hi = k, rank = 0;
+  if (last < n1) hi = n1;
+  else if (first >= n1) {
+    lo = n1;
+    rank = (part == 0) ? n1 : 0;
+  }
+  for (int t0 = lo; t0 < hi; t0 += kRankTile) {
     __syncthreads();
-    for (int i = threadIdx.x; i < kRankTile; i += kRankThreads) tile[i] = (t0 + i < k) ? in[t0 + i] : 0ull;
+    for (int i = threadIdx.x; i < kRankTile; i += kRankThreads) tile[i] = (t0 + i < hi) ? in[t0 + i] : 0ull;
     __syncthreads();
     const unsigned long long* tp = tile + part * (kRankTile / kParts);
 #pragma unroll 16
@@ -479,7 +491,8 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
   }
   if (k <= kRankSortMaxK) {
     const dim3 g((unsigned)((k + kRankMine - 1) / kRankMine), (unsigned)rows);
-    topk_rank_emit_kernel<<<g, kRankThreads, 0, st>>>(buf, n_pow2, (int)k, ib, scores, row_stride, col_stride, idx_out, val_out);
+    topk_rank_emit_kernel<<<g, kRankThreads, 0, st>>>(buf, n_pow2, (int)k, ib, take_all ? nullptr : states, scores, row_stride,
+                                                     col_stride, idx_out, val_out);
     OD_LAUNCH_CHECK("topk_rank_emit_kernel");
   } else if (n_pow2 <= kSmemSortMax) {
     const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
