@@ -14,6 +14,7 @@
  *   od_crop_and_resize             replaces  tf.image.crop_and_resize       maskrcnn.py:152, FasterRCNN/building_blocks/fastrcnn.py:68
  *   od_detection_target_forward    replaces  BuildDetectionTargets.build_detection_target   data_processor.py:512-652
  *   od_detection_forward           replaces  DetectionLayer.build           detection.py:80-260
+ *   od_rpn_target_forward          replaces  PreprareTrainData.build_rpn_targets   data_processor.py:173-294
  *   od_frcnn_proposal_forward      replaces  FasterRCNN Proposals.build     FasterRCNN/building_blocks/proposals.py:392-512
  *   od_roi_pool_forward            replaces  roi_pool                       FasterRCNN/building_blocks/fastrcnn.py:22-70
  *
@@ -219,6 +220,26 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
                                 const DLTensor* gt_masks, DLTensor* mask_targets,
                                 const od_target_debug* debug,
                                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---- RPN targets (data_processor.py:173-294; SURVEY.md §8f "next" row) --------- */
+typedef struct od_rpn_target_params {
+  int32_t max_rpn_targets;  /* RPN_TRAIN_ANCHORS_PER_IMAGE (256) */
+  double bbox_stddev[4];    /* RPN_BBOX_STDDEV; the reference computes in float64 */
+} od_rpn_target_params;
+
+size_t od_rpn_target_workspace_bytes(int64_t batch, int64_t num_anchors, int64_t num_gt);
+/* PreprareTrainData.build_rpn_targets, batched, float64 like the reference's numpy code.
+ * anchors [A,4] f64 pixel coordinates (gen_anchors_pixel_coord), gt_boxes [B,G,4] f64 pixels with gt_count [B] i32 valid
+ * rows each, perm_pos / perm_neg [B,A] i32: permutations standing in for the two np.random.choice draws (:246,:253):
+ * with idx = where(label == +1 / -1), the entries idx[q] for the first `extra` values q of the permutation that
+ * satisfy q < len(idx) are reset to 0.
+ * rpn_target_class [B,A] i32 in {-1,0,+1}; rpn_target_bbox [B,max_rpn_targets,4] f64 (row i = i-th positive anchor in
+ * ascending order, zero padded); positive_anchors [B,max_rpn_targets,4] f64 (zero padded);
+ * counts [B,4] i32: positives / negatives before subsampling, positives / negatives kept. */
+int od_rpn_target_forward(const DLTensor* anchors, const DLTensor* gt_boxes, const DLTensor* gt_count,
+                          const DLTensor* perm_pos, const DLTensor* perm_neg, const od_rpn_target_params* params,
+                          DLTensor* rpn_target_class, DLTensor* rpn_target_bbox, DLTensor* positive_anchors,
+                          DLTensor* counts, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- DetectionLayer (detection.py:56-279) ---------------------------------- */
 typedef struct od_detection_params {

@@ -57,6 +57,10 @@ class TargetDebug(ctypes.Structure):
                                         "sampled_pos", "sampled_neg", "gt_assignment")]
 
 
+class RpnTargetParams(ctypes.Structure):
+    _fields_ = [("max_rpn_targets", c_int32), ("bbox_stddev", c_double * 4)]
+
+
 class DetectionParams(ctypes.Structure):
     _fields_ = [("bbox_stddev", c_float * 4), ("min_confidence", c_float), ("nms_threshold", c_float),
                 ("max_instances", c_int32)]
@@ -97,6 +101,8 @@ SIGNATURES = {
     "od_detection_target_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "od_detection_target_forward": (c_int, [_P, _P, _P, _P, _P, POINTER(TargetParams), _P, _P, _P, _P, _P,
                                             POINTER(TargetDebug), _P, c_size_t, _P]),
+    "od_rpn_target_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "od_rpn_target_forward": (c_int, [_P, _P, _P, _P, _P, POINTER(RpnTargetParams), _P, _P, _P, _P, _P, c_size_t, _P]),
     "od_detection_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "od_detection_forward": (c_int, [_P, _P, _P, _P, POINTER(DetectionParams), _P, POINTER(DetectionDebug), _P,
                                      c_size_t, _P]),

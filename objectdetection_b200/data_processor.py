@@ -105,3 +105,75 @@ class BuildDetectionTargets():
 
     def debug_outputs(self):
         return self.debug_dict
+
+
+class PreprareTrainData():
+    """RPN-target part of the reference's training data preparer (data_processor.py:110-294; the class name keeps
+    the reference's spelling). ``PreprareTrainData(conf, dataset=None)`` builds the pixel-coordinate anchors once
+    (:129-140, on the GPU, bit-exact with numpy) and ``build_rpn_targets(batch_gt_boxes)`` labels them against one
+    image's GT boxes exactly like the reference's float64 numpy code (:173-294) - on the device, in float64.
+
+    The image molding / mask resizing / batch assembly methods of the reference class are host data-pipeline code
+    outside the detection-head path and are not part of this package.
+
+    ``np.random.choice(idx, extra, replace=False)`` (:246, :253) is unseeded in the reference. Here the two draws are
+    explicit permutations ``perm_pos`` / ``perm_neg`` of ``0..A-1``: with ``idx = where(label == +1 / -1)``, the entries
+    ``idx[q]`` for the first ``extra`` values ``q`` of the permutation with ``q < len(idx)`` are reset to 0. (numpy's
+    legacy ``choice`` takes ``permutation(len(idx))[:extra]``, so a permutation that starts with that draw reproduces
+    the reference bit for bit - see tests/golden/make_golden_rpn.py.) Omitted permutations come from ``torch.randperm``.
+    """
+
+    def __init__(self, conf, dataset=None, device=None):
+        from . import utils
+        self.conf = conf
+        self.dataset = dataset
+        self.max_rpn_targets = conf.RPN_TRAIN_ANCHORS_PER_IMAGE
+        self.bbox_std_dev = conf.RPN_BBOX_STDDEV
+        feature_shapes = utils.get_resnet_stage_shapes(conf, conf.IMAGE_SHAPE)
+        self.anchors = utils.gen_anchors_pixel_coord(conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, feature_shapes,
+                                                     conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE, device=device)
+        self.anchor_area = (self.anchors[:, 2] - self.anchors[:, 0]) * (self.anchors[:, 3] - self.anchors[:, 1])
+
+    def build_rpn_targets(self, batch_gt_boxes, perm_pos=None, perm_neg=None, generator=None, gt_count=None,
+                          return_counts=False):
+        """batch_gt_boxes: [num_objects, (y1,x1,y2,x2)] pixels for ONE image (the reference's form) -> returns
+        (positive_anchors [num_pos,4] f64, rpn_target_class [A] i32, rpn_target_bbox [max_rpn_targets,4] f64).
+        A 3-D [B,G,4] input (with ``gt_count`` [B], default G) runs the batch in one call and returns the padded
+        tensors ([B,max,4], [B,A], [B,max,4]) plus counts [B,4] when ``return_counts``."""
+        L = _lib.lib()
+        anchors = self.anchors
+        dev = anchors.device
+        gt = _lib.as_cuda(batch_gt_boxes, torch.float64, dev)
+        single = gt.dim() == 2
+        if single:
+            gt = gt[None]
+        B, G = gt.shape[0], gt.shape[1]
+        A, T = anchors.shape[0], int(self.max_rpn_targets)
+        if gt_count is None:
+            cnt = torch.full((B,), G, dtype=torch.int32, device=dev)
+        else:
+            cnt = _lib.as_cuda(gt_count, torch.int32, dev).reshape(B)
+
+        def perm(p):
+            if p is None:
+                return torch.stack([torch.randperm(A, device=dev, generator=generator) for _ in range(B)]).to(torch.int32)
+            p = _lib.as_cuda(p, torch.int32, dev)
+            return (p[None] if p.dim() == 1 else p).contiguous()
+        pp, pn = perm(perm_pos), perm(perm_neg)
+        cls = torch.empty((B, A), dtype=torch.int32, device=dev)
+        bbox = torch.empty((B, T, 4), dtype=torch.float64, device=dev)
+        pos = torch.empty((B, T, 4), dtype=torch.float64, device=dev)
+        counts = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        sd = [float(v) for v in self.bbox_std_dev]
+        params = _lib.RpnTargetParams(T, (ctypes.c_double * 4)(*sd))
+        ws = _lib.workspace(L.od_rpn_target_workspace_bytes(B, A, G), dev)
+        dl = _lib.DL()
+        _lib.check(L.od_rpn_target_forward(dl(anchors), dl(gt.contiguous()), dl(cnt), dl(pp), dl(pn), ctypes.byref(params),
+                                           dl(cls), dl(bbox), dl(pos), dl(counts), ws.data_ptr(), ws.numel(),
+                                           _lib.stream_ptr(dev)), "od_rpn_target_forward")
+        if single:
+            n_pos = int(counts[0, 2].item())          # like the reference: positive_anchors has one row per positive
+            out = (pos[0, :n_pos], cls[0], bbox[0])
+        else:
+            out = (pos, cls, bbox)
+        return out + (counts,) if return_counts else out

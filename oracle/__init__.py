@@ -244,6 +244,63 @@ def mask_targets(rois, gt_class_ids, gt_boxes, gt_masks_hwg, dbg, mask_shape=(28
     return out
 
 
+def rpn_targets(anchors, gt_boxes, perm_pos, perm_neg, max_rpn_targets: int, stddev):
+    """PreprareTrainData.build_rpn_targets (data_processor.py:173-294) for ONE image, numpy float64 like the reference,
+    with utils.intersection_over_union (utils.py:32-40). The two ``np.random.choice(idx, extra, replace=False)``
+    draws (:246, :253) are explicit permutations: ``idx[q]`` is reset to 0 for the first ``extra`` entries ``q`` of the
+    permutation with ``q < len(idx)``. Pinned by tests/golden/reference_rpn_targets.npz (the reference's own output).
+    Returns (positive_anchors [n_pos,4], rpn_target_class [A] int32, rpn_target_bbox [max,4], counts [4])."""
+    anchors = _f64(anchors)
+    gt = _f64(gt_boxes)
+    A = anchors.shape[0]
+    cls = np.zeros([A], dtype="int32")
+    anchor_area = (anchors[:, 2] - anchors[:, 0]) * (anchors[:, 3] - anchors[:, 1])
+    gt_area = (gt[:, 2] - gt[:, 0]) * (gt[:, 3] - gt[:, 1])
+    overlaps = np.zeros((gt.shape[0], A))
+    for i in range(gt.shape[0]):
+        y1 = np.maximum(gt[i, 0], anchors[:, 0])
+        y2 = np.minimum(gt[i, 2], anchors[:, 2])
+        x1 = np.maximum(gt[i, 1], anchors[:, 1])
+        x2 = np.minimum(gt[i, 3], anchors[:, 3])
+        inter = np.maximum(x2 - x1, 0) * np.maximum(y2 - y1, 0)
+        overlaps[i] = inter / (gt_area[i] + anchor_area - inter)
+    overlaps = overlaps.T
+    if gt.shape[0] > 0:
+        amax_idx = np.argmax(overlaps, axis=1)
+        amax = overlaps[np.arange(A), amax_idx]
+    else:                                   # (the reference cannot run without GT; all background here)
+        amax_idx, amax = np.zeros(A, np.int64), np.zeros(A)
+    cls[amax < 0.3] = -1
+    if gt.shape[0] > 0:
+        cls[np.argmax(overlaps, axis=0)] = 1
+    cls[amax >= 0.7] = 1
+
+    def drop(label, perm, extra):
+        idx = np.where(cls == label)[0]
+        if extra > 0:
+            q = np.asarray(perm)[np.asarray(perm) < len(idx)][:extra]
+            cls[idx[q]] = 0
+    idx = np.where(cls == 1)[0]
+    n_pos0 = len(idx)
+    drop(1, perm_pos, n_pos0 - max_rpn_targets // 2)
+    n_neg0 = int(np.sum(cls == -1))
+    drop(-1, perm_neg, n_neg0 - (max_rpn_targets - int(np.sum(cls == 1))))
+    bbox = np.zeros((max_rpn_targets, 4))
+    pos_idx = np.where(cls == 1)[0]
+    sd = _f64(stddev)
+    for i, a in enumerate(pos_idx):
+        g = gt[amax_idx[a]]
+        an = anchors[a]
+        ah, aw = an[2] - an[0], an[3] - an[1]
+        acy, acx = an[0] + 0.5 * ah, an[1] + 0.5 * aw
+        gh, gw = g[2] - g[0], g[3] - g[1]
+        gcy, gcx = g[0] + 0.5 * gh, g[1] + 0.5 * gw
+        bbox[i] = [(gcy - acy) / ah, (gcx - acx) / aw, np.log(gh / ah), np.log(gw / aw)]
+        bbox[i] /= sd
+    counts = np.array([n_pos0, n_neg0, len(pos_idx), int(np.sum(cls == -1))], np.int32)
+    return anchors[pos_idx], cls, bbox, counts
+
+
 def detection_forward(proposals, probs, bbox, window_norm, stddev, min_conf: float, nms_thr: float,
                       max_instances: int, debug: bool = False):
     """DetectionLayer.build. Returns detections [B,M,6] (and intermediates if debug)."""

@@ -502,6 +502,56 @@ def test_frcnn_proposals_and_roi_pool(golden):
     assert_bits(pooled, wp, "roi_pool")
 
 
+# ------------------------------------------------------------------ RPN targets
+def test_rpn_targets_golden_and_coco_shape():
+    """PreprareTrainData.build_rpn_targets: (1) the reference's own outputs (golden, subsampling replayed),
+    (2) COCO shape: 261,888 anchors x up to 100 GT boxes, batch 3, against the numpy oracle."""
+    import os
+    from objectdetection_b200.data_processor import PreprareTrainData
+    from objectdetection_b200 import ShapesConfig, config
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_rpn_targets.npz"))
+
+    class Sub(config):
+        IMAGE_SHAPE = [256, 256, 3]
+        RPN_ANCHOR_SCALES = (16, 32, 64, 128, 256)
+        RPN_TRAIN_ANCHORS_PER_IMAGE = 16
+    for case, conf in (("toy", ShapesConfig()), ("sub", Sub())):
+        P = PreprareTrainData(conf)
+        assert np.array_equal(host(P.anchors), g[case + "_anchors"])
+        pos, cls, bbox = P.build_rpn_targets(g[case + "_gt"], perm_pos=g[case + "_perm_pos"], perm_neg=g[case + "_perm_neg"])
+        assert np.array_equal(host(cls), g[case + "_cls"])                        # labels: bit-exact
+        assert np.array_equal(host(pos), g[case + "_pos_anchors"])
+        assert np.allclose(host(bbox), g[case + "_bbox"], rtol=1e-13, atol=0)     # fp64 deltas (log may differ by an ulp)
+    # COCO shape against the oracle
+    conf = Conf()
+    P = PreprareTrainData(conf)
+    A = P.anchors.shape[0]
+    assert A == 261888
+    rs = np.random.RandomState(21)
+    B, G = 3, 100
+    anc = host(P.anchors)
+    gt = np.zeros((B, G, 4))
+    cnt = np.array([100, 37, 1], np.int32)
+    for b in range(B):
+        pick = rs.choice(A, cnt[b], replace=False)
+        gt[b, :cnt[b]] = np.round(np.clip(anc[pick] + rs.normal(0, 3, (cnt[b], 4)), 0, 1024))
+        bad = (gt[b, :, 2] <= gt[b, :, 0]) | (gt[b, :, 3] <= gt[b, :, 1])
+        gt[b, bad] = [100, 100, 164, 164]
+    pp = np.stack([rs.permutation(A) for _ in range(B)]).astype(np.int32)
+    pn = np.stack([rs.permutation(A) for _ in range(B)]).astype(np.int32)
+    pos, cls, bbox, counts = P.build_rpn_targets(gt, perm_pos=pp, perm_neg=pn, gt_count=cnt, return_counts=True)
+    pos, cls, bbox, counts = host(pos), host(cls), host(bbox), host(counts)
+    for b in range(B):
+        w_pos, w_cls, w_bbox, w_counts = oracle.rpn_targets(anc, gt[b, :cnt[b]], pp[b], pn[b], conf.RPN_TRAIN_ANCHORS_PER_IMAGE,
+                                                            conf.RPN_BBOX_STDDEV)
+        assert np.array_equal(counts[b], w_counts), (counts[b], w_counts)
+        assert np.array_equal(cls[b], w_cls)
+        n = w_counts[2]
+        assert np.array_equal(pos[b, :n], w_pos) and not pos[b, n:].any()
+        assert np.allclose(bbox[b], w_bbox, rtol=1e-13, atol=0)
+        assert (cls[b] == 1).sum() <= 128 and (cls[b] == 1).sum() + (cls[b] == -1).sum() == 256
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_are_loud():
     from objectdetection_b200 import _lib

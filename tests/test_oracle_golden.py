@@ -92,3 +92,19 @@ def test_frcnn_full_layer_matches_reference_pieces(golden):
         ref = golden[f"frcnn_nms_out_thr{int(thr * 10)}"]
         assert out.shape == (ref.shape[0], 5)
         assert np.array_equal(out[:, 1:], ref.astype(np.float32)) and np.all(out[:, 0] == 0)
+
+
+def test_rpn_targets_match_the_reference():
+    """oracle.rpn_targets against the reference's own build_rpn_targets output (tests/golden/make_golden_rpn.py):
+    labels, subsampling (replayed np.random.choice permutations) and box deltas; includes SURVEY G7."""
+    import os
+    import oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_rpn_targets.npz"))
+    for case in ("toy", "sub"):
+        pos, cls, bbox, counts = oracle.rpn_targets(g[case + "_anchors"], g[case + "_gt"], g[case + "_perm_pos"],
+                                                    g[case + "_perm_neg"], int(g[case + "_max_targets"]), [0.1, 0.1, 0.2, 0.2])
+        assert np.array_equal(cls, g[case + "_cls"])
+        assert np.array_equal(bbox, g[case + "_bbox"])
+        assert np.array_equal(pos, g[case + "_pos_anchors"])
+        assert counts[0] == int(g[case + "_n_pos0"]) and counts[1] == int(g[case + "_n_neg0"])
+    assert (g["toy_cls"] == 1).sum() == 3 and (g["toy_cls"] == -1).sum() == 253      # G7
