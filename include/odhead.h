@@ -14,6 +14,7 @@
  *   od_crop_and_resize             replaces  tf.image.crop_and_resize       maskrcnn.py:152, FasterRCNN/building_blocks/fastrcnn.py:68
  *   od_detection_target_forward    replaces  BuildDetectionTargets.build_detection_target   data_processor.py:512-652
  *   od_detection_forward           replaces  DetectionLayer.build           detection.py:80-260
+ *   od_unmold_detections           replaces  unmold_detection + denorm_boxes   detection.py:8-53, utils.py:212-227
  *   od_rpn_target_forward          replaces  PreprareTrainData.build_rpn_targets   data_processor.py:173-294
  *   od_frcnn_proposal_forward      replaces  FasterRCNN Proposals.build     FasterRCNN/building_blocks/proposals.py:392-512
  *   od_roi_pool_forward            replaces  roi_pool                       FasterRCNN/building_blocks/fastrcnn.py:22-70
@@ -268,6 +269,13 @@ int od_detection_forward(const DLTensor* proposals, const DLTensor* mrcnn_class_
                          const od_detection_params* params, DLTensor* detections,
                          const od_detection_debug* debug,
                          void* ws, size_t ws_bytes, void* stream);
+
+/* unmold_detection (detection.py:8-53) + denorm_boxes (utils.py:212-227) for a batch, on the device:
+ * detections [B,M,6] f32, window_norm [B,4] f32 (norm_boxes of the pixel windows), original_shape [B,2] i32 (h,w).
+ * boxes [B,M,4] i32 pixel (y1,x1,y2,x2), class_ids [B,M] i32, scores [B,M] f32: the surviving rows (class_id != 0
+ * prefix, zero-area boxes dropped) in order, zero padded; counts [B] i32 = rows kept. */
+int od_unmold_detections(const DLTensor* detections, const DLTensor* window_norm, const DLTensor* original_shape,
+                         DLTensor* boxes, DLTensor* class_ids, DLTensor* scores, DLTensor* counts, void* stream);
 
 /* ---- Faster R-CNN single-level variants ------------------------------------ */
 typedef struct od_frcnn_params {

@@ -250,6 +250,71 @@ det_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* 
   }
 }
 
+// unmold_detection (detection.py:8-53) + denorm_boxes (utils.py:212-227) for a whole batch on the device (SURVEY.md
+// §8f rank 2: the step after the path, e.g. straight after the all-gather). One CTA per image:
+//   N = first row with class_id == 0; boxes = (boxes - shift) / scale in fp32 (window frame), then
+//   around(boxes * (h-1, w-1, h-1, w-1) + (0,0,1,1)) in fp64 -> int32 (numpy promotes float32 * int64 to float64;
+//   around = half to even); rows with (y2-y1)*(x2-x1) <= 0 are dropped; survivors keep their order.
+constexpr int kUnmoldThreads = 128;
+__global__ void __launch_bounds__(kUnmoldThreads)
+unmold_kernel(const float* __restrict__ detections, const float4* __restrict__ window_norm,
+              const int32_t* __restrict__ original_shape, int M, int32_t* __restrict__ boxes, int32_t* __restrict__ class_ids,
+              float* __restrict__ scores, int32_t* __restrict__ counts) {
+  __shared__ int s_first_zero;
+  __shared__ int warp_cnt[kUnmoldThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* det = detections + (int64_t)b * M * 6;
+  if (tid == 0) s_first_zero = M;
+  __syncthreads();
+  for (int i = tid; i < M; i += kUnmoldThreads)
+    if (det[i * 6 + 4] == 0.0f) atomicMin(&s_first_zero, i);
+  __syncthreads();
+  const int N = s_first_zero;
+  const float4 w = window_norm[b];
+  const float wh = w.z - w.x, ww = w.w - w.y;
+  const double sh = (double)(original_shape[b * 2 + 0] - 1), sw = (double)(original_shape[b * 2 + 1] - 1);
+  int32_t* ob = boxes + (int64_t)b * M * 4;
+  int32_t* oc = class_ids + (int64_t)b * M;
+  float* os = scores + (int64_t)b * M;
+  int base = 0;
+  for (int t0 = 0; t0 < N; t0 += kUnmoldThreads) {
+    const int i = t0 + tid;
+    bool keep = false;
+    int y1 = 0, x1 = 0, y2 = 0, x2 = 0;
+    if (i < N) {
+      const float by1 = (det[i * 6 + 0] - w.x) / wh, bx1 = (det[i * 6 + 1] - w.y) / ww;
+      const float by2 = (det[i * 6 + 2] - w.x) / wh, bx2 = (det[i * 6 + 3] - w.y) / ww;
+      y1 = (int)rint((double)by1 * sh + 0.0);
+      x1 = (int)rint((double)bx1 * sw + 0.0);
+      y2 = (int)rint((double)by2 * sh + 1.0);
+      x2 = (int)rint((double)bx2 * sw + 1.0);
+      keep = (y2 - y1) * (x2 - x1) > 0;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = base, total = 0;
+    for (int q = 0; q < kUnmoldThreads / 32; ++q) {
+      if (q < warp) off += warp_cnt[q];
+      total += warp_cnt[q];
+    }
+    if (keep) {
+      const int r = off + __popc(bal & ((1u << lane) - 1u));
+      ob[r * 4 + 0] = y1; ob[r * 4 + 1] = x1; ob[r * 4 + 2] = y2; ob[r * 4 + 3] = x2;
+      oc[r] = (int32_t)det[i * 6 + 4];
+      os[r] = det[i * 6 + 5];
+    }
+    base += total;
+    __syncthreads();
+  }
+  for (int r = base + tid; r < M; r += kUnmoldThreads) {
+    ob[r * 4 + 0] = 0; ob[r * 4 + 1] = 0; ob[r * 4 + 2] = 0; ob[r * 4 + 3] = 0;
+    oc[r] = 0;
+    os[r] = 0.0f;
+  }
+  if (tid == 0) counts[b] = base;
+}
+
 struct DetWs {
   int32_t* cls;
   float* score;
@@ -382,6 +447,33 @@ int od_detection_forward(const DLTensor* proposals, const DLTensor* mrcnn_class_
                                                                 dptr<int32_t>(dbg.nms_keep_mask));
     OD_LAUNCH_CHECK("det_finalize_kernel");
   }
+  return OD_OK;
+}
+
+int od_unmold_detections(const DLTensor* detections, const DLTensor* window_norm, const DLTensor* original_shape,
+                         DLTensor* boxes, DLTensor* class_ids, DLTensor* scores, DLTensor* counts, void* stream) {
+  int dev = -1;
+  OD_CHECK(check_tensor(detections, "detections", F32, 3, true, &dev));
+  OD_CHECK(check_tensor(window_norm, "window_norm", F32, 2, true, &dev));
+  OD_CHECK(check_tensor(original_shape, "original_shape", I32, 2, true, &dev));
+  OD_CHECK(check_tensor(boxes, "boxes", I32, 3, true, &dev));
+  OD_CHECK(check_tensor(class_ids, "class_ids", I32, 2, true, &dev));
+  OD_CHECK(check_tensor(scores, "scores", F32, 2, true, &dev));
+  OD_CHECK(check_tensor(counts, "counts", I32, 1, true, &dev));
+  const int64_t B = detections->shape[0], M = detections->shape[1];
+  if (detections->shape[2] != 6) OD_FAIL(OD_ERR_SHAPE, "detections must be [B,M,6]");
+  if (window_norm->shape[0] != B || window_norm->shape[1] != 4) OD_FAIL(OD_ERR_SHAPE, "window_norm must be [B,4]");
+  if (original_shape->shape[0] != B || original_shape->shape[1] != 2) OD_FAIL(OD_ERR_SHAPE, "original_shape must be [B,2] (h,w)");
+  if (boxes->shape[0] != B || boxes->shape[1] != M || boxes->shape[2] != 4 || class_ids->shape[0] != B ||
+      class_ids->shape[1] != M || scores->shape[0] != B || scores->shape[1] != M || counts->shape[0] != B)
+    OD_FAIL(OD_ERR_SHAPE, "outputs must be boxes [B,M,4], class_ids [B,M], scores [B,M], counts [B]");
+  if (reinterpret_cast<uintptr_t>(dptr<float>(window_norm)) % 16) OD_FAIL(OD_ERR_LAYOUT, "window_norm must be 16-byte aligned");
+  if (B > 0x7FFFFFFFll || M > (1 << 24)) OD_FAIL(OD_ERR_PARAM, "batch / rows out of range");
+  if (B == 0) return OD_OK;
+  unmold_kernel<<<(unsigned)B, kUnmoldThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dptr<float>(detections), dptr<float4>(window_norm), dptr<int32_t>(original_shape), (int)M, dptr<int32_t>(boxes),
+      dptr<int32_t>(class_ids), dptr<float>(scores), dptr<int32_t>(counts));
+  OD_LAUNCH_CHECK("unmold_kernel");
   return OD_OK;
 }
 

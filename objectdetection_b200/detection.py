@@ -38,6 +38,32 @@ def unmold_detection(original_image_shape, image_shape, detections, image_window
     return boxes, class_ids, scores
 
 
+def unmold_detections_batch(original_image_shapes, image_shape, detections, image_windows):
+    """``unmold_detection`` for a whole batch on the device (e.g. right after the multi-GPU all-gather): detections
+    [B,M,6] CUDA float32, image_windows [B,4] pixel windows, original_image_shapes [B,2|3] (or one shape for all).
+    Returns (boxes [B,M,4] int32, class_ids [B,M] int32, scores [B,M] float32, counts [B] int32); the first
+    ``counts[b]`` rows of image b equal the reference function's output, the rest is zero."""
+    det = _lib.as_cuda(detections, torch.float32)
+    dev = det.device
+    B, M = det.shape[0], det.shape[1]
+    win = norm_boxes(np.asarray(image_windows).reshape(-1, 4), image_shape[:2])          # detection.py:17, host, tiny
+    if win.shape[0] == 1 and B > 1:
+        win = np.repeat(win, B, 0)
+    shp = np.asarray(original_image_shapes, np.int32).reshape(-1, np.asarray(original_image_shapes).shape[-1])[:, :2]
+    if shp.shape[0] == 1 and B > 1:
+        shp = np.repeat(shp, B, 0)
+    win_t = _lib.const_cuda(np.ascontiguousarray(win, np.float32), torch.float32, dev)
+    shp_t = _lib.const_cuda(np.ascontiguousarray(shp, np.int32), torch.int32, dev)
+    boxes = torch.empty((B, M, 4), dtype=torch.int32, device=dev)
+    cls = torch.empty((B, M), dtype=torch.int32, device=dev)
+    scores = torch.empty((B, M), dtype=torch.float32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    dl = _lib.DL()
+    _lib.check(_lib.lib().od_unmold_detections(dl(det), dl(win_t), dl(shp_t), dl(boxes), dl(cls), dl(scores), dl(counts),
+                                               _lib.stream_ptr(dev)), "od_unmold_detections")
+    return boxes, cls, scores, counts
+
+
 class DetectionLayer():
     """Per-ROI argmax class -> class-specific delta decode -> clip to window -> bg/score filter -> per-class NMS
     -> top-100 -> zero-padded [B,100,6] rows (y1,x1,y2,x2,class_id,score). Signature of detection.py:57."""

@@ -502,6 +502,35 @@ def test_frcnn_proposals_and_roi_pool(golden):
     assert_bits(pooled, wp, "roi_pool")
 
 
+# ------------------------------------------------------------------ device unmold
+def test_unmold_detections_on_device(golden):
+    """od_unmold_detections vs the reference-shaped host function (itself pinned by the reference's numpy code in
+    test_oracle_golden) on DetectionLayer outputs, plus zero-area / empty / full edge rows."""
+    from objectdetection_b200.detection import unmold_detection, unmold_detections_batch
+    rs = np.random.RandomState(31)
+    B, M = 5, 100
+    det = np.zeros((B, M, 6), f32)
+    for b, n in enumerate([37, 0, 100, 5, 64]):
+        y1 = rs.uniform(0.13, 0.8, n); x1 = rs.uniform(0.0, 0.9, n)
+        det[b, :n, 0], det[b, :n, 1] = y1, x1
+        det[b, :n, 2], det[b, :n, 3] = y1 + rs.uniform(0, 0.07, n), x1 + rs.uniform(0, 0.1, n)
+        det[b, :n, 4] = rs.randint(1, 81, n)
+        det[b, :n, 5] = rs.uniform(0.7, 1, n)
+    det[0, 3, 2:4] = det[0, 3, 0:2]                      # zero-size row: 1 px after the +1 shift of denorm_boxes -> kept
+    det[0, 7, 3] = det[0, 7, 1] - 0.01                   # flipped in x -> negative area -> dropped
+    det[3, 1, 2] = det[3, 1, 0] - 0.01                   # flipped -> negative area -> dropped
+    windows = np.array([[131, 0, 893, 1024], [0, 0, 1024, 1024], [131, 0, 893, 1024], [0, 100, 1024, 924], [131, 0, 893, 1024]])
+    shapes = np.array([[480, 640, 3], [1024, 1024, 3], [375, 500, 3], [600, 600, 3], [720, 1280, 3]])
+    boxes, cls, scores, counts = (host(x) for x in unmold_detections_batch(shapes, [1024, 1024, 3], cu(det), windows))
+    for b in range(B):
+        wb, wc, ws = unmold_detection(shapes[b], [1024, 1024, 3], det[b], windows[b])
+        n = counts[b]
+        assert n == wb.shape[0]
+        assert np.array_equal(boxes[b, :n], wb) and np.array_equal(cls[b, :n], wc) and np.array_equal(scores[b, :n], ws)
+        assert not boxes[b, n:].any() and not cls[b, n:].any()
+    assert counts.tolist() == [36, 0, 100, 4, 64]
+
+
 # ------------------------------------------------------------------ RPN targets (SURVEY §8f)
 def test_rpn_targets_golden_and_coco_shape():
     """PreprareTrainData.build_rpn_targets: (1) the reference's own outputs (golden, subsampling replayed),
