@@ -9,8 +9,9 @@ Workload (BASELINE.json configs[1], SURVEY.md §8d cfg 2): Mask R-CNN COCO-shape
 261,888 anchors, 6000 pre-NMS -> 1000 proposals, ROIAlign 7x7 and 14x14 over P2-P5 (D=256), 81 classes,
 batch 2 per GPU (weak scaling: every rank owns its own 2 images; N>1 adds one all-gather of the detections).
 
-One step = Proposals -> PyramidROIAlign 7x7 (1000 ROIs/img) -> DetectionLayer (synthetic head outputs)
-           -> PyramidROIAlign 14x14 (1000 ROIs/img)  [-> all_gather(detections) when N>1]
+One step = Proposals -> PyramidROIAlign 7x7 (1000 ROIs/img) -> { DetectionLayer (synthetic head outputs)  ||
+           PyramidROIAlign 14x14 (1000 ROIs/img) }  [-> all_gather(detections) when N>1]
+           (the two branches only depend on the proposals and run on two streams; the step ends when both are done)
 
 Reported on ONE JSON line (rank 0):
   value        images/s with the inputs resident in HBM, CUDA events around exactly K steps, max over ranks
@@ -315,41 +316,62 @@ def run_ours(args):
     pooled14 = torch.empty((1, B * N_ROIS, 14, 14, DEPTH), dtype=torch.float32, device=dev)
     roi_ev = []
 
-    def front(inp):
+    def front(inp):      # Proposals -> ROIAlign 7x7
         proposals = Proposals(conf, B, inp["probs"], inp["bbox"], anchors).get_proposals()
         pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [7, 7], out=pooled7)
-        det = DetectionLayer(conf, conf.IMAGE_SHAPE, B, window, proposals, inp["hprobs"], inp["hbbox"]).get_detections()
-        return proposals, det
+        return proposals
 
-    # Proposals -> ROIAlign 7x7 -> DetectionLayer of every resident input set is captured once into a CUDA graph (the
-    # layer classes are called unchanged inside torch.cuda.graph); the 14x14 ROIAlign launch - the roofline kernel -
-    # stays an eager call so that CUDA events can bracket it inside the timed region.
+    def detect(inp, proposals):
+        return DetectionLayer(conf, conf.IMAGE_SHAPE, B, window, proposals, inp["hprobs"], inp["hbbox"]).get_detections()
+
+    # The layer classes are called unchanged inside torch.cuda.graph: per resident input set, graph A = Proposals ->
+    # ROIAlign 7x7 and graph B = DetectionLayer. The 14x14 ROIAlign launch - the roofline kernel - stays an eager call
+    # so that CUDA events can bracket it inside the timed region. DetectionLayer (a chain of small latency-bound
+    # kernels on a few SMs) and the 14x14 ROIAlign (HBM-bound, all SMs) only depend on the proposals, so graph B runs
+    # on a second stream next to the ROIAlign launch and the step joins both at its end.
     graphs = [None] * NSETS
-    static_out = [None] * NSETS
-    graph_launches = [0] * NSETS      # kernels captured per graph (od_launch_count delta during capture)
+    graphs_det = [None] * NSETS
+    static_prop = [None] * NSETS
+    static_det = [None] * NSETS
+    graph_launches = [0] * NSETS      # kernels captured per step (od_launch_count delta during the captures)
+    main_stream = torch.cuda.current_stream()
+    det_stream = torch.cuda.Stream(priority=-1)     # high priority: its small CTAs slip in between ROIAlign CTAs
+    ev_prop = [torch.cuda.Event() for _ in range(NSETS)]
+    ev_det = [torch.cuda.Event() for _ in range(NSETS)]
     if not args.no_graph:
         side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for s_ in range(NSETS):
-                front(dev_sets[s_])      # eager run on the capture stream: workspace + constant caches exist
-        torch.cuda.current_stream().wait_stream(side)
+        for cap_stream in (side, det_stream):        # eager runs on the capture streams: workspaces + constant caches exist
+            cap_stream.wait_stream(main_stream)
+            with torch.cuda.stream(cap_stream):
+                for s_ in range(NSETS):
+                    detect(dev_sets[s_], front(dev_sets[s_]))
+            main_stream.wait_stream(cap_stream)
         torch.cuda.synchronize()
         for s_ in range(NSETS):
-            g = torch.cuda.CUDAGraph()
             n0 = L.od_launch_count()
+            g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                static_out[s_] = front(dev_sets[s_])
+                static_prop[s_] = front(dev_sets[s_])
+            gd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gd, stream=det_stream):
+                static_det[s_] = detect(dev_sets[s_], static_prop[s_])
             graph_launches[s_] = L.od_launch_count() - n0
-            graphs[s_] = g
+            graphs[s_], graphs_det[s_] = g, gd
 
     def step(s_, time_roi=False):
         inp = dev_sets[s_]
         if graphs[s_] is not None:
             graphs[s_].replay()
-            proposals, det = static_out[s_]
+            proposals = static_prop[s_]
+            ev_prop[s_].record(main_stream)
+            with torch.cuda.stream(det_stream):
+                det_stream.wait_event(ev_prop[s_])
+                graphs_det[s_].replay()
+                ev_det[s_].record(det_stream)
+            det = static_det[s_]
         else:
-            proposals, det = front(inp)
+            proposals = front(inp)
+            det = detect(inp, proposals)
         if time_roi:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -357,6 +379,8 @@ def run_ours(args):
         if time_roi:
             e1.record()
             roi_ev.append((e0, e1))
+        if graphs[s_] is not None:
+            main_stream.wait_event(ev_det[s_])       # join: the step ends when both branches are done
         if world > 1:
             return gather_detections(det, batch=world * B), proposals     # the path's only collective
         return det, proposals
@@ -440,7 +464,6 @@ def run_ours(args):
     # buffers the layer classes read), runs the step and reads the detections back D2H. The copy of step i+1 runs on
     # a second stream while step i computes (two input sets = double buffer); everything is inside the timed region.
     copy_stream = torch.cuda.Stream()
-    main_stream = torch.cuda.current_stream()
     ready = [torch.cuda.Event() for _ in range(NSETS)]      # H2D of set s finished
     consumed = [torch.cuda.Event() for _ in range(NSETS)]   # compute on set s finished (buffers may be overwritten)
     det_host = [torch.empty((B, conf.DETECTION_POST_NMS_INSTANCES, 6), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
@@ -526,7 +549,8 @@ def run_ours(args):
                        "l2": f"{NSETS} rotating input sets; each step reads 2x89 MB of pyramid and writes 0.5 GB of "
                              f"pooled ROIs (> 126 MB L2)",
                        "collective": "all_gather(detections) per step" if world > 1 else "none",
-                       "launch": "eager" if args.no_graph else "CUDA graph (Proposals+ROIAlign7+Detection) + eager ROIAlign14"},
+                       "launch": "eager, one stream" if args.no_graph else
+                                 "CUDA graph A (Proposals+ROIAlign7), then graph B (DetectionLayer, 2nd stream) || eager ROIAlign14"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": clocks, "roialign_standalone": standalone,
             "detections_per_image": float((det[:, :, 4] > 0).sum().item()) / det.shape[0],
