@@ -36,8 +36,8 @@ __global__ void frcnn_decode_kernel(const T* __restrict__ probs, const T* __rest
                                     int32_t* __restrict__ counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   Key128 k;
-  k.hi = 0ull;
-  k.lo = 0ull;
+  k.hi = 0ull;                                            // filtered-out rows: below every valid key, still unique
+  k.lo = 0xFFFFFFFFFFFFFFFFull - (unsigned long long)i;
   bool valid = false;
   if (i < total) {
     const int na = p.num_anchors;
@@ -72,33 +72,49 @@ __global__ void frcnn_decode_kernel(const T* __restrict__ probs, const T* __rest
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&counters[0], __popc(bal));
 }
 
-__global__ void bitonic_step_k128_kernel(Key128* __restrict__ keys, int64_t n_pow2, int64_t k, int64_t j) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (n_pow2 >> 1)) return;
-  const int64_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-  const int64_t l = i | j;
-  const bool desc = ((i & k) == 0);
-  const Key128 a = keys[i], b = keys[l];
-  if (key_less(a, b) == desc) {
-    keys[i] = b;
-    keys[l] = a;
+// Rank sort fused with the gather: keys are unique, the visiting position of a box is the number of keys greater
+// than its own. grid ceil(total/32); a CTA owns 32 keys, 8 thread groups each count over an 8th of every 1024-key
+// tile in shared memory. Position r < K receives the box (zeros for filtered-out rows); counters[1] = npre.
+constexpr int kFrRankThreads = 256;
+constexpr int kFrRankMine = 32;
+constexpr int kFrRankTile = 1024;
+__global__ void __launch_bounds__(kFrRankThreads)
+frcnn_rank_gather_kernel(const Key128* __restrict__ keys, const double* __restrict__ boxes, int64_t total, int pre_n, int K,
+                         double* __restrict__ sorted, int32_t* __restrict__ counters) {
+  __shared__ Key128 tile[kFrRankTile];
+  __shared__ int32_t partial[kFrRankThreads];
+  constexpr int kParts = kFrRankThreads / kFrRankMine;
+  const int64_t me = (int64_t)blockIdx.x * kFrRankMine + (threadIdx.x & (kFrRankMine - 1));
+  const int part = threadIdx.x / kFrRankMine;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counters[1] = min(counters[0], pre_n);
+  Key128 mine;
+  mine.hi = ~0ull;
+  mine.lo = ~0ull;
+  if (me < total) mine = keys[me];
+  int rank = 0;
+  for (int64_t t0 = 0; t0 < total; t0 += kFrRankTile) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFrRankTile; i += kFrRankThreads) {
+      Key128 z;
+      z.hi = 0ull;
+      z.lo = 0ull;
+      tile[i] = (t0 + i < total) ? keys[t0 + i] : z;
+    }
+    __syncthreads();
+    const Key128* tp = tile + part * (kFrRankTile / kParts);
+#pragma unroll 8
+    for (int j = 0; j < kFrRankTile / kParts; ++j) rank += key_less(mine, tp[j]) ? 1 : 0;
   }
-}
-
-// counters[0] = #valid -> counters[1] = npre = min(#valid, pre_n); gather boxes in visiting order.
-__global__ void frcnn_gather_kernel(const Key128* __restrict__ keys, const double* __restrict__ boxes, int pre_n, int K,
-                                    double* __restrict__ sorted, int32_t* __restrict__ counters) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int npre = min(counters[0], pre_n);
-  if (i == 0) counters[1] = npre;
-  if (i >= K) return;
-  if (i < npre) {
-    const int64_t src = (int64_t)(0xFFFFFFFFFFFFFFFFull - keys[i].lo);
+  partial[threadIdx.x] = rank;
+  __syncthreads();
+  if (part == 0 && me < total) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) sorted[4 * (int64_t)i + c] = boxes[4 * src + c];
-  } else {
+    for (int q = 1; q < kParts; ++q) rank += partial[threadIdx.x + q * kFrRankMine];
+    if (rank < K) {
+      const bool valid = mine.hi != 0ull && rank < pre_n;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) sorted[4 * (int64_t)i + c] = 0.0;
+      for (int c = 0; c < 4; ++c) sorted[4 * (int64_t)rank + c] = valid ? boxes[4 * me + c] : 0.0;
+    }
   }
 }
 
@@ -246,19 +262,11 @@ int od_frcnn_proposal_forward(const DLTensor* rpn_box_class_prob, const DLTensor
   else
     frcnn_decode_kernel<float><<<blocks, 256, 0, st>>>(dptr<float>(rpn_box_class_prob), dptr<float>(rpn_bbox), d, total, n_pow2, f.boxes, f.keys, f.counters);
   OD_LAUNCH_CHECK("frcnn_decode_kernel");
-  {
-    const unsigned g = (unsigned)((n_pow2 / 2 + 255) / 256);
-    for (int64_t k = 2; k <= n_pow2; k <<= 1)
-      for (int64_t j = k >> 1; j > 0; j >>= 1) {
-        bitonic_step_k128_kernel<<<g ? g : 1, 256, 0, st>>>(f.keys, n_pow2, k, j);
-        count_launches(1);
-      }
-    OD_LAUNCH_CHECK_NC("bitonic_step_k128_kernel");
-  }
   const int W = (int)((K + 63) / 64);
   if (K > 0) {
-    frcnn_gather_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(f.keys, f.boxes, params->pre_nms_top_n, (int)K, f.sorted, f.counters);
-    OD_LAUNCH_CHECK("frcnn_gather_kernel");
+    frcnn_rank_gather_kernel<<<(unsigned)((total + kFrRankMine - 1) / kFrRankMine), kFrRankThreads, 0, st>>>(
+        f.keys, f.boxes, total, params->pre_nms_top_n, (int)K, f.sorted, f.counters);
+    OD_LAUNCH_CHECK("frcnn_rank_gather_kernel");
     const dim3 grid((unsigned)W, (unsigned)W, 1);
     frcnn_mask_kernel<<<grid, 64, 0, st>>>(f.sorted, f.counters, (int)K, W, params->nms_threshold, f.mask, f.diagT);
     OD_LAUNCH_CHECK("frcnn_mask_kernel");

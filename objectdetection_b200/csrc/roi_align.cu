@@ -15,7 +15,7 @@
 //      flag. The main loop then is table lookup + 4 unconditional 16-byte loads per output quad (2 quads,
 //      i.e. 8 loads in flight per thread), 3 lerps on packed fp32 pairs (FADD2) and one streaming
 //      16-byte store. No meta kernel, no per-call allocation.
-//   crop_pool2_rows_kernel (+ crop_meta_kernel) : FasterRCNN roi_pool = crop 14x14 fused with 2x2 max-pool.
+//   crop_pool_bins_kernel : FasterRCNN roi_pool = crop 14x14 fused with 2x2 max-pool, same scheme over pooled bins.
 #include "common.cuh"
 
 namespace od {
@@ -67,63 +67,15 @@ __device__ __forceinline__ void fill_grid(RoiMeta& m, float4 box, int32_t ph, in
   }
 }
 
-// Generic tf.image.crop_and_resize meta. frcnn != 0: boxes are [n,5] (batch,x1,y1,x2,y2) pixels divided by
-// (image_h, image_w) (fastrcnn.py:55-64).
-__global__ void crop_meta_kernel(const float* __restrict__ image, int32_t B, int32_t H, int32_t W, int32_t D,
-                                 const float* __restrict__ boxes, const int32_t* __restrict__ box_ind, int32_t n,
-                                 int32_t ph, int32_t pw, int32_t frcnn, float image_h, float image_w,
-                                 RoiMeta* __restrict__ meta) {
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 box;
-  int32_t b;
-  if (frcnn) {
-    const float* p = boxes + 5 * (int64_t)i;
-    b = (int32_t)p[0];
-    box = make_float4(p[2] / image_h, p[1] / image_w, p[4] / image_h, p[3] / image_w);
-  } else {
-    box = reinterpret_cast<const float4*>(boxes)[i];
-    b = box_ind[i];
-  }
-  RoiMeta m;
-  m.H = H;
-  m.W = W;
-  m.base = (b >= 0 && b < B) ? image + (int64_t)b * H * W * D : nullptr;
-  fill_grid(m, box, ph, pw);
-  meta[i] = m;
-}
-
-struct XSample {
-  int32_t left, right;
-  float lerp;
-  int32_t valid;
-};
-constexpr int kMaxPoolW = 64;
-constexpr int kCropThreads = 128;
-
-__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
-  return make_float4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t);
-}
 __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(f_max(a.x, b.x), f_max(a.y, b.y), f_max(a.z, b.z), f_max(a.w, b.w));
 }
 
-__device__ __forceinline__ void build_xsamples(const RoiMeta& m, int32_t pw, XSample* xs) {
-  for (int32_t x = threadIdx.x; x < pw; x += blockDim.x) {
-    const float in_x = m.in_x0 + (float)x * m.ws;
-    XSample s;
-    s.valid = (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
-    const float fl = floorf(in_x);
-    s.left = s.valid ? (int32_t)fl : 0;
-    s.right = s.valid ? (int32_t)ceilf(in_x) : 0;
-    s.lerp = in_x - fl;
-    xs[x] = s;
-  }
-}
-
 // ----------------------------------------------------------------------------- crop_bins_kernel
 // Where a ROI comes from: mode 0 = PyramidROIAlign (level from the box, batch = roi / rois_per_image),
-// mode 1 = tf.image.crop_and_resize (explicit box_ind, one image tensor in lt slot 0).
+// mode 1 = tf.image.crop_and_resize (explicit box_ind, one image tensor in lt slot 0),
+// mode 2 = FasterRCNN roi_pool: rows (batch, x1, y1, x2, y2) in pixels, divided by (image_h, image_w)
+//          (fastrcnn.py:55-64), one image tensor in lt slot 0.
 struct RoiSource {
   int32_t mode;
   int32_t rois_per_image;
@@ -132,6 +84,8 @@ struct RoiSource {
   LevelTable lt;
   const float4* boxes;
   const int32_t* box_ind;
+  const float* boxes5;
+  float fimage_h, fimage_w;
 };
 
 struct __align__(16) BinTaps {  // tap offsets from the image base, in 16-byte units
@@ -174,6 +128,68 @@ __device__ __forceinline__ float4 lerp4p(float4 a, float4 b, float t) {
   return r;
 }
 
+// One entry of a CTA's bin table: level assignment + crop_and_resize grid of ROI `roi`, sampled at bin (y, x) ->
+// base pointer | flag, the four tap offsets (16-byte units) and the two lerp weights.
+__device__ __forceinline__ void bin_table_entry(const RoiSource& src, int64_t roi, int32_t y, int32_t x, bool first_bin,
+                                                int32_t ph, int32_t pw, int32_t D4, int32_t* __restrict__ level_out,
+                                                BinTaps* tp_out, BinInfo* bi_out) {
+  float4 box;
+  RoiMeta m;
+  uintptr_t flag = kBinSample;
+  if (src.mode == 0) {
+    box = __ldg(&src.boxes[roi]);
+    const int32_t level = roi_level_of(box, src.image_h, src.image_w, src.min_level, src.min_level + src.num_levels - 1);
+    const int32_t l = level - src.min_level;
+    m.H = src.lt.H[l];
+    m.W = src.lt.W[l];
+    m.base = src.lt.ptr[l] + (roi / src.rois_per_image) * ((int64_t)m.H * m.W * D4 * 4);
+    if (level_out && first_bin) level_out[roi] = level;
+  } else {
+    int32_t b;
+    if (src.mode == 1) {
+      box = __ldg(&src.boxes[roi]);
+      b = __ldg(&src.box_ind[roi]);
+    } else {
+      const float* p = src.boxes5 + 5 * roi;
+      b = (int32_t)p[0];
+      box = make_float4(p[2] / src.fimage_h, p[1] / src.fimage_w, p[4] / src.fimage_h, p[3] / src.fimage_w);
+    }
+    m.H = src.lt.H[0];
+    m.W = src.lt.W[0];
+    if (b >= 0 && b < src.batch) {
+      m.base = src.lt.ptr[0] + (int64_t)b * ((int64_t)m.H * m.W * D4 * 4);
+    } else {  // box_ind out of range: TF skips the crop, the output rows are left untouched
+      m.base = src.lt.ptr[0];
+      flag = kBinSkip;
+    }
+  }
+  fill_grid(m, box, ph, pw);
+  const float in_y = m.in_y0 + (float)y * m.hs;
+  const float in_x = m.in_x0 + (float)x * m.ws;
+  const bool ok = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1)) && (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
+  BinTaps tp = {0u, 0u, 0u, 0u};
+  BinInfo bi;
+  bi.xl = 0.0f;
+  bi.yl = 0.0f;
+  if (ok) {
+    const float fy = floorf(in_y), fx = floorf(in_x);
+    const uint32_t top = (uint32_t)fy, bot = (uint32_t)ceilf(in_y);
+    const uint32_t left = (uint32_t)fx, right = (uint32_t)ceilf(in_x);
+    const uint32_t W = (uint32_t)m.W, d4 = (uint32_t)D4;
+    tp.tl = (top * W + left) * d4;
+    tp.tr = (top * W + right) * d4;
+    tp.bl = (bot * W + left) * d4;
+    tp.br = (bot * W + right) * d4;
+    bi.xl = in_x - fx;
+    bi.yl = in_y - fy;
+  } else if (flag == kBinSample) {
+    flag = kBinExtrapolate;
+  }
+  bi.base_flag = reinterpret_cast<uintptr_t>(m.base) | flag;
+  *tp_out = tp;
+  *bi_out = bi;
+}
+
 template <int BINS, int UNROLL, bool POW2>
 __global__ void __launch_bounds__(kBinThreads)
 crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_t ph, int32_t pw, int32_t D4,
@@ -188,53 +204,8 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
     const int64_t fb = bin0 + i;
     const int64_t roi = fb / bins_per_roi;
     const int32_t bin = (int32_t)(fb - roi * bins_per_roi);
-    const int32_t y = bin / pw, x = bin - y * pw;
-    const float4 box = __ldg(&src.boxes[roi]);
-    RoiMeta m;
-    uintptr_t flag = kBinSample;
-    if (src.mode == 0) {
-      const int32_t level = roi_level_of(box, src.image_h, src.image_w, src.min_level, src.min_level + src.num_levels - 1);
-      const int32_t l = level - src.min_level;
-      m.H = src.lt.H[l];
-      m.W = src.lt.W[l];
-      m.base = src.lt.ptr[l] + (roi / src.rois_per_image) * ((int64_t)m.H * m.W * D4 * 4);
-      if (level_out && bin == 0) level_out[roi] = level;
-    } else {
-      const int32_t b = __ldg(&src.box_ind[roi]);
-      m.H = src.lt.H[0];
-      m.W = src.lt.W[0];
-      if (b >= 0 && b < src.batch) {
-        m.base = src.lt.ptr[0] + (int64_t)b * ((int64_t)m.H * m.W * D4 * 4);
-      } else {  // box_ind out of range: TF skips the crop, the output rows are left untouched
-        m.base = src.lt.ptr[0];
-        flag = kBinSkip;
-      }
-    }
-    fill_grid(m, box, ph, pw);
-    const float in_y = m.in_y0 + (float)y * m.hs;
-    const float in_x = m.in_x0 + (float)x * m.ws;
-    const bool ok = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1)) && (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
-    BinTaps tp = {0u, 0u, 0u, 0u};
-    BinInfo bi;
-    bi.xl = 0.0f;
-    bi.yl = 0.0f;
-    if (ok) {
-      const float fy = floorf(in_y), fx = floorf(in_x);
-      const uint32_t top = (uint32_t)fy, bot = (uint32_t)ceilf(in_y);
-      const uint32_t left = (uint32_t)fx, right = (uint32_t)ceilf(in_x);
-      const uint32_t W = (uint32_t)m.W, d4 = (uint32_t)D4;
-      tp.tl = (top * W + left) * d4;
-      tp.tr = (top * W + right) * d4;
-      tp.bl = (bot * W + left) * d4;
-      tp.br = (bot * W + right) * d4;
-      bi.xl = in_x - fx;
-      bi.yl = in_y - fy;
-    } else if (flag == kBinSample) {
-      flag = kBinExtrapolate;
-    }
-    bi.base_flag = reinterpret_cast<uintptr_t>(m.base) | flag;
-    s_taps[i] = tp;
-    s_info[i] = bi;
+    const int32_t y = bin / pw;
+    bin_table_entry(src, roi, y, bin - y * pw, bin == 0, ph, pw, D4, level_out, &s_taps[i], &s_info[i]);
   }
   __syncthreads();
 
@@ -273,59 +244,59 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
   }
 }
 
-// FasterRCNN roi_pool: crop 14x14 (ph=pw=14 grid in meta) fused with max_pool 2x2/2 -> 7x7.
-// One CTA per (roi, pooled row). NOTE: a skipped crop (base == nullptr) leaves zeros in TF's
-// crop output; the pooled output is then zero as well.
-__global__ void __launch_bounds__(kCropThreads)
-crop_pool2_rows_kernel(const RoiMeta* __restrict__ meta, int32_t ph, int32_t pw, int32_t D4,
-                       float4* __restrict__ out) {
-  __shared__ XSample xs[kMaxPoolW];
-  const int32_t oh = ph / 2, ow = pw / 2;
-  const int64_t item = blockIdx.x;
-  const int64_t roi = item / oh;
-  const int32_t oy = (int32_t)(item - roi * oh);
-  const RoiMeta m = meta[roi];
-  float4* orow = out + (roi * oh + oy) * (int64_t)ow * D4;
-  const int32_t total = ow * D4;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (m.base == nullptr) {
-    for (int32_t e = threadIdx.x; e < total; e += kCropThreads) stg_cs_f4(orow + e, zero4);
-    return;
+// FasterRCNN roi_pool (fastrcnn.py:22-70): crop_and_resize to (2*oh) x (2*ow) fused with max_pool 2x2 / stride 2.
+// Same flat-bin scheme as crop_bins_kernel over the POOLED bins: a CTA owns kPoolBins pooled bins, its table has 4
+// entries (the 2x2 sub-bins) per pooled bin; per output quad a thread issues the 16 unconditional 16-byte loads of the
+// four sub-bins, blends each and takes the max in the visiting order (0,0),(0,1),(1,0),(1,1). Out-of-range samples
+// contribute the extrapolation value 0; a row whose batch index is out of range yields zeros.
+constexpr int kPoolBins = 32;
+__global__ void __launch_bounds__(kBinThreads)
+crop_pool_bins_kernel(RoiSource src, int64_t total_bins, int32_t oh, int32_t ow, int32_t D4, float4* __restrict__ out) {
+  __shared__ BinTaps s_taps[kPoolBins * 4];
+  __shared__ BinInfo s_info[kPoolBins * 4];
+  const int32_t t = threadIdx.x;
+  const int64_t bin0 = (int64_t)blockIdx.x * kPoolBins;
+  const int32_t nb = (int32_t)min((int64_t)kPoolBins, total_bins - bin0);
+  const int32_t bins_per_roi = oh * ow;
+  for (int32_t i = t; i < nb * 4; i += kBinThreads) {
+    const int64_t fb = bin0 + (i >> 2);
+    const int64_t roi = fb / bins_per_roi;
+    const int32_t ob = (int32_t)(fb - roi * bins_per_roi);
+    const int32_t oy = ob / ow, ox = ob - oy * ow;
+    bin_table_entry(src, roi, 2 * oy + ((i >> 1) & 1), 2 * ox + (i & 1), false, 2 * oh, 2 * ow, D4, nullptr, &s_taps[i], &s_info[i]);
   }
-  build_xsamples(m, pw, xs);
   __syncthreads();
-  int32_t top[2], bot[2], yok[2];
-  float yl[2];
+  const int32_t total = nb * D4;
+  float4* __restrict__ o = out + bin0 * D4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int32_t e = t; e < total; e += kBinThreads) {
+    const int32_t bin = e / D4;
+    const uint32_t c = (uint32_t)(e - bin * D4);
+    float4 tl[4], tr[4], bl[4], br[4];
+    float xl[4], yl[4];
+    uint32_t fl[4];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const float in_y = m.in_y0 + (float)(2 * oy + r) * m.hs;
-    yok[r] = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1));
-    const float fl = floorf(in_y);
-    top[r] = yok[r] ? (int32_t)fl : 0;
-    bot[r] = yok[r] ? (int32_t)ceilf(in_y) : 0;
-    yl[r] = in_y - fl;
-  }
-  const float4* __restrict__ img = reinterpret_cast<const float4*>(m.base);
-  for (int32_t e = threadIdx.x; e < total; e += kCropThreads) {
-    const int32_t ox = e / D4, c = e - ox * D4;
+    for (int q = 0; q < 4; ++q) {
+      const BinTaps tp = s_taps[bin * 4 + q];
+      const BinInfo bi = s_info[bin * 4 + q];
+      const float4* __restrict__ base = reinterpret_cast<const float4*>(bi.base_flag & ~(uintptr_t)15);
+      fl[q] = (uint32_t)(bi.base_flag & 3u);
+      xl[q] = bi.xl;
+      yl[q] = bi.yl;
+      tl[q] = ldg_f4(base + (tp.tl + c));
+      tr[q] = ldg_f4(base + (tp.tr + c));
+      bl[q] = ldg_f4(base + (tp.bl + c));
+      br[q] = ldg_f4(base + (tp.br + c));
+    }
     float4 v[4];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const XSample s = xs[2 * ox + q];
-        float4 val = zero4;  // extrapolation_value = 0 (fastrcnn.py:68 default)
-        if (yok[r] && s.valid) {
-          const float4* rt = img + (int64_t)top[r] * m.W * D4;
-          const float4* rb = img + (int64_t)bot[r] * m.W * D4;
-          const float4 t = lerp4(ldg_f4(rt + s.left * D4 + c), ldg_f4(rt + s.right * D4 + c), s.lerp);
-          const float4 b = lerp4(ldg_f4(rb + s.left * D4 + c), ldg_f4(rb + s.right * D4 + c), s.lerp);
-          val = lerp4(t, b, yl[r]);
-        }
-        v[r * 2 + q] = val;
-      }
-    // same visiting order as the oracle: (0,0),(0,1),(1,0),(1,1)
-    stg_cs_f4(orow + e, max4(max4(max4(v[0], v[1]), v[2]), v[3]));
+    for (int q = 0; q < 4; ++q) {
+      const float4 top = lerp4p(tl[q], tr[q], xl[q]);
+      const float4 bot = lerp4p(bl[q], br[q], xl[q]);
+      v[q] = lerp4p(top, bot, yl[q]);
+      if (fl[q] != (uint32_t)kBinSample) v[q] = zero4;
+    }
+    stg_cs_f4(o + e, max4(max4(max4(v[0], v[1]), v[2]), v[3]));
   }
 }
 
@@ -474,18 +445,23 @@ int od_roi_pool_forward(const DLTensor* feature_map, const DLTensor* proposals, 
   if (reinterpret_cast<uintptr_t>(dptr<float>(feature_map)) % 16 || reinterpret_cast<uintptr_t>(dptr<float>(out)) % 16)
     OD_FAIL(OD_ERR_LAYOUT, "feature_map/out must be 16-byte aligned");
   if (n == 0) return OD_OK;
-  RoiMeta* meta = nullptr;
-  OD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&meta), sizeof(RoiMeta) * (size_t)n, st));
-  crop_meta_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(
-      dptr<float>(feature_map), (int32_t)feature_map->shape[0], (int32_t)feature_map->shape[1],
-      (int32_t)feature_map->shape[2], (int32_t)D, dptr<float>(proposals), nullptr, (int32_t)n, 14, 14, 1, image_h,
-      image_w, meta);
-  OD_LAUNCH_CHECK("crop_meta_kernel");
-  crop_pool2_rows_kernel<<<(unsigned)(n * 7), kCropThreads, 0, st>>>(meta, 14, 14, (int32_t)(D / 4), dptr<float4>(out));
-  count_launches(1);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(meta, st);
-  if (e != cudaSuccess) OD_FAIL(OD_ERR_CUDA, "launch crop_pool2_rows_kernel: %s", cudaGetErrorString(e));
+  if ((int64_t)feature_map->shape[1] * feature_map->shape[2] * (D / 4) > 0xFFFFFFFFll)
+    OD_FAIL(OD_ERR_PARAM, "feature map exceeds 2^32 16-byte units per image");
+  RoiSource src;
+  memset(&src, 0, sizeof(src));
+  src.mode = 2;
+  src.batch = (int32_t)feature_map->shape[0];
+  src.lt.ptr[0] = dptr<float>(feature_map);
+  src.lt.H[0] = (int32_t)feature_map->shape[1];
+  src.lt.W[0] = (int32_t)feature_map->shape[2];
+  src.boxes5 = dptr<float>(proposals);
+  src.fimage_h = image_h;
+  src.fimage_w = image_w;
+  const int64_t total_bins = n * 49;
+  const int64_t grid = (total_bins + kPoolBins - 1) / kPoolBins;
+  if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many ROIs");
+  crop_pool_bins_kernel<<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, 7, 7, (int32_t)(D / 4), dptr<float4>(out));
+  OD_LAUNCH_CHECK("crop_pool_bins_kernel");
   return OD_OK;
 }
 
