@@ -81,7 +81,8 @@ constexpr int kFrRankTile = 1024;
 __global__ void __launch_bounds__(kFrRankThreads)
 frcnn_rank_gather_kernel(const Key128* __restrict__ keys, const double* __restrict__ boxes, int64_t total, int pre_n, int K,
                          double* __restrict__ sorted, int32_t* __restrict__ counters) {
-  __shared__ Key128 tile[kFrRankTile];
+  __shared__ unsigned long long tile_hi[kFrRankTile];   // score keys; the index half is only read on equal scores
+  __shared__ unsigned long long tile_lo[kFrRankTile];
   __shared__ int32_t partial[kFrRankThreads];
   constexpr int kParts = kFrRankThreads / kFrRankMine;
   const int64_t me = (int64_t)blockIdx.x * kFrRankMine + (threadIdx.x & (kFrRankMine - 1));
@@ -98,12 +99,18 @@ frcnn_rank_gather_kernel(const Key128* __restrict__ keys, const double* __restri
       Key128 z;
       z.hi = 0ull;
       z.lo = 0ull;
-      tile[i] = (t0 + i < total) ? keys[t0 + i] : z;
+      if (t0 + i < total) z = keys[t0 + i];
+      tile_hi[i] = z.hi;
+      tile_lo[i] = z.lo;
     }
     __syncthreads();
-    const Key128* tp = tile + part * (kFrRankTile / kParts);
+    const int j0 = part * (kFrRankTile / kParts);
 #pragma unroll 8
-    for (int j = 0; j < kFrRankTile / kParts; ++j) rank += key_less(mine, tp[j]) ? 1 : 0;
+    for (int j = j0; j < j0 + kFrRankTile / kParts; ++j) {
+      const unsigned long long h = tile_hi[j];
+      rank += (h > mine.hi) ? 1 : 0;
+      if (h == mine.hi) rank += (tile_lo[j] > mine.lo) ? 1 : 0;
+    }
   }
   partial[threadIdx.x] = rank;
   __syncthreads();
@@ -155,8 +162,11 @@ frcnn_mask_kernel(const double* __restrict__ boxes, const int32_t* __restrict__ 
         const double xx2 = d_min(my.x2, o.x2), yy2 = d_min(my.y2, o.y2);
         const double w = d_max(0.0, xx2 - xx1 + 1), h = d_max(0.0, yy2 - yy1 + 1);
         const double inter = w * h;
-        const double ovr = inter / (my.area + o.area - inter);
-        if (ovr >= thr) bits |= 1ull << jj;
+        // inter == 0 gives ovr = +-0 (or NaN for a zero union), never >= a positive threshold: skip the fp64 divide
+        if (inter != 0.0 || !(thr > 0.0)) {
+          const double ovr = inter / (my.area + o.area - inter);
+          if (ovr >= thr) bits |= 1ull << jj;
+        }
       }
     }
     mask[(int64_t)i * W + cb] = bits;

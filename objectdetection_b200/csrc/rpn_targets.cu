@@ -22,6 +22,8 @@ __device__ __forceinline__ double rpn_iou(const double* g, double g_area, double
   const double y1 = fmax(g[0], a0), y2 = fmin(g[2], a2);
   const double x1 = fmax(g[1], a1), x2 = fmin(g[3], a3);
   const double inter = fmax(x2 - x1, 0.0) * fmax(y2 - y1, 0.0);
+  // disjoint boxes: 0 / union is +-0 (the comparisons below treat both alike); skips the fp64 divide for ~99 % of pairs
+  if (inter == 0.0) return 0.0;
   const double uni = g_area + a_area - inter;
   return inter / uni;
 }
@@ -110,18 +112,19 @@ __global__ void rpn_label_best_kernel(const int32_t* __restrict__ gt_best, int G
   if (a >= 0) cls[(int64_t)b * A + a] = 1;
 }
 
-// Stable compaction of {i in [0,n) : pred(i)} by a 1024-thread CTA, 4 consecutive elements per thread and round;
+constexpr int kCompactItems = 8;
+// Stable compaction of {i in [0,n) : pred(i)} by a 1024-thread CTA, 8 consecutive elements per thread and round;
 // emit(i, rank) for every selected i; returns the count. scratch: 33 ints of shared memory.
 template <typename Pred, typename Emit>
-__device__ int cta_compact4(int n, Pred pred, Emit emit, int* scratch) {
+__device__ int cta_compact(int n, Pred pred, Emit emit, int* scratch) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int base = 0;
-  for (int t0 = 0; t0 < n; t0 += 4 * kRpnSubThreads) {
-    const int i0 = t0 + 4 * tid;
-    bool p[4];
+  for (int t0 = 0; t0 < n; t0 += kCompactItems * kRpnSubThreads) {
+    const int i0 = t0 + kCompactItems * tid;
+    bool p[kCompactItems];
     int cnt = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kCompactItems; ++u) {
       p[u] = (i0 + u < n) && pred(i0 + u);
       cnt += p[u] ? 1 : 0;
     }
@@ -145,7 +148,7 @@ __device__ int cta_compact4(int n, Pred pred, Emit emit, int* scratch) {
     __syncthreads();
     int r = base + (warp ? scratch[warp - 1] : 0) + incl - cnt;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < kCompactItems; ++u)
       if (p[u]) emit(i0 + u, r++);
     base += scratch[31];
     __syncthreads();
@@ -166,21 +169,21 @@ rpn_subsample_kernel(const double* __restrict__ anchors, int A, const double* __
   const int32_t* pp = perm_pos + (int64_t)b * A;
   const int32_t* pn = perm_neg + (int64_t)b * A;
   // positives: idx = where(cls == 1); drop `extra` of them (:242-247)
-  const int n_pos0 = cta_compact4(A, [&](int i) { return c[i] == 1; }, [&](int i, int r) { lst[r] = i; }, scratch);
+  const int n_pos0 = cta_compact(A, [&](int i) { return c[i] == 1; }, [&](int i, int r) { lst[r] = i; }, scratch);
   __syncthreads();
   const int extra_pos = n_pos0 - max_targets / 2;
   if (extra_pos > 0) {
-    cta_compact4(A, [&](int t) { const int q = pp[t]; return q >= 0 && q < n_pos0; },
+    cta_compact(A, [&](int t) { const int q = pp[t]; return q >= 0 && q < n_pos0; },
                  [&](int t, int r) { if (r < extra_pos) c[lst[pp[t]]] = 0; }, scratch);
     __syncthreads();
   }
   const int n_pos = extra_pos > 0 ? n_pos0 - extra_pos : n_pos0;
   // negatives: idx = where(cls == -1); keep max_targets - n_pos of them (:249-253)
-  const int n_neg0 = cta_compact4(A, [&](int i) { return c[i] == -1; }, [&](int i, int r) { lst[r] = i; }, scratch);
+  const int n_neg0 = cta_compact(A, [&](int i) { return c[i] == -1; }, [&](int i, int r) { lst[r] = i; }, scratch);
   __syncthreads();
   const int extra_neg = n_neg0 - (max_targets - n_pos);
   if (extra_neg > 0) {
-    cta_compact4(A, [&](int t) { const int q = pn[t]; return q >= 0 && q < n_neg0; },
+    cta_compact(A, [&](int t) { const int q = pn[t]; return q >= 0 && q < n_neg0; },
                  [&](int t, int r) { if (r < extra_neg) c[lst[pn[t]]] = 0; }, scratch);
     __syncthreads();
   }
@@ -192,7 +195,7 @@ rpn_subsample_kernel(const double* __restrict__ anchors, int A, const double* __
     pa[i] = 0.0;
   }
   __syncthreads();
-  cta_compact4(A, [&](int i) { return c[i] == 1; },
+  cta_compact(A, [&](int i) { return c[i] == 1; },
                [&](int i, int r) {
                  if (r >= max_targets) return;
                  const double* an = anchors + 4 * (int64_t)i;
