@@ -417,6 +417,14 @@ def run_ours(args):
         for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             print(f"{us / 4:9.1f} us/step  x{cnt / 4:4.1f}  {name}", file=sys.stderr)
         print(f"{tot:9.1f} us/step  total kernel time", file=sys.stderr)
+        seq = sorted([ev for ev in prof.events() if ev.device_type is not None and "cuda" in str(ev.device_type).lower()],
+                     key=lambda ev: ev.time_range.start)
+        per_step = len(seq) // 4
+        print("  -- launch order, last profiled step (start offset us, duration us) --", file=sys.stderr)
+        t0 = seq[-per_step].time_range.start
+        for ev in seq[-per_step:]:
+            dur = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+            print(f"  +{ev.time_range.start - t0:8.1f}  {dur:7.1f}  {ev.name[:60]}", file=sys.stderr)
 
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)

@@ -14,7 +14,7 @@ import torch
 from torch.utils.dlpack import to_dlpack
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libodhead.so")
+LIB_PATH = os.environ.get("ODHEAD_LIB") or os.path.join(_HERE, "libodhead.so")   # ODHEAD_LIB: A/B a second build
 
 OD_MAX_LEVELS = 8
 OD_MAX_RATIOS = 8

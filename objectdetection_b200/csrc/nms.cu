@@ -1,26 +1,25 @@
 // nms.cu — greedy hard NMS with tf.image.non_max_suppression semantics as a bitmask-IoU kernel
 // plus a single-CTA keep scan. Call sites replaced: proposals_tf.py:234, detection.py:177.
 //
-//   mask kernel : 64x64 IoU tiles over the upper triangle; a CTA owns 64 rows x 4 column tiles whose canonical boxes
-//                 sit in shared memory; a thread owns row i and builds the 64-bit words "which later boxes j does
-//                 i suppress" of two tiles. The
-//                 pair test is TF's IoU in TF's operation order, but the IEEE division only runs when the
-//                 intersection is positive (inter == 0 gives IoU 0 or NaN, never > thr for thr >= 0), which
-//                 is the rare case. Diagonal tiles also emit their transpose with warp ballots (word j =
-//                 which earlier boxes of the tile suppress j) for the scan.
+//   mask layout : tile-major. With W = ceil(K/64), tile (rb, cb), cb > rb, is 64 consecutive 64-bit words at
+//                 ((rb*W + cb)*64): word r = "which boxes of column chunk cb does box rb*64+r suppress". The diagonal
+//                 tile (rb, rb) holds the TRANSPOSE instead (word j = which earlier boxes of the chunk suppress box j),
+//                 which is what the scan needs. All the data of row chunk c - tiles (c, c..W-1) - is one contiguous
+//                 span of (W-c)*512 bytes.
+//   mask kernel : a CTA owns 64 rows x 4 column tiles whose canonical boxes sit in shared memory; a thread owns row i
+//                 and builds the words of two tiles. Pass 1 is branch-free: a pair is a candidate iff four fp32
+//                 differences are all negative (sign-bit AND, one funnel shift per pair). Pass 2 evaluates the exact
+//                 TF IoU (TF's operation order, IEEE division, `> thr`) for the candidates only.
 //   scan kernel : one CTA per image walks the 64-box chunks in order. Inside a chunk the greedy recurrence
-//                 kept_j = cand_j && !(sup_j & kept) is solved by warp-ballot fixed-point iteration (bit j is
-//                 final after j+1 rounds; typically 2-4 rounds), then the mask rows of the kept boxes are
-//                 OR-ed into the running `removed` bitmap in shared memory. The 64 mask rows of chunk c+1
-//                 and its transposed diagonal tile are prefetched (cp.async into a double buffer / registers)
-//                 while chunk c is resolved, so the per-chunk critical path never waits on L2. Stops as soon
-//                 as max_out boxes are kept.
+//                 kept_j = cand_j && !(sup_j & kept) is solved by warp-ballot fixed-point iteration (bit j is final
+//                 after j+1 rounds; typically 2-4 rounds), then the rows of the kept boxes are OR-ed into the running
+//                 `removed` bitmap (one warp per word, lanes = rows, REDUX.OR). The span of chunk c + nslots - 1
+//                 arrives through ONE cp.async.bulk (TMA) into a shared-memory ring, completion counted in bytes on
+//                 an mbarrier per slot, while chunk c is resolved. Stops as soon as max_out boxes are kept.
 #include "nms.cuh"
 #include "topk.cuh"
 
 namespace od {
-
-constexpr int kScanThreads = 512;
 
 constexpr int kMaskColTiles = 4;   // column tiles (of 64 boxes) per CTA
 constexpr int kMaskThreads = 128;  // 64 rows x 2 halves; half h owns column tiles h, h+2 of the CTA's span
@@ -28,8 +27,7 @@ constexpr int kMaskThreads = 128;  // 64 rows x 2 halves; half h owns column til
 template <bool FAST>  // FAST: thr >= 0, division skipped when the intersection is not positive
 __global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ num_valid,
-                const int32_t* __restrict__ group, int K, int W, int Ws, float thr,
-                unsigned long long* __restrict__ mask, uint32_t* __restrict__ diagT) {
+                const int32_t* __restrict__ group, int K, int W, float thr, unsigned long long* __restrict__ mask) {
   const int rb = blockIdx.y, b = blockIdx.z;
   const int cb0 = rb + blockIdx.x * kMaskColTiles;
   const int n = num_valid ? min(num_valid[b], K) : K;
@@ -109,10 +107,12 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
     }
     if (cb == rb) bits &= (r == 63) ? 0ull : ~((2ull << r) - 1ull);   // only j > i
     if (!row_ok) bits = 0ull;
-    if (row_ok) mask[((int64_t)b * K + i) * Ws + cb] = bits;
-    if (cb == rb) {
-      // transpose of the diagonal tile: word jj, bit r = "box r of this chunk suppresses box jj"
-      uint32_t* dt = diagT + ((int64_t)b * W + cb) * 128;
+    unsigned long long* otile = mask + (((int64_t)b * W + rb) * W + cb) * 64;
+    if (cb != rb) {
+      otile[r] = bits;   // rows beyond n write zeros: the scan may read them (masked by its kept bits) but never garbage
+    } else {
+      // diagonal tile, stored transposed: word jj, bit r = "box r of this chunk suppresses box jj"
+      uint32_t* dt = reinterpret_cast<uint32_t*>(otile);
       const int warp = (t >> 5) & 1, lane = t & 31;
 #pragma unroll 8
       for (int jj = 0; jj < 64; ++jj) {
@@ -123,79 +123,88 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
   }
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+// ---- mbarrier / bulk-copy (TMA) helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
-// NBUF >= 2: staged scan — Ws is even and NBUF buffers of (64 mask rows + the transposed diagonal tile) fit in shared
-// memory; chunk c+NBUF-1 is prefetched with cp.async while chunk c is resolved. NBUF == 0: direct global loads.
-template <int NBUF>
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanMaxSlots = 8;
+
+// STAGED: nslots >= 2 spans of W*512 bytes fit in shared memory (K <= ~12800); otherwise the tiles are read from
+// global memory (L2) with 8 words in flight per warp.
+template <bool STAGED>
 __global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __restrict__ diagT,
-                const int32_t* __restrict__ num_valid, int K, int W, int Ws, int max_out, int32_t* __restrict__ keep_pos,
-                int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
-  constexpr bool STAGED = NBUF >= 2;
-  constexpr int DIST = STAGED ? NBUF - 1 : 1;
-  extern __shared__ __align__(16) unsigned long long smem_u64[];
-  unsigned long long* removed = smem_u64;       // [Ws]
-  unsigned long long* stage = smem_u64 + Ws;    // [NBUF][64*Ws + 64] when STAGED
-  const size_t buf_words = (size_t)64 * Ws + 64;
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __restrict__ num_valid, int K, int W, int nslots,
+                int max_out, int32_t* __restrict__ keep_pos, int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
+  extern __shared__ __align__(128) unsigned long long smem_u64[];
+  const int Wr = (W + 15) & ~15;                 // keeps the ring 128-byte aligned
+  unsigned long long* removed = smem_u64;        // [Wr]
+  unsigned long long* stage = smem_u64 + Wr;     // [nslots][W*64] when STAGED
+  const size_t slot_words = (size_t)W * 64;
+  __shared__ __align__(8) unsigned long long full_bar[kScanMaxSlots];
   __shared__ unsigned long long kept_word;
   const int b = blockIdx.x;
   const int n = num_valid ? min(num_valid[b], K) : K;
   const int Wn = (n + 63) / 64;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int w = tid; w < Ws; w += kScanThreads) removed[w] = 0ull;
+  for (int w = tid; w < Wr; w += kScanThreads) removed[w] = 0ull;
   if (keep_flag)
     for (int i = tid; i < K; i += kScanThreads) keep_flag[(int64_t)b * K + i] = 0;
-  int kept_total = 0;
-  const unsigned long long* mrow = mask + (int64_t)b * K * Ws;
-  const uint32_t* dbase = diagT + (int64_t)b * W * 128;
-
-  // chunk c -> stage[c % NBUF]: its 64 mask rows, 16-byte units [(c+1)/2, ceil(Wn/2)), and its diagonal tile
-  auto prefetch = [&](int c) {
-    if (STAGED && c < Wn) {
-      unsigned long long* dst = stage + (size_t)(c % (STAGED ? NBUF : 1)) * buf_words;
-      const int u0 = (c + 1) >> 1, u1 = (Wn + 1) >> 1;
-      const int r = tid >> 3;
-      const int row = c * 64 + r;
-      if (row < n)
-        for (int u = u0 + (tid & 7); u < u1; u += 8)
-          cp_async16(dst + (size_t)r * Ws + 2 * u, mrow + (size_t)row * Ws + 2 * u);
-      if (tid < 32) cp_async16(dst + (size_t)64 * Ws + 2 * tid, dbase + (size_t)c * 128 + 4 * tid);
-    }
-    cp_async_commit();
-  };
-  unsigned long long sup0 = 0ull, sup1 = 0ull;   // !STAGED: warp 0 holds the diagonal tile of the current chunk
-  auto load_diag = [&](int c, unsigned long long& s0, unsigned long long& s1) {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(dbase + (size_t)c * 128) + lane);
-    const uint2 d = __ldg(reinterpret_cast<const uint2*>(dbase + (size_t)c * 128) + lane + 32);
-    s0 = ((unsigned long long)a.y << 32) | a.x;
-    s1 = ((unsigned long long)d.y << 32) | d.x;
-  };
-  if (STAGED) {
-#pragma unroll
-    for (int c = 0; c < DIST; ++c) prefetch(c);
-  } else if (warp == 0 && Wn > 0) {
-    load_diag(0, sup0, sup1);
+  if (STAGED && tid == 0) {
+    for (int s = 0; s < nslots; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  __syncthreads();
+  const unsigned long long* mimg = mask + (int64_t)b * W * W * 64;
 
+  // thread 0 stages the span of chunk c (tiles (c, c..Wn-1), the first one being the transposed diagonal tile)
+  auto stage_chunk = [&](int c) {
+    if (STAGED && tid == 0 && c < Wn) {
+      unsigned long long* bar = &full_bar[c % nslots];
+      const uint32_t bytes = (uint32_t)(Wn - c) * 512u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(stage + (size_t)(c % nslots) * slot_words, mimg + ((size_t)c * W + c) * 64, bytes, bar);
+    }
+  };
+  if (STAGED)
+    for (int c = 0; c < nslots - 1; ++c) stage_chunk(c);
+
+  int kept_total = 0;
+  int c_waited = -1;
   for (int c = 0; c < Wn; ++c) {
-    if (STAGED) cp_async_wait<DIST - 1>();   // this thread's share of chunk c has landed
-    __syncthreads();                         // everyone's share; removed[c] is final; buffer (c-1)%NBUF is free
-    if (STAGED) prefetch(c + DIST);
-    unsigned long long nsup0 = 0ull, nsup1 = 0ull;
-    if (!STAGED && warp == 0 && c + 1 < Wn) load_diag(c + 1, nsup0, nsup1);
-    const unsigned long long* buf = stage + (size_t)(c % (STAGED ? NBUF : 1)) * buf_words;
+    if (STAGED) {
+      mbar_wait(&full_bar[c % nslots], (uint32_t)((c / nslots) & 1));   // the span of chunk c has landed
+      c_waited = c;
+    }
+    __syncthreads();   // removed[c] is final; slot (c-1) % nslots is free again
+    stage_chunk(c + nslots - 1);
+    const unsigned long long* span = STAGED ? stage + (size_t)(c % nslots) * slot_words : mimg + ((size_t)c * W + c) * 64;
     if (warp == 0) {
-      if (STAGED) {
-        sup0 = buf[(size_t)64 * Ws + lane];
-        sup1 = buf[(size_t)64 * Ws + lane + 32];
-      }
+      const unsigned long long sup0 = span[lane], sup1 = span[lane + 32];   // transposed diagonal tile
       const unsigned long long word = removed[c];
       const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
       const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
@@ -213,10 +222,6 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __r
       const int allow = max_out - kept_total;
       while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
       if (lane == 0) kept_word = kept;
-      if (!STAGED) {
-        sup0 = nsup0;
-        sup1 = nsup1;
-      }
     }
     __syncthreads();
     const unsigned long long kept = kept_word;
@@ -228,42 +233,48 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __r
       }
       kept_total += __popcll(kept);
       if (kept_total >= max_out) break;
-      // OR the rows of the kept boxes into removed[c+1 .. Wn)
+      // OR the rows of the kept boxes into removed[c+1 .. Wn): one warp per word, lanes = rows, REDUX.OR across lanes
+      const bool k0 = (kept >> lane) & 1ull, k1 = (kept >> (lane + 32)) & 1ull;
       if (STAGED) {
-        // 8 row groups x 64 word lanes, rows from shared memory (unconditional loads, select by kept bit)
-        const int rg = tid >> 6, wl = tid & 63;
-        const unsigned int kbits = (unsigned int)(kept >> (rg * 8)) & 0xFFu;
-        if (kbits)
-          for (int w = c + 1 + wl; w < Wn; w += 64) {
-            const unsigned long long* col = buf + (size_t)(rg * 8) * Ws + w;
-            unsigned long long acc = 0ull;
+        for (int w0 = c + 1 + warp; w0 < Wn; w0 += kScanWarps * 4) {   // 4 words per round: 8 LDS, then 8 REDUX
+          unsigned long long acc[4];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const unsigned long long v = col[(size_t)r * Ws];
-              acc |= ((kbits >> r) & 1u) ? v : 0ull;
-            }
-            if (acc) atomicOr(&removed[w], acc);
+          for (int u = 0; u < 4; ++u) {
+            const unsigned long long* tile = span + (size_t)(min(w0 + u * kScanWarps, Wn - 1) - c) * 64;
+            acc[u] = (k0 ? tile[lane] : 0ull) | (k1 ? tile[lane + 32] : 0ull);
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc[u]);
+            const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc[u] >> 32));
+            const int w = w0 + u * kScanWarps;
+            if (lane == 0 && w < Wn) removed[w] |= ((unsigned long long)hi << 32) | lo;
+          }
+        }
       } else {
-        // unconditional, fully pipelined global loads: 8 row groups x 64 word lanes
-        const int rg = tid >> 6, wl = tid & 63;
-        for (int w = c + 1 + wl; w < Wn; w += 64) {
-          unsigned long long v[8];
+        for (int w0 = c + 1 + warp * 8; w0 < Wn; w0 += kScanWarps * 8) {
+          unsigned long long acc[8];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int row = min(c * 64 + rg * 8 + r, K - 1);
-            v[r] = __ldg(&mrow[(size_t)row * Ws + w]);
+          for (int u = 0; u < 8; ++u) {   // 16 independent loads per lane
+            const unsigned long long* tile = span + (size_t)(min(w0 + u, Wn - 1) - c) * 64;
+            acc[u] = (k0 ? __ldg(&tile[lane]) : 0ull) | (k1 ? __ldg(&tile[lane + 32]) : 0ull);
           }
-          unsigned long long acc = 0ull;
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if ((kept >> (rg * 8 + r)) & 1ull) acc |= v[r];
-          if (acc) atomicOr(&removed[w], acc);
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc[u]);
+            const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc[u] >> 32));
+            if (lane == 0 && w0 + u < Wn) removed[w0 + u] |= ((unsigned long long)hi << 32) | lo;
+          }
         }
       }
     }
   }
-  if (STAGED) cp_async_wait<0>();
+  if (STAGED) {
+    // early exit: every bulk copy already issued (chunks < c_waited + nslots) must land before the CTA and its shared
+    // memory go away
+    for (int cc = c_waited + 1; cc < min(Wn, c_waited + nslots); ++cc)
+      mbar_wait(&full_bar[cc % nslots], (uint32_t)((cc / nslots) & 1));
+  }
   __syncthreads();
   if (keep_pos)
     for (int j = kept_total + tid; j < max_out; j += kScanThreads) keep_pos[(int64_t)b * max_out + j] = -1;
@@ -271,10 +282,9 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const uint32_t* __r
 }
 
 size_t nms_sorted_workspace_bytes(int64_t B, int64_t K) {
-  const int64_t W = (K + 63) / 64, Ws = nms_mask_stride(K);
+  const int64_t W = (K + 63) / 64;
   Workspace w(nullptr, 0);
-  w.take<unsigned long long>((size_t)(B * K * Ws));
-  w.take<uint32_t>((size_t)(B * W * 128));
+  w.take<unsigned long long>((size_t)(B * W * W * 64));
   return w.off + 256;
 }
 
@@ -284,46 +294,46 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
   if (B == 0) return OD_OK;
   if (B > 65535) OD_FAIL(OD_ERR_PARAM, "NMS batch %lld > 65535", (long long)B);
   if (K >= (1 << 22)) OD_FAIL(OD_ERR_PARAM, "NMS supports < 4M boxes per image");
-  const int W = (int)((K + 63) / 64), Ws = (int)nms_mask_stride(K);
+  const int W = (int)((K + 63) / 64);
   Workspace w(ws, ws_bytes);
-  unsigned long long* mask = w.take<unsigned long long>((size_t)(B * K * Ws));
-  uint32_t* diagT = w.take<uint32_t>((size_t)(B * W * 128));
+  unsigned long long* mask = w.take<unsigned long long>((size_t)(B * W * W * 64));
   if (!ws || !w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "NMS workspace %zu < %zu bytes", ws_bytes, w.off);
   if (K > 0) {
     if (W > 65535) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
     const dim3 grid((unsigned)((W + kMaskColTiles - 1) / kMaskColTiles), (unsigned)W, (unsigned)B);
     if (thr >= 0.0f)
-      nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
+      nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, thr, mask);
     else
-      nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, Ws, thr, mask, diagT);
+      nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, thr, mask);
     OD_LAUNCH_CHECK("nms_mask_kernel");
   }
-  return nms_scan_launch(mask, diagT, num_valid, B, K, Ws, max_out, keep_pos, num_kept, keep_flag, st);
+  return nms_scan_launch(mask, num_valid, B, K, max_out, keep_pos, num_kept, keep_flag, st);
 }
 
-int nms_scan_launch(const unsigned long long* mask, const uint32_t* diagT, const int32_t* num_valid, int64_t B,
-                    int64_t K, int64_t mask_stride, int64_t max_out, int32_t* keep_pos, int32_t* num_kept,
-                    int32_t* keep_flag, cudaStream_t st) {
-  const int W = (int)((K + 63) / 64), Ws = (int)mask_stride;
-  if (Ws < W) OD_FAIL(OD_ERR_PARAM, "NMS mask stride %d < %d words", Ws, W);
-  const size_t plain = (size_t)(Ws > 0 ? Ws : 1) * sizeof(unsigned long long);
-  const size_t per_buf = ((size_t)64 * Ws + 64) * sizeof(unsigned long long);
-  const bool aligned = (Ws % 2 == 0) && (reinterpret_cast<uintptr_t>(mask) % 16 == 0) &&
-                       (reinterpret_cast<uintptr_t>(diagT) % 16 == 0);
+int nms_scan_launch(const unsigned long long* mask, const int32_t* num_valid, int64_t B, int64_t K, int64_t max_out,
+                    int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag, cudaStream_t st) {
+  const int W = (int)((K + 63) / 64);
+  const size_t plain = (size_t)((W + 15) & ~15) * sizeof(unsigned long long);
+  const size_t per_slot = (size_t)W * 512;
   const size_t kSmemBudget = 200 * 1024;
-  const int nbuf = !aligned ? 0 : (plain + 3 * per_buf <= kSmemBudget ? 3 : (plain + 2 * per_buf <= kSmemBudget ? 2 : 0));
-  const size_t smem = plain + (size_t)nbuf * per_buf;
-#define OD_SCAN_LAUNCH(NB)                                                                                          \
-  do {                                                                                                              \
-    if (smem > 48 * 1024)                                                                                           \
-      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    nms_scan_kernel<NB><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, (int)max_out, \
-                                                                 keep_pos, num_kept, keep_flag);                    \
-  } while (0)
-  if (nbuf == 3) OD_SCAN_LAUNCH(3);
-  else if (nbuf == 2) OD_SCAN_LAUNCH(2);
-  else OD_SCAN_LAUNCH(0);
-#undef OD_SCAN_LAUNCH
+  int nslots = 0;
+  if (W > 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 && plain + 2 * per_slot <= kSmemBudget) {
+    nslots = (int)((kSmemBudget - plain) / per_slot);
+    if (nslots > kScanMaxSlots) nslots = kScanMaxSlots;
+  }
+  if (nslots >= 2) {
+    const size_t smem = plain + (size_t)nslots * per_slot;
+    if (smem > 48 * 1024)
+      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, nslots, (int)max_out, keep_pos,
+                                                                   num_kept, keep_flag);
+  } else {
+    const size_t smem = plain > 0 ? plain : 128;
+    if (smem > 48 * 1024)
+      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_kernel<false><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, 0, (int)max_out, keep_pos,
+                                                                    num_kept, keep_flag);
+  }
   OD_LAUNCH_CHECK("nms_scan_kernel");
   return OD_OK;
 }
