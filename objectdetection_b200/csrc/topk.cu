@@ -7,9 +7,9 @@
 // (12-bit digits) in three launches: a histogram pass over the leading digit (per-CTA shared-memory histograms ->
 // global atomics -> the last CTA of the row, found with a ticket counter, scans the 4096 buckets), a split pass
 // (keys above the threshold bucket are winners, keys inside it become candidates) and a one-CTA-per-row tail
-// that resolves the remaining digits over the candidates in shared memory. The k winners are then ordered by a
-// rank sort spread over the whole GPU (k <= 8192), a single-CTA shared-memory bitonic sort (k <= 16384) or a
-// global-memory bitonic sort above that.
+// that resolves the remaining digits over the candidates in shared memory. The k winners are then ordered by
+// 1024-key tile sorts (register/shuffle bitonic) plus a merge-rank kernel (binary search of every key in every other
+// sorted tile) for k <= 16384, or a global-memory bitonic sort above that.
 #include "topk.cuh"
 
 namespace od {
@@ -19,7 +19,6 @@ constexpr int kBins = 1 << kDigitBits;
 constexpr int kSelThreads = 256;
 constexpr int kSortThreads = 1024;
 constexpr int64_t kSmemSortMax = 16384;
-constexpr int64_t kRankSortMaxK = 8192;   // above this the k^2 rank sort loses to the bitonic networks
 
 struct __align__(16) SelState {
   unsigned long long prefix;  // determined high bits of the k-th key (low `shift` bits are zero)
@@ -74,26 +73,6 @@ topk_collect_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_
       base = __shfl_sync(0xffffffffu, base, 0);
       if (sel) out[base + __popc(ballot & ((1u << lane) - 1u))] = c;
     }
-  }
-}
-
-// One CTA per row: sort k keys (padded with 0 to n_pow2) descending in shared memory, emit indices / values.
-__global__ void __launch_bounds__(kSortThreads)
-topk_sort_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int64_t k, int n_pow2, int ib,
-                      const float* __restrict__ scores, int64_t row_stride, int64_t col_stride,
-                      int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
-  extern __shared__ unsigned long long skeys[];
-  const int row = blockIdx.x;
-  const unsigned long long* in = buf + (int64_t)row * buf_stride;
-  for (int i = threadIdx.x; i < n_pow2; i += kSortThreads) skeys[i] = (i < k) ? in[i] : 0ull;
-  __syncthreads();
-  block_bitonic_sort_desc(skeys, n_pow2);
-  const uint32_t imask = (1u << ib) - 1u;
-  const float* srow = scores + (int64_t)row * row_stride;
-  for (int i = threadIdx.x; i < k; i += kSortThreads) {
-    const uint32_t idx = imask - (uint32_t)(skeys[i] & imask);
-    idx_out[(int64_t)row * k + i] = (int32_t)idx;
-    if (val_out) val_out[(int64_t)row * k + i] = srow[(int64_t)idx * col_stride];
   }
 }
 
@@ -328,53 +307,72 @@ topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_str
   }
 }
 
-// Rank sort + emit: keys are unique, so the position of a key in descending order is the number of keys greater
-// than it. grid (ceil(k/16), rows); a CTA owns 16 keys, its 16 thread groups each count over a 16th of every
-// 1024-key tile staged in shared memory (k^2 compares spread over the whole GPU instead of one CTA's bitonic
-// network: 36 M compares per row at k = 6000).
-constexpr int kRankThreads = 256;
-constexpr int kRankMine = 16;
-constexpr int kRankTile = 1024;
-__global__ void __launch_bounds__(kRankThreads)
-topk_rank_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int k, int ib,
-                      const SelState* __restrict__ states, const float* __restrict__ scores, int64_t row_stride,
-                      int64_t col_stride, int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
-  __shared__ unsigned long long tile[kRankTile];
-  __shared__ int32_t partial[kRankThreads];
+// Tile sort + merge rank (k <= kMergeMaxK): (1) topk_tile_sort_kernel sorts every 1024-key tile of the winners in
+// shared memory (bitonic, one CTA per tile); (2) topk_merge_emit_kernel stages all sorted tiles of a row in shared
+// memory; the final position of a key is its position inside its own tile plus, for every other tile, the number of
+// keys greater than it, found by binary search: ~60 compares per key instead of k.
+constexpr int kTileKeys = 1024;
+constexpr int kTileSortThreads = kTileKeys;   // one key per thread, held in a register
+constexpr int kMergeThreads = 256;
+constexpr int64_t kMergeMaxK = 16384;
+
+// Bitonic network over 1024 keys, one per thread: partner distances below 32 are warp shuffles (40 of the 55 stages,
+// no barrier), the rest go through shared memory.
+__global__ void __launch_bounds__(kTileSortThreads)
+topk_tile_sort_kernel(unsigned long long* __restrict__ buf, int64_t buf_stride, int k) {
+  __shared__ unsigned long long skeys[kTileKeys];
+  const int row = blockIdx.y, t0 = blockIdx.x * kTileKeys, t = threadIdx.x;
+  unsigned long long* seg = buf + (int64_t)row * buf_stride + t0;
+  unsigned long long key = (t0 + t < k) ? seg[t] : 0ull;   // padding zeros sort last and stay out of the buffer
+  for (int kk = 2; kk <= kTileKeys; kk <<= 1) {
+    const bool desc = ((t & kk) == 0);
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      unsigned long long other;
+      if (j >= 32) {
+        skeys[t] = key;
+        __syncthreads();
+        other = skeys[t ^ j];
+        __syncthreads();
+      } else {
+        other = __shfl_xor_sync(0xffffffffu, key, j);
+      }
+      const bool keep_max = (((t & j) == 0) == desc);   // lower index of a descending pair keeps the larger key
+      key = keep_max ? (key > other ? key : other) : (key < other ? key : other);
+    }
+  }
+  if (t0 + t < k) seg[t] = key;
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+topk_merge_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int k, int ib,
+                       const float* __restrict__ scores, int64_t row_stride, int64_t col_stride,
+                       int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  extern __shared__ unsigned long long sk[];   // [k] the row's sorted tiles
   const int row = blockIdx.y;
   const unsigned long long* in = buf + (int64_t)row * buf_stride;
-  const int first = blockIdx.x * kRankMine;
-  const int me = first + (threadIdx.x & (kRankMine - 1));
-  constexpr int kParts = kRankThreads / kRankMine;
-  const int part = threadIdx.x / kRankMine;
-  const unsigned long long mine = (me < k) ? in[me] : ~0ull;
-  // buf[0, n1) holds keys that are all greater than buf[n1, k): a CTA whose keys lie on one side only counts there
-  const int n1 = states ? min((int)states[row].reserved, k) : k;
-  const int last = min(first + kRankMine, k) - 1;
-  int lo = 0, hi = k, rank = 0;
-  if (last < n1) hi = n1;
-  else if (first >= n1) {
-    lo = n1;
-    rank = (part == 0) ? n1 : 0;
-  }
-  for (int t0 = lo; t0 < hi; t0 += kRankTile) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kRankTile; i += kRankThreads) tile[i] = (t0 + i < hi) ? in[t0 + i] : 0ull;
-    __syncthreads();
-    const unsigned long long* tp = tile + part * (kRankTile / kParts);
-#pragma unroll 16
-    for (int j = 0; j < kRankTile / kParts; ++j) rank += (tp[j] > mine) ? 1 : 0;
-  }
-  partial[threadIdx.x] = rank;
+  for (int i = threadIdx.x; i < k; i += kMergeThreads) sk[i] = in[i];
   __syncthreads();
-  if (part == 0 && me < k) {
-#pragma unroll
-    for (int q = 1; q < kParts; ++q) rank += partial[threadIdx.x + q * kRankMine];
-    const uint32_t imask = (1u << ib) - 1u;
-    const uint32_t idx = imask - (uint32_t)(mine & imask);
-    idx_out[(int64_t)row * k + rank] = (int32_t)idx;
-    if (val_out) val_out[(int64_t)row * k + rank] = scores[(int64_t)row * row_stride + (int64_t)idx * col_stride];
+  const int me = blockIdx.x * kMergeThreads + threadIdx.x;
+  if (me >= k) return;
+  const unsigned long long mine = sk[me];
+  const int my_tile = me / kTileKeys;
+  int rank = me - my_tile * kTileKeys;   // keys ahead of me inside my (descending) tile
+  const int ntiles = (k + kTileKeys - 1) / kTileKeys;
+  for (int t = 0; t < ntiles; ++t) {
+    if (t == my_tile) continue;
+    const unsigned long long* tp = sk + t * kTileKeys;
+    int lo = 0, hi = min(kTileKeys, k - t * kTileKeys);   // first position whose key is not greater than mine
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (tp[mid] > mine) lo = mid + 1;
+      else hi = mid;
+    }
+    rank += lo;
   }
+  const uint32_t imask = (1u << ib) - 1u;
+  const uint32_t idx = imask - (uint32_t)(mine & imask);
+  idx_out[(int64_t)row * k + rank] = (int32_t)idx;
+  if (val_out) val_out[(int64_t)row * k + rank] = scores[(int64_t)row * row_stride + (int64_t)idx * col_stride];
 }
 
 // ---- generic descending sort of uint64 segments (shared-memory when it fits, global bitonic otherwise)
@@ -489,17 +487,16 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
     topk_tail_kernel<<<(unsigned)rows, kTailThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, n_pow2, cap, states, buf, cand);
     OD_LAUNCH_CHECK("topk_tail_kernel");
   }
-  if (k <= kRankSortMaxK) {
-    const dim3 g((unsigned)((k + kRankMine - 1) / kRankMine), (unsigned)rows);
-    topk_rank_emit_kernel<<<g, kRankThreads, 0, st>>>(buf, n_pow2, (int)k, ib, take_all ? nullptr : states, scores, row_stride,
-                                                     col_stride, idx_out, val_out);
-    OD_LAUNCH_CHECK("topk_rank_emit_kernel");
-  } else if (n_pow2 <= kSmemSortMax) {
-    const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
-    OD_CUDA(cudaFuncSetAttribute(topk_sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_sort_emit_kernel<<<(unsigned)rows, kSortThreads, smem, st>>>(buf, n_pow2, k, (int)n_pow2, ib, scores, row_stride,
-                                                                      col_stride, idx_out, val_out);
-    OD_LAUNCH_CHECK("topk_sort_emit_kernel");
+  if (k <= kMergeMaxK) {
+    const int ntiles = (int)((k + kTileKeys - 1) / kTileKeys);
+    topk_tile_sort_kernel<<<dim3((unsigned)ntiles, (unsigned)rows), kTileSortThreads, 0, st>>>(buf, n_pow2, (int)k);
+    OD_LAUNCH_CHECK("topk_tile_sort_kernel");
+    const size_t smem = (size_t)k * sizeof(unsigned long long);
+    if (smem > 48 * 1024)
+      OD_CUDA(cudaFuncSetAttribute(topk_merge_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_emit_kernel<<<dim3((unsigned)((k + kMergeThreads - 1) / kMergeThreads), (unsigned)rows), kMergeThreads, smem, st>>>(
+        buf, n_pow2, (int)k, ib, scores, row_stride, col_stride, idx_out, val_out);
+    OD_LAUNCH_CHECK("topk_merge_emit_kernel");
   } else {
     // zero the padding, sort in global memory, then emit
     for (int64_t r = 0; r < rows; ++r)
