@@ -27,11 +27,14 @@ constexpr int kMaskThreads = 128;  // 64 rows x 2 halves; half h owns column til
 template <bool FAST>  // FAST: thr >= 0, division skipped when the intersection is not positive
 __global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ num_valid,
-                const int32_t* __restrict__ group, int K, int W, float thr, unsigned long long* __restrict__ mask) {
-  const int rb = blockIdx.y, b = blockIdx.z;
+                const int32_t* __restrict__ group, int K, int W, int rb_begin, float thr, int max_out,
+                const int32_t* __restrict__ scan_state, int state_stride, unsigned long long* __restrict__ mask) {
+  const int rb = rb_begin + blockIdx.y, b = blockIdx.z;
   const int cb0 = rb + blockIdx.x * kMaskColTiles;
   const int n = num_valid ? min(num_valid[b], K) : K;
   if (cb0 * 64 >= n) return;  // rb <= cb0: nothing valid in this span
+  // second round of a two-round NMS: the first round's scan may already have kept max_out boxes
+  if (scan_state && scan_state[(int64_t)b * state_stride] >= max_out) return;
   __shared__ float4 cbox[kMaskColTiles * 64];   // canonical corners; boxes >= n are zero-area (never hit)
   __shared__ float carea[kMaskColTiles * 64];
   __shared__ int32_t cgrp[kMaskColTiles * 64];
@@ -158,7 +161,8 @@ constexpr int kScanMaxSlots = 8;
 template <bool STAGED>
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __restrict__ num_valid, int K, int W, int nslots,
-                int max_out, int32_t* __restrict__ keep_pos, int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
+                int max_out, int c_begin, int c_end, int final_round, int32_t* __restrict__ scan_state, int state_stride,
+                int32_t* __restrict__ keep_pos, int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
   extern __shared__ __align__(128) unsigned long long smem_u64[];
   const int Wr = (W + 15) & ~15;                 // keeps the ring 128-byte aligned
   unsigned long long* removed = smem_u64;        // [Wr]
@@ -170,9 +174,18 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
   const int n = num_valid ? min(num_valid[b], K) : K;
   const int Wn = (n + 63) / 64;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int w = tid; w < Wr; w += kScanThreads) removed[w] = 0ull;
-  if (keep_flag)
-    for (int i = tid; i < K; i += kScanThreads) keep_flag[(int64_t)b * K + i] = 0;
+  // scan_state (two-round NMS): [0] = boxes kept so far, then the `removed` bitmap as 2*Wr 32-bit halves
+  int32_t* state = scan_state ? scan_state + (int64_t)b * state_stride : nullptr;
+  const bool resume = state != nullptr && c_begin > 0;
+  const int c_last = min(c_end, Wn);
+  if (resume) {
+    const unsigned long long* sr = reinterpret_cast<const unsigned long long*>(state + 2);
+    for (int w = tid; w < Wr; w += kScanThreads) removed[w] = sr[w];
+  } else {
+    for (int w = tid; w < Wr; w += kScanThreads) removed[w] = 0ull;
+    if (keep_flag)
+      for (int i = tid; i < K; i += kScanThreads) keep_flag[(int64_t)b * K + i] = 0;
+  }
   if (STAGED && tid == 0) {
     for (int s = 0; s < nslots; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -181,28 +194,30 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
   __syncthreads();
   const unsigned long long* mimg = mask + (int64_t)b * W * W * 64;
 
+  int kept_total = resume ? state[0] : 0;
+  const int c_first = (kept_total >= max_out) ? c_last : c_begin;   // nothing left to do: skip the loop
   // thread 0 stages the span of chunk c (tiles (c, c..Wn-1), the first one being the transposed diagonal tile)
   auto stage_chunk = [&](int c) {
-    if (STAGED && tid == 0 && c < Wn) {
-      unsigned long long* bar = &full_bar[c % nslots];
+    if (STAGED && tid == 0 && c < c_last) {
+      unsigned long long* bar = &full_bar[(c - c_first) % nslots];
       const uint32_t bytes = (uint32_t)(Wn - c) * 512u;
       mbar_expect_tx(bar, bytes);
-      bulk_g2s(stage + (size_t)(c % nslots) * slot_words, mimg + ((size_t)c * W + c) * 64, bytes, bar);
+      bulk_g2s(stage + (size_t)((c - c_first) % nslots) * slot_words, mimg + ((size_t)c * W + c) * 64, bytes, bar);
     }
   };
   if (STAGED)
-    for (int c = 0; c < nslots - 1; ++c) stage_chunk(c);
+    for (int c = c_first; c < c_first + nslots - 1; ++c) stage_chunk(c);
 
-  int kept_total = 0;
-  int c_waited = -1;
-  for (int c = 0; c < Wn; ++c) {
+  int c_waited = c_first - 1;
+  for (int c = c_first; c < c_last; ++c) {
     if (STAGED) {
-      mbar_wait(&full_bar[c % nslots], (uint32_t)((c / nslots) & 1));   // the span of chunk c has landed
+      mbar_wait(&full_bar[(c - c_first) % nslots], (uint32_t)(((c - c_first) / nslots) & 1));   // the span of chunk c has landed
       c_waited = c;
     }
     __syncthreads();   // removed[c] is final; slot (c-1) % nslots is free again
     stage_chunk(c + nslots - 1);
-    const unsigned long long* span = STAGED ? stage + (size_t)(c % nslots) * slot_words : mimg + ((size_t)c * W + c) * 64;
+    const unsigned long long* span =
+        STAGED ? stage + (size_t)((c - c_first) % nslots) * slot_words : mimg + ((size_t)c * W + c) * 64;
     if (warp == 0) {
       const unsigned long long sup0 = span[lane], sup1 = span[lane + 32];   // transposed diagonal tile
       const unsigned long long word = removed[c];
@@ -272,20 +287,60 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
   if (STAGED) {
     // early exit: every bulk copy already issued (chunks < c_waited + nslots) must land before the CTA and its shared
     // memory go away
-    for (int cc = c_waited + 1; cc < min(Wn, c_waited + nslots); ++cc)
-      mbar_wait(&full_bar[cc % nslots], (uint32_t)((cc / nslots) & 1));
+    for (int cc = c_waited + 1; cc < min(c_last, c_waited + nslots); ++cc)
+      mbar_wait(&full_bar[(cc - c_first) % nslots], (uint32_t)(((cc - c_first) / nslots) & 1));
   }
   __syncthreads();
+  if (state) {   // carry over to (or report to) the next round
+    if (tid == 0) state[0] = kept_total;
+    unsigned long long* sr = reinterpret_cast<unsigned long long*>(state + 2);
+    for (int w = tid; w < Wr; w += kScanThreads) sr[w] = removed[w];
+  }
+  if (!final_round) return;
   if (keep_pos)
     for (int j = kept_total + tid; j < max_out; j += kScanThreads) keep_pos[(int64_t)b * max_out + j] = -1;
   if (num_kept && tid == 0) num_kept[b] = kept_total;
 }
 
+// int32 words of per-image scan state for the two-round NMS: kept count (+ pad) and the removed bitmap
+static int64_t scan_state_stride(int64_t W) { return 2 + 2 * ((W + 15) & ~(int64_t)15); }
+
 size_t nms_sorted_workspace_bytes(int64_t B, int64_t K) {
   const int64_t W = (K + 63) / 64;
   Workspace w(nullptr, 0);
   w.take<unsigned long long>((size_t)(B * W * W * 64));
+  w.take<unsigned long long>((size_t)(B * scan_state_stride(W) / 2 + 1));
   return w.off + 256;
+}
+
+static int scan_round_launch(const unsigned long long* mask, const int32_t* num_valid, int64_t B, int64_t K, int64_t max_out,
+                             int c_begin, int c_end, int final_round, int32_t* scan_state, int32_t* keep_pos,
+                             int32_t* num_kept, int32_t* keep_flag, cudaStream_t st) {
+  const int W = (int)((K + 63) / 64);
+  const size_t plain = (size_t)((W + 15) & ~15) * sizeof(unsigned long long);
+  const size_t per_slot = (size_t)W * 512;
+  const size_t kSmemBudget = 200 * 1024;
+  const int stride = (int)scan_state_stride(W);
+  int nslots = 0;
+  if (W > 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 && plain + 2 * per_slot <= kSmemBudget) {
+    nslots = (int)((kSmemBudget - plain) / per_slot);
+    if (nslots > kScanMaxSlots) nslots = kScanMaxSlots;
+  }
+  if (nslots >= 2) {
+    const size_t smem = plain + (size_t)nslots * per_slot;
+    if (smem > 48 * 1024)
+      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, nslots, (int)max_out, c_begin, c_end,
+                                                                   final_round, scan_state, stride, keep_pos, num_kept, keep_flag);
+  } else {
+    const size_t smem = plain > 0 ? plain : 128;
+    if (smem > 48 * 1024)
+      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_kernel<false><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, 0, (int)max_out, c_begin, c_end,
+                                                                    final_round, scan_state, stride, keep_pos, num_kept, keep_flag);
+  }
+  OD_LAUNCH_CHECK("nms_scan_kernel");
+  return OD_OK;
 }
 
 int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32_t* group, int64_t B, int64_t K,
@@ -297,45 +352,38 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
   const int W = (int)((K + 63) / 64);
   Workspace w(ws, ws_bytes);
   unsigned long long* mask = w.take<unsigned long long>((size_t)(B * W * W * 64));
+  int32_t* state = reinterpret_cast<int32_t*>(w.take<unsigned long long>((size_t)(B * scan_state_stride(W) / 2 + 1)));
   if (!ws || !w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "NMS workspace %zu < %zu bytes", ws_bytes, w.off);
-  if (K > 0) {
-    if (W > 65535) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
-    const dim3 grid((unsigned)((W + kMaskColTiles - 1) / kMaskColTiles), (unsigned)W, (unsigned)B);
+  if (K == 0) return scan_round_launch(mask, num_valid, B, K, max_out, 0, 0, 1, nullptr, keep_pos, num_kept, keep_flag, st);
+  if (W > 65535) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
+  // Two rounds when far fewer boxes are wanted than offered (proposals: 1000 of 6000): the first round covers the row
+  // chunks that normally suffice (1.5 x max_out boxes); the second one - the remaining rows - returns at once on the
+  // device if max_out boxes are already kept. Costs two nearly empty launches, saves up to ~55 % of the pair tests.
+  int c1 = (int)((max_out + max_out / 2 + 63) / 64);
+  const bool two_rounds = c1 + 8 <= W;
+  if (!two_rounds) c1 = W;
+  const int stride = (int)scan_state_stride(W);
+  for (int round = 0; round < (two_rounds ? 2 : 1); ++round) {
+    const int rb0 = round == 0 ? 0 : c1, rb1 = round == 0 ? c1 : W;
+    const dim3 grid((unsigned)((W - rb0 + kMaskColTiles - 1) / kMaskColTiles), (unsigned)(rb1 - rb0), (unsigned)B);
+    const int32_t* st_in = round == 0 ? nullptr : state;
     if (thr >= 0.0f)
-      nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, thr, mask);
+      nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
+                                                           stride, mask);
     else
-      nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, thr, mask);
+      nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
+                                                            stride, mask);
     OD_LAUNCH_CHECK("nms_mask_kernel");
+    OD_CHECK(scan_round_launch(mask, num_valid, B, K, max_out, rb0, rb1, round == (two_rounds ? 1 : 0), two_rounds ? state : nullptr,
+                               keep_pos, num_kept, keep_flag, st));
   }
-  return nms_scan_launch(mask, num_valid, B, K, max_out, keep_pos, num_kept, keep_flag, st);
+  return OD_OK;
 }
 
 int nms_scan_launch(const unsigned long long* mask, const int32_t* num_valid, int64_t B, int64_t K, int64_t max_out,
                     int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag, cudaStream_t st) {
   const int W = (int)((K + 63) / 64);
-  const size_t plain = (size_t)((W + 15) & ~15) * sizeof(unsigned long long);
-  const size_t per_slot = (size_t)W * 512;
-  const size_t kSmemBudget = 200 * 1024;
-  int nslots = 0;
-  if (W > 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 && plain + 2 * per_slot <= kSmemBudget) {
-    nslots = (int)((kSmemBudget - plain) / per_slot);
-    if (nslots > kScanMaxSlots) nslots = kScanMaxSlots;
-  }
-  if (nslots >= 2) {
-    const size_t smem = plain + (size_t)nslots * per_slot;
-    if (smem > 48 * 1024)
-      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, nslots, (int)max_out, keep_pos,
-                                                                   num_kept, keep_flag);
-  } else {
-    const size_t smem = plain > 0 ? plain : 128;
-    if (smem > 48 * 1024)
-      OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<false><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, 0, (int)max_out, keep_pos,
-                                                                    num_kept, keep_flag);
-  }
-  OD_LAUNCH_CHECK("nms_scan_kernel");
-  return OD_OK;
+  return scan_round_launch(mask, num_valid, B, K, max_out, 0, W, 1, nullptr, keep_pos, num_kept, keep_flag, st);
 }
 
 // ---- unsorted front-end (tf.image.non_max_suppression on arbitrary score order)
