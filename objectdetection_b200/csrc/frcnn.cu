@@ -137,8 +137,8 @@ __device__ __forceinline__ PBox load_pbox(const double* b) {
 
 // proposals.py:141-164 as 64x64 tiles (i = kept/earlier box, j = later box).
 __global__ void __launch_bounds__(64)
-frcnn_mask_kernel(const double* __restrict__ boxes, const int32_t* __restrict__ counters, int K, int W, double thr,
-                  unsigned long long* __restrict__ mask) {
+frcnn_mask_kernel(const double* __restrict__ boxes, const int32_t* __restrict__ counters, int K, int W, int Ws, double thr,
+                  unsigned long long* __restrict__ mask, unsigned long long* __restrict__ diagT) {
   const int cb = blockIdx.x, rb = blockIdx.y;
   if (cb < rb) return;
   const int n = min(counters[1], K);
@@ -169,12 +169,10 @@ frcnn_mask_kernel(const double* __restrict__ boxes, const int32_t* __restrict__ 
         }
       }
     }
+    if (cb != rb) mask[(int64_t)i * Ws + cb] = bits;
   }
-  unsigned long long* tile = mask + ((int64_t)rb * W + cb) * 64;   // tile-major layout of nms.cu
-  if (cb != rb) {
-    tile[t] = bits;
-  } else {
-    uint32_t* dt = reinterpret_cast<uint32_t*>(tile);                // diagonal tile: stored transposed
+  if (cb == rb) {
+    uint32_t* dt = reinterpret_cast<uint32_t*>(diagT + (int64_t)cb * 64);   // diagonal tile: stored transposed
     const int warp = t >> 5, lane = t & 31;
     for (int jj = 0; jj < 64; ++jj) {
       const uint32_t bal = __ballot_sync(0xffffffffu, (bits >> jj) & 1ull);
@@ -203,6 +201,7 @@ struct FrcnnWs {
   double* sorted;
   int32_t* keep_pos;
   unsigned long long* mask;
+  unsigned long long* diagT;
 };
 static size_t carve_frcnn_ws(Workspace& w, int64_t total, int64_t K, int64_t post_n, FrcnnWs* out) {
   FrcnnWs f;
@@ -213,7 +212,8 @@ static size_t carve_frcnn_ws(Workspace& w, int64_t total, int64_t K, int64_t pos
   f.boxes = w.take<double>((size_t)(4 * total));
   f.sorted = w.take<double>((size_t)(4 * K));
   f.keep_pos = w.take<int32_t>((size_t)post_n);
-  f.mask = w.take<unsigned long long>((size_t)(W * W * 64));
+  f.mask = w.take<unsigned long long>((size_t)(K * nms_mask_stride(K)));
+  f.diagT = w.take<unsigned long long>((size_t)(W * 64));
   if (out) *out = f;
   return w.off + 256;
 }
@@ -278,10 +278,11 @@ int od_frcnn_proposal_forward(const DLTensor* rpn_box_class_prob, const DLTensor
         f.keys, f.boxes, total, params->pre_nms_top_n, (int)K, f.sorted, f.counters);
     OD_LAUNCH_CHECK("frcnn_rank_gather_kernel");
     const dim3 grid((unsigned)W, (unsigned)W, 1);
-    frcnn_mask_kernel<<<grid, 64, 0, st>>>(f.sorted, f.counters, (int)K, W, params->nms_threshold, f.mask);
+    frcnn_mask_kernel<<<grid, 64, 0, st>>>(f.sorted, f.counters, (int)K, W, (int)nms_mask_stride(K), params->nms_threshold, f.mask,
+                                           f.diagT);
     OD_LAUNCH_CHECK("frcnn_mask_kernel");
   }
-  OD_CHECK(nms_scan_launch(f.mask, f.counters + 1, 1, K, post_n, f.keep_pos, f.counters + 2, nullptr, st));
+  OD_CHECK(nms_scan_launch(f.mask, f.diagT, f.counters + 1, 1, K, nms_mask_stride(K), post_n, f.keep_pos, f.counters + 2, nullptr, st));
   frcnn_emit_kernel<<<(unsigned)((post_n + 255) / 256), 256, 0, st>>>(f.sorted, f.keep_pos, f.counters + 2, (int)post_n,
                                                                      dptr<float>(proposals), dptr<int32_t>(num_out));
   OD_LAUNCH_CHECK("frcnn_emit_kernel");

@@ -1,20 +1,20 @@
 // nms.cu — greedy hard NMS with tf.image.non_max_suppression semantics as a bitmask-IoU kernel
 // plus a single-CTA keep scan. Call sites replaced: proposals_tf.py:234, detection.py:177.
 //
-//   mask layout : tile-major. With W = ceil(K/64), tile (rb, cb), cb > rb, is 64 consecutive 64-bit words at
-//                 ((rb*W + cb)*64): word r = "which boxes of column chunk cb does box rb*64+r suppress". The diagonal
-//                 tile (rb, rb) holds the TRANSPOSE instead (word j = which earlier boxes of the chunk suppress box j),
-//                 which is what the scan needs. All the data of row chunk c - tiles (c, c..W-1) - is one contiguous
-//                 span of (W-c)*512 bytes.
+//   mask layout : row-major words. With W = ceil(K/64) and Ws = W rounded up to even, word (i, w) at i*Ws + w says which
+//                 boxes of chunk w box i suppresses (only w > i/64 is read). The diagonal tiles are kept TRANSPOSED in
+//                 a second array diagT [W][64] (word j of chunk c = which earlier boxes of the chunk suppress box
+//                 c*64+j), which is what the scan needs. The 64 rows of chunk c are one contiguous span of 64*Ws words.
 //   mask kernel : a CTA owns 64 rows x 4 column tiles whose canonical boxes sit in shared memory; a thread owns row i
 //                 and builds the words of two tiles. Pass 1 is branch-free: a pair is a candidate iff four fp32
 //                 differences are all negative (sign-bit AND, one funnel shift per pair). Pass 2 evaluates the exact
 //                 TF IoU (TF's operation order, IEEE division, `> thr`) for the candidates only.
 //   scan kernel : one CTA per image walks the 64-box chunks in order. Inside a chunk the greedy recurrence
 //                 kept_j = cand_j && !(sup_j & kept) is solved by warp-ballot fixed-point iteration (bit j is final
-//                 after j+1 rounds; typically 2-4 rounds), then the rows of the kept boxes are OR-ed into the running
-//                 `removed` bitmap (one warp per word, lanes = rows, REDUX.OR). The span of chunk c + nslots - 1
-//                 arrives through ONE cp.async.bulk (TMA) into a shared-memory ring, completion counted in bytes on
+//                 after j+1 rounds; typically 2-4 rounds), then every later word of the `removed` bitmap is updated by
+//                 the ONE thread that owns it: it ORs that word of the kept rows (conflict-free shared-memory reads,
+//                 no atomics, no cross-lane reduction). The rows and the diagonal tile of chunk c + nslots - 1 arrive
+//                 through two cp.async.bulk (TMA) copies into a shared-memory ring, completion counted in bytes on
 //                 an mbarrier per slot, while chunk c is resolved. Stops as soon as max_out boxes are kept.
 #include "nms.cuh"
 #include "topk.cuh"
@@ -28,7 +28,8 @@ template <bool FAST>  // FAST: thr >= 0, division skipped when the intersection 
 __global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ num_valid,
                 const int32_t* __restrict__ group, int K, int W, int rb_begin, float thr, int max_out,
-                const int32_t* __restrict__ scan_state, int state_stride, unsigned long long* __restrict__ mask) {
+                const int32_t* __restrict__ scan_state, int state_stride, int Ws, unsigned long long* __restrict__ mask,
+                unsigned long long* __restrict__ diagT) {
   const int rb = rb_begin + blockIdx.y, b = blockIdx.z;
   const int cb0 = rb + blockIdx.x * kMaskColTiles;
   const int n = num_valid ? min(num_valid[b], K) : K;
@@ -110,12 +111,11 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
     }
     if (cb == rb) bits &= (r == 63) ? 0ull : ~((2ull << r) - 1ull);   // only j > i
     if (!row_ok) bits = 0ull;
-    unsigned long long* otile = mask + (((int64_t)b * W + rb) * W + cb) * 64;
     if (cb != rb) {
-      otile[r] = bits;   // rows beyond n write zeros: the scan may read them (masked by its kept bits) but never garbage
+      if (row_ok) mask[((int64_t)b * K + i) * Ws + cb] = bits;
     } else {
       // diagonal tile, stored transposed: word jj, bit r = "box r of this chunk suppresses box jj"
-      uint32_t* dt = reinterpret_cast<uint32_t*>(otile);
+      uint32_t* dt = reinterpret_cast<uint32_t*>(diagT + ((int64_t)b * W + cb) * 64);
       const int warp = (t >> 5) & 1, lane = t & 31;
 #pragma unroll 8
       for (int jj = 0; jj < 64; ++jj) {
@@ -156,18 +156,19 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanMaxSlots = 8;
 
-// STAGED: nslots >= 2 spans of W*512 bytes fit in shared memory (K <= ~12800); otherwise the tiles are read from
-// global memory (L2) with 8 words in flight per warp.
+// STAGED: nslots >= 2 ring slots of (64 rows x Ws words + the diagonal tile) fit in shared memory (K <= ~12000);
+// otherwise the rows are read from global memory (L2).
 template <bool STAGED>
 __global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __restrict__ num_valid, int K, int W, int nslots,
-                int max_out, int c_begin, int c_end, int final_round, int32_t* __restrict__ scan_state, int state_stride,
-                int32_t* __restrict__ keep_pos, int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long long* __restrict__ diagT,
+                const int32_t* __restrict__ num_valid, int K, int W, int Ws, int nslots, int max_out, int c_begin, int c_end,
+                int final_round, int32_t* __restrict__ scan_state, int state_stride, int32_t* __restrict__ keep_pos,
+                int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
   extern __shared__ __align__(128) unsigned long long smem_u64[];
   const int Wr = (W + 15) & ~15;                 // keeps the ring 128-byte aligned
-  unsigned long long* removed = smem_u64;        // [Wr]
-  unsigned long long* stage = smem_u64 + Wr;     // [nslots][W*64] when STAGED
-  const size_t slot_words = (size_t)W * 64;
+  unsigned long long* removed = smem_u64;        // [Wr]; word w is only ever written by thread w % kScanThreads
+  unsigned long long* stage = smem_u64 + Wr;     // [nslots][64*Ws + 64] when STAGED: rows of a chunk, then its diagonal tile
+  const size_t slot_words = (size_t)64 * Ws + 64;
   __shared__ __align__(8) unsigned long long full_bar[kScanMaxSlots];
   __shared__ unsigned long long kept_word;
   const int b = blockIdx.x;
@@ -192,17 +193,23 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const unsigned long long* mimg = mask + (int64_t)b * W * W * 64;
+  const unsigned long long* mrow = mask + (int64_t)b * K * Ws;
+  const unsigned long long* dimg = diagT + (int64_t)b * W * 64;
 
   int kept_total = resume ? state[0] : 0;
   const int c_first = (kept_total >= max_out) ? c_last : c_begin;   // nothing left to do: skip the loop
-  // thread 0 stages the span of chunk c (tiles (c, c..Wn-1), the first one being the transposed diagonal tile)
+  // One thread of the last warp (off the fixed point's critical path) stages chunk c into ring slot (c - c_first) %
+  // nslots with two bulk copies: its 64 mask rows (contiguous) and its transposed diagonal tile.
   auto stage_chunk = [&](int c) {
-    if (STAGED && tid == 0 && c < c_last) {
-      unsigned long long* bar = &full_bar[(c - c_first) % nslots];
-      const uint32_t bytes = (uint32_t)(Wn - c) * 512u;
-      mbar_expect_tx(bar, bytes);
-      bulk_g2s(stage + (size_t)((c - c_first) % nslots) * slot_words, mimg + ((size_t)c * W + c) * 64, bytes, bar);
+    if (STAGED && tid == kScanThreads - 32 && c < c_last) {
+      const int slot = (c - c_first) % nslots;
+      unsigned long long* bar = &full_bar[slot];
+      unsigned long long* dst = stage + (size_t)slot * slot_words;
+      const int rows = min(64, n - c * 64);
+      const uint32_t row_bytes = (uint32_t)rows * (uint32_t)Ws * 8u;
+      mbar_expect_tx(bar, row_bytes + 512u);
+      bulk_g2s(dst, mrow + (size_t)c * 64 * Ws, row_bytes, bar);
+      bulk_g2s(dst + (size_t)64 * Ws, dimg + (size_t)c * 64, 512u, bar);
     }
   };
   if (STAGED)
@@ -211,15 +218,15 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
   int c_waited = c_first - 1;
   for (int c = c_first; c < c_last; ++c) {
     if (STAGED) {
-      mbar_wait(&full_bar[(c - c_first) % nslots], (uint32_t)(((c - c_first) / nslots) & 1));   // the span of chunk c has landed
+      mbar_wait(&full_bar[(c - c_first) % nslots], (uint32_t)(((c - c_first) / nslots) & 1));   // chunk c has landed
       c_waited = c;
     }
     __syncthreads();   // removed[c] is final; slot (c-1) % nslots is free again
-    stage_chunk(c + nslots - 1);
-    const unsigned long long* span =
-        STAGED ? stage + (size_t)((c - c_first) % nslots) * slot_words : mimg + ((size_t)c * W + c) * 64;
+    const unsigned long long* rows =
+        STAGED ? stage + (size_t)((c - c_first) % nslots) * slot_words : mrow + (size_t)c * 64 * Ws;
     if (warp == 0) {
-      const unsigned long long sup0 = span[lane], sup1 = span[lane + 32];   // transposed diagonal tile
+      const unsigned long long* dt = STAGED ? rows + (size_t)64 * Ws : dimg + (size_t)c * 64;
+      const unsigned long long sup0 = dt[lane], sup1 = dt[lane + 32];   // transposed diagonal tile
       const unsigned long long word = removed[c];
       const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
       const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
@@ -239,6 +246,9 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
       if (lane == 0) kept_word = kept;
     }
     __syncthreads();
+    // (issuing the two bulk copies costs their thread ~1400 cycles: done here, next to the OR phase in which the last
+    //  warp is otherwise idle, and not between the two barriers where everybody would wait for it)
+    stage_chunk(c + nslots - 1);
     const unsigned long long kept = kept_word;
     if (kept != 0ull) {
       if (tid < 64 && ((kept >> tid) & 1ull)) {
@@ -248,39 +258,24 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
       }
       kept_total += __popcll(kept);
       if (kept_total >= max_out) break;
-      // OR the rows of the kept boxes into removed[c+1 .. Wn): one warp per word, lanes = rows, REDUX.OR across lanes
-      const bool k0 = (kept >> lane) & 1ull, k1 = (kept >> (lane + 32)) & 1ull;
-      if (STAGED) {
-        for (int w0 = c + 1 + warp; w0 < Wn; w0 += kScanWarps * 4) {   // 4 words per round: 8 LDS, then 8 REDUX
-          unsigned long long acc[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const unsigned long long* tile = span + (size_t)(min(w0 + u * kScanWarps, Wn - 1) - c) * 64;
-            acc[u] = (k0 ? tile[lane] : 0ull) | (k1 ? tile[lane + 32] : 0ull);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc[u]);
-            const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc[u] >> 32));
-            const int w = w0 + u * kScanWarps;
-            if (lane == 0 && w < Wn) removed[w] |= ((unsigned long long)hi << 32) | lo;
-          }
+      // removed[w] |= OR of word w over the kept rows, for every later word w; thread w % 256 owns word w. Rows beyond n
+      // are never kept, so their (unwritten) words are never selected.
+      const uint32_t klo = (uint32_t)kept, khi = (uint32_t)(kept >> 32);
+      for (int w = c + 1 + tid; w < Wn; w += kScanThreads) {
+        const unsigned long long* col = rows + w;
+        unsigned long long acc = 0ull;
+#pragma unroll 16
+        for (int r = 0; r < 32; ++r) {
+          const unsigned long long v = STAGED ? col[(size_t)r * Ws] : (((klo >> r) & 1u) ? __ldg(&col[(size_t)r * Ws]) : 0ull);
+          acc |= ((klo >> r) & 1u) ? v : 0ull;
         }
-      } else {
-        for (int w0 = c + 1 + warp * 8; w0 < Wn; w0 += kScanWarps * 8) {
-          unsigned long long acc[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {   // 16 independent loads per lane
-            const unsigned long long* tile = span + (size_t)(min(w0 + u, Wn - 1) - c) * 64;
-            acc[u] = (k0 ? __ldg(&tile[lane]) : 0ull) | (k1 ? __ldg(&tile[lane + 32]) : 0ull);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc[u]);
-            const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc[u] >> 32));
-            if (lane == 0 && w0 + u < Wn) removed[w0 + u] |= ((unsigned long long)hi << 32) | lo;
-          }
+#pragma unroll 16
+        for (int r = 0; r < 32; ++r) {
+          const unsigned long long v =
+              STAGED ? col[(size_t)(r + 32) * Ws] : (((khi >> r) & 1u) ? __ldg(&col[(size_t)(r + 32) * Ws]) : 0ull);
+          acc |= ((khi >> r) & 1u) ? v : 0ull;
         }
+        removed[w] |= acc;
       }
     }
   }
@@ -306,23 +301,27 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int32_t* __re
 static int64_t scan_state_stride(int64_t W) { return 2 + 2 * ((W + 15) & ~(int64_t)15); }
 
 size_t nms_sorted_workspace_bytes(int64_t B, int64_t K) {
-  const int64_t W = (K + 63) / 64;
+  const int64_t W = (K + 63) / 64, Ws = nms_mask_stride(K);
   Workspace w(nullptr, 0);
-  w.take<unsigned long long>((size_t)(B * W * W * 64));
+  w.take<unsigned long long>((size_t)(B * K * Ws));
+  w.take<unsigned long long>((size_t)(B * W * 64));
   w.take<unsigned long long>((size_t)(B * scan_state_stride(W) / 2 + 1));
   return w.off + 256;
 }
 
-static int scan_round_launch(const unsigned long long* mask, const int32_t* num_valid, int64_t B, int64_t K, int64_t max_out,
-                             int c_begin, int c_end, int final_round, int32_t* scan_state, int32_t* keep_pos,
-                             int32_t* num_kept, int32_t* keep_flag, cudaStream_t st) {
-  const int W = (int)((K + 63) / 64);
+static int scan_round_launch(const unsigned long long* mask, const unsigned long long* diagT, const int32_t* num_valid,
+                             int64_t B, int64_t K, int64_t mask_stride, int64_t max_out, int c_begin, int c_end,
+                             int final_round, int32_t* scan_state, int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag,
+                             cudaStream_t st) {
+  const int W = (int)((K + 63) / 64), Ws = (int)mask_stride;
+  if (Ws < W) OD_FAIL(OD_ERR_PARAM, "NMS mask stride %d < %d words", Ws, W);
   const size_t plain = (size_t)((W + 15) & ~15) * sizeof(unsigned long long);
-  const size_t per_slot = (size_t)W * 512;
+  const size_t per_slot = ((size_t)64 * Ws + 64) * sizeof(unsigned long long);
   const size_t kSmemBudget = 200 * 1024;
   const int stride = (int)scan_state_stride(W);
   int nslots = 0;
-  if (W > 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 && plain + 2 * per_slot <= kSmemBudget) {
+  if (W > 0 && Ws % 2 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 && reinterpret_cast<uintptr_t>(diagT) % 16 == 0 &&
+      plain + 2 * per_slot <= kSmemBudget) {
     nslots = (int)((kSmemBudget - plain) / per_slot);
     if (nslots > kScanMaxSlots) nslots = kScanMaxSlots;
   }
@@ -330,14 +329,16 @@ static int scan_round_launch(const unsigned long long* mask, const int32_t* num_
     const size_t smem = plain + (size_t)nslots * per_slot;
     if (smem > 48 * 1024)
       OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, nslots, (int)max_out, c_begin, c_end,
-                                                                   final_round, scan_state, stride, keep_pos, num_kept, keep_flag);
+    nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, nslots, (int)max_out,
+                                                                   c_begin, c_end, final_round, scan_state, stride, keep_pos,
+                                                                   num_kept, keep_flag);
   } else {
     const size_t smem = plain > 0 ? plain : 128;
     if (smem > 48 * 1024)
       OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<false><<<(unsigned)B, kScanThreads, smem, st>>>(mask, num_valid, (int)K, W, 0, (int)max_out, c_begin, c_end,
-                                                                    final_round, scan_state, stride, keep_pos, num_kept, keep_flag);
+    nms_scan_kernel<false><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, 0, (int)max_out, c_begin,
+                                                                    c_end, final_round, scan_state, stride, keep_pos, num_kept,
+                                                                    keep_flag);
   }
   OD_LAUNCH_CHECK("nms_scan_kernel");
   return OD_OK;
@@ -349,12 +350,14 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
   if (B == 0) return OD_OK;
   if (B > 65535) OD_FAIL(OD_ERR_PARAM, "NMS batch %lld > 65535", (long long)B);
   if (K >= (1 << 22)) OD_FAIL(OD_ERR_PARAM, "NMS supports < 4M boxes per image");
-  const int W = (int)((K + 63) / 64);
+  const int W = (int)((K + 63) / 64), Ws = (int)nms_mask_stride(K);
   Workspace w(ws, ws_bytes);
-  unsigned long long* mask = w.take<unsigned long long>((size_t)(B * W * W * 64));
+  unsigned long long* mask = w.take<unsigned long long>((size_t)(B * K * Ws));
+  unsigned long long* diagT = w.take<unsigned long long>((size_t)(B * W * 64));
   int32_t* state = reinterpret_cast<int32_t*>(w.take<unsigned long long>((size_t)(B * scan_state_stride(W) / 2 + 1)));
   if (!ws || !w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "NMS workspace %zu < %zu bytes", ws_bytes, w.off);
-  if (K == 0) return scan_round_launch(mask, num_valid, B, K, max_out, 0, 0, 1, nullptr, keep_pos, num_kept, keep_flag, st);
+  if (K == 0)
+    return scan_round_launch(mask, diagT, num_valid, B, K, Ws, max_out, 0, 0, 1, nullptr, keep_pos, num_kept, keep_flag, st);
   if (W > 65535) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
   // Two rounds when far fewer boxes are wanted than offered (proposals: 1000 of 6000): the first round covers the row
   // chunks that normally suffice (1.5 x max_out boxes); the second one - the remaining rows - returns at once on the
@@ -369,21 +372,23 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
     const int32_t* st_in = round == 0 ? nullptr : state;
     if (thr >= 0.0f)
       nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
-                                                           stride, mask);
+                                                           stride, Ws, mask, diagT);
     else
       nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
-                                                            stride, mask);
+                                                            stride, Ws, mask, diagT);
     OD_LAUNCH_CHECK("nms_mask_kernel");
-    OD_CHECK(scan_round_launch(mask, num_valid, B, K, max_out, rb0, rb1, round == (two_rounds ? 1 : 0), two_rounds ? state : nullptr,
-                               keep_pos, num_kept, keep_flag, st));
+    OD_CHECK(scan_round_launch(mask, diagT, num_valid, B, K, Ws, max_out, rb0, rb1, round == (two_rounds ? 1 : 0),
+                               two_rounds ? state : nullptr, keep_pos, num_kept, keep_flag, st));
   }
   return OD_OK;
 }
 
-int nms_scan_launch(const unsigned long long* mask, const int32_t* num_valid, int64_t B, int64_t K, int64_t max_out,
-                    int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag, cudaStream_t st) {
+int nms_scan_launch(const unsigned long long* mask, const unsigned long long* diagT, const int32_t* num_valid, int64_t B,
+                    int64_t K, int64_t mask_stride, int64_t max_out, int32_t* keep_pos, int32_t* num_kept,
+                    int32_t* keep_flag, cudaStream_t st) {
   const int W = (int)((K + 63) / 64);
-  return scan_round_launch(mask, num_valid, B, K, max_out, 0, W, 1, nullptr, keep_pos, num_kept, keep_flag, st);
+  return scan_round_launch(mask, diagT, num_valid, B, K, mask_stride, max_out, 0, W, 1, nullptr, keep_pos, num_kept,
+                           keep_flag, st);
 }
 
 // ---- unsorted front-end (tf.image.non_max_suppression on arbitrary score order)

@@ -4,6 +4,10 @@
 
 namespace od {
 
+// Row stride (in 64-bit words) of the suppression bitmask for K boxes: ceil(K/64) rounded up to even, so that every
+// mask row is 16-byte aligned (bulk-copy staging in the scan).
+inline int64_t nms_mask_stride(int64_t K) { return (((K + 63) / 64) + 1) & ~(int64_t)1; }
+
 // Workspace for nms_sorted_launch (mask + transposed diagonal blocks).
 size_t nms_sorted_workspace_bytes(int64_t batch, int64_t K);
 
@@ -18,12 +22,12 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
                       float thr, int64_t max_out, int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag,
                       void* ws, size_t ws_bytes, cudaStream_t st);
 
-// The keep scan alone, over a precomputed suppression bitmask in the tile-major layout of nms.cu: with
-// W = ceil(K/64), tile (rb, cb), cb > rb, is 64 consecutive words at ((b*W + rb)*W + cb)*64 (word r = which boxes of
-// chunk cb does box rb*64+r suppress); the diagonal tile (rb, rb) holds the transpose (word j = which earlier boxes of
-// the chunk suppress box rb*64+j). Tiles with cb < rb are never read. Rows/columns beyond num_valid must be zero or
-// unwritten-but-masked: the scan only ORs rows of kept boxes.
-int nms_scan_launch(const unsigned long long* mask, const int32_t* num_valid, int64_t B, int64_t K, int64_t max_out,
-                    int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag, cudaStream_t st);
+// The keep scan alone, over a precomputed suppression bitmask:
+//   mask  [B,K,mask_stride] (mask_stride >= W = ceil(K/64), even for the staged path): word (i,w) bit j = box i
+//         suppresses box w*64+j (only w > i/64 is read; rows beyond num_valid are never read into a result)
+//   diagT [B,W,64]: transposed diagonal tiles (word j of chunk c, bit t: box c*64+t suppresses box c*64+j, t < j)
+int nms_scan_launch(const unsigned long long* mask, const unsigned long long* diagT, const int32_t* num_valid, int64_t B,
+                    int64_t K, int64_t mask_stride, int64_t max_out, int32_t* keep_pos, int32_t* num_kept,
+                    int32_t* keep_flag, cudaStream_t st);
 
 }  // namespace od
