@@ -12,8 +12,8 @@
 //   scan kernel : one CTA per image walks the 64-box chunks in order. Inside a chunk the greedy recurrence
 //                 kept_j = cand_j && !(sup_j & kept) is solved by warp-ballot fixed-point iteration (bit j is final
 //                 after j+1 rounds; typically 2-4 rounds), then every later word of the `removed` bitmap is updated by
-//                 the ONE thread that owns it: it ORs that word of the kept rows (conflict-free shared-memory reads,
-//                 no atomics, no cross-lane reduction). The rows and the diagonal tile of chunk c + nslots - 1 arrive
+//                 two threads (one per half of the chunk's rows): each ORs that word of its kept rows (conflict-free
+//                 shared-memory reads, no cross-lane reduction, one atomicOr). The rows and the diagonal tile of chunk c + nslots - 1 arrive
 //                 through two cp.async.bulk (TMA) copies into a shared-memory ring, completion counted in bytes on
 //                 an mbarrier per slot, while chunk c is resolved. Stops as soon as max_out boxes are kept.
 #include "nms.cuh"
@@ -166,7 +166,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
                 int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
   extern __shared__ __align__(128) unsigned long long smem_u64[];
   const int Wr = (W + 15) & ~15;                 // keeps the ring 128-byte aligned
-  unsigned long long* removed = smem_u64;        // [Wr]; word w is only ever written by thread w % kScanThreads
+  unsigned long long* removed = smem_u64;        // [Wr]
   unsigned long long* stage = smem_u64 + Wr;     // [nslots][64*Ws + 64] when STAGED: rows of a chunk, then its diagonal tile
   const size_t slot_words = (size_t)64 * Ws + 64;
   __shared__ __align__(8) unsigned long long full_bar[kScanMaxSlots];
@@ -216,6 +216,11 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     for (int c = c_first; c < c_first + nslots - 1; ++c) stage_chunk(c);
 
   int c_waited = c_first - 1;
+  unsigned long long nsup0 = 0ull, nsup1 = 0ull;
+  if (!STAGED && warp == 0 && c_first < c_last) {
+    nsup0 = __ldg(&dimg[(size_t)c_first * 64 + lane]);
+    nsup1 = __ldg(&dimg[(size_t)c_first * 64 + lane + 32]);
+  }
   for (int c = c_first; c < c_last; ++c) {
     if (STAGED) {
       mbar_wait(&full_bar[(c - c_first) % nslots], (uint32_t)(((c - c_first) / nslots) & 1));   // chunk c has landed
@@ -225,8 +230,19 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     const unsigned long long* rows =
         STAGED ? stage + (size_t)((c - c_first) % nslots) * slot_words : mrow + (size_t)c * 64 * Ws;
     if (warp == 0) {
-      const unsigned long long* dt = STAGED ? rows + (size_t)64 * Ws : dimg + (size_t)c * 64;
-      const unsigned long long sup0 = dt[lane], sup1 = dt[lane + 32];   // transposed diagonal tile
+      unsigned long long sup0, sup1;   // transposed diagonal tile
+      if (STAGED) {
+        const unsigned long long* dt = rows + (size_t)64 * Ws;
+        sup0 = dt[lane];
+        sup1 = dt[lane + 32];
+      } else {   // global path: the tile of the next chunk is loaded one chunk ahead
+        sup0 = nsup0;
+        sup1 = nsup1;
+        if (c + 1 < c_last) {
+          nsup0 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane]);
+          nsup1 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane + 32]);
+        }
+      }
       const unsigned long long word = removed[c];
       const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
       const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
@@ -258,24 +274,46 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       }
       kept_total += __popcll(kept);
       if (kept_total >= max_out) break;
-      // removed[w] |= OR of word w over the kept rows, for every later word w; thread w % 256 owns word w. Rows beyond n
-      // are never kept, so their (unwritten) words are never selected.
-      const uint32_t klo = (uint32_t)kept, khi = (uint32_t)(kept >> 32);
-      for (int w = c + 1 + tid; w < Wn; w += kScanThreads) {
-        const unsigned long long* col = rows + w;
-        unsigned long long acc = 0ull;
+      // removed[w] |= OR of word w over the kept rows, for every later word w: two threads per word (rows 0-31 / 32-63,
+      // in different warps), conflict-free shared-memory reads, one 64-bit atomicOr each. Rows beyond n are never
+      // kept, so their (unwritten) words are never selected.
+      if (STAGED) {
+        const uint32_t kbits = (tid < kScanThreads / 2) ? (uint32_t)kept : (uint32_t)(kept >> 32);
+        const int r0 = (tid < kScanThreads / 2) ? 0 : 32;
+        if (kbits)
+          for (int w = c + 1 + (tid & (kScanThreads / 2 - 1)); w < Wn; w += kScanThreads / 2) {
+            const unsigned long long* col = rows + (size_t)r0 * Ws + w;
+            unsigned long long acc = 0ull;
 #pragma unroll 16
-        for (int r = 0; r < 32; ++r) {
-          const unsigned long long v = STAGED ? col[(size_t)r * Ws] : (((klo >> r) & 1u) ? __ldg(&col[(size_t)r * Ws]) : 0ull);
-          acc |= ((klo >> r) & 1u) ? v : 0ull;
-        }
-#pragma unroll 16
-        for (int r = 0; r < 32; ++r) {
-          const unsigned long long v =
-              STAGED ? col[(size_t)(r + 32) * Ws] : (((khi >> r) & 1u) ? __ldg(&col[(size_t)(r + 32) * Ws]) : 0ull);
-          acc |= ((khi >> r) & 1u) ? v : 0ull;
-        }
-        removed[w] |= acc;
+            for (int r = 0; r < 32; ++r) acc |= ((kbits >> r) & 1u) ? col[(size_t)r * Ws] : 0ull;
+            if (acc) atomicOr(&removed[w], acc);
+          }
+      } else {
+        // rows straight from global memory (L2): 8 row groups x 32 word lanes, 4 words x 8 rows = up to 32 predicated
+        // loads in flight per thread
+        const int rg = warp;
+        const uint32_t kb = (uint32_t)(kept >> (rg * 8)) & 0xFFu;
+        if (kb)
+          for (int w0 = c + 1 + lane; w0 < Wn; w0 += 32 * 4) {
+            unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int w = w0 + 32 * u;
+              const int wc = min(w, Wn - 1);   // clamped: the loads are unconditional so that all 32 are in flight
+              unsigned long long v[8];
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const int row = min(c * 64 + rg * 8 + r, K - 1);
+                v[r] = __ldg(&mrow[(size_t)row * Ws + wc]);
+              }
+#pragma unroll
+              for (int r = 0; r < 8; ++r) acc[u] |= ((kb >> r) & 1u) ? v[r] : 0ull;
+              if (w >= Wn) acc[u] = 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (acc[u]) atomicOr(&removed[w0 + 32 * u], acc[u]);
+          }
       }
     }
   }
