@@ -367,11 +367,15 @@ def run_ours(args):
             with torch.cuda.stream(det_stream):
                 det_stream.wait_event(ev_prop[s_])
                 graphs_det[s_].replay()
+                det = static_det[s_]
+                if world > 1:      # the path's only collective, also hidden under the 14x14 ROIAlign
+                    det = gather_detections(det, batch=world * B)
                 ev_det[s_].record(det_stream)
-            det = static_det[s_]
         else:
             proposals = front(inp)
             det = detect(inp, proposals)
+            if world > 1:
+                det = gather_detections(det, batch=world * B)
         if time_roi:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -381,8 +385,6 @@ def run_ours(args):
             roi_ev.append((e0, e1))
         if graphs[s_] is not None:
             main_stream.wait_event(ev_det[s_])       # join: the step ends when both branches are done
-        if world > 1:
-            return gather_detections(det, batch=world * B), proposals     # the path's only collective
         return det, proposals
 
     def barrier():
