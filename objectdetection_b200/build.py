@@ -49,6 +49,24 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Developer aid: a second library with extra -D flags (A/B runs select it with ODHEAD_LIB)."""
+    nvcc = _nvcc()
+    out = os.path.join(HERE, f"libodhead_{name}.so")
+    tmp = os.path.join(OBJ, f"variant_{name}")
+    os.makedirs(tmp, exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
+        subprocess.run([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-c", src, "-o", obj], check=True,
+                       capture_output=True, text=True)
+        objs.append(obj)
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs, "-Xcompiler", "-fPIC",
+                    "-Xlinker", "--no-undefined", "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True,
+                   capture_output=True, text=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()

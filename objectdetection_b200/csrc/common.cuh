@@ -163,8 +163,32 @@ __device__ __forceinline__ float tf_iou(const CBox& i, const CBox& j) {
 }
 
 // 16-byte global accesses with cache hints.
-__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
-__device__ __forceinline__ void stg_cs_f4(float4* p, float4 v) { __stcs(p, v); }   // streaming store (evict first)
+#ifndef OD_LOAD_MODE
+#define OD_LOAD_MODE 0
+#endif
+#ifndef OD_STORE_MODE
+#define OD_STORE_MODE 0
+#endif
+__device__ __forceinline__ float4 ldg_f4(const float4* p) {
+#if OD_LOAD_MODE == 0
+  return __ldg(p);
+#elif OD_LOAD_MODE == 1
+  return __ldcg(p);    // L2 only
+#else
+  float4 v;
+  asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#endif
+}
+__device__ __forceinline__ void stg_cs_f4(float4* p, float4 v) {   // streaming store (evict first)
+#if OD_STORE_MODE == 0
+  __stcs(p, v);
+#elif OD_STORE_MODE == 1
+  *p = v;
+#else
+  __stcg(p, v);
+#endif
+}
 
 constexpr int kNumSMsB200 = 148;
 

@@ -153,7 +153,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 constexpr int kScanThreads = 256;
-constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanMaxSlots = 8;
 
 // STAGED: nslots >= 2 ring slots of (64 rows x Ws words + the diagonal tile) fit in shared memory (K <= ~12000);

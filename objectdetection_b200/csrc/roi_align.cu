@@ -9,7 +9,7 @@
 // re-sort (maskrcnn.py:127-173) are not reproduced: each ROI writes straight to out[b*N+n].
 //
 //   crop_bins_kernel : the output is one flat array of bins (roi, y, x), each D*4 contiguous bytes. A CTA owns
-//      kBinsPerCta consecutive bins (every CTA does the same amount of work, ROI boundaries are irrelevant). Its
+//      32 consecutive bins (every CTA does the same amount of work, ROI boundaries are irrelevant). Its
 //      first threads build a per-bin table in shared memory: level assignment + crop_and_resize grid of the bin's
 //      ROI -> image base pointer, the four tap offsets (in 16-byte units), the two lerp weights and a validity
 //      flag. The main loop then is table lookup + 4 unconditional 16-byte loads per output quad (2 quads,
@@ -96,7 +96,18 @@ struct __align__(16) BinInfo {  // base pointer (16-byte aligned) | flag in the 
   float xl, yl;
 };
 constexpr uintptr_t kBinSample = 0, kBinExtrapolate = 1, kBinSkip = 2;
-constexpr int kBinThreads = 256;
+// CTA shape of the flat-bin kernels; the -D overrides exist for A/B builds (build.build_variant, tools/ab_libs.sh).
+// 128 threads x 32 bins measured best (profiles/r1_crop_variants.md).
+#ifndef OD_BIN_THREADS
+#define OD_BIN_THREADS 128
+#endif
+#ifndef OD_BIN_MINB
+#define OD_BIN_MINB 1
+#endif
+#ifndef OD_BIN_BINS
+#define OD_BIN_BINS 32
+#endif
+constexpr int kBinThreads = OD_BIN_THREADS;
 
 // packed fp32 pairs (sm_100 FADD2): IEEE add/sub on both halves, so results equal two scalar ops
 __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
@@ -191,7 +202,7 @@ __device__ __forceinline__ void bin_table_entry(const RoiSource& src, int64_t ro
 }
 
 template <int BINS, int UNROLL, bool POW2>
-__global__ void __launch_bounds__(kBinThreads)
+__global__ void __launch_bounds__(kBinThreads, OD_BIN_MINB)
 crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_t ph, int32_t pw, int32_t D4,
                  int32_t lgD4, float extrap, float4* __restrict__ out, int32_t* __restrict__ level_out) {
   __shared__ BinTaps s_taps[BINS];
@@ -318,10 +329,10 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
   }
   if (lg >= 0 && D4 >= 16) {
     if ((int64_t)64 * D4 > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "depth %d too large", D);
-    constexpr int BINS = 64;
+    constexpr int BINS = OD_BIN_BINS;
     const int64_t grid = (total_bins + BINS - 1) / BINS;
     if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
-    // 64 bins x 2 quads in flight per thread: best of the {32,64,128} x {1,2,4,8} sweep (profiles/r1_crop_variants.md)
+    // 32 bins per 128-thread CTA, 2 quads in flight per thread: best of the sweeps in profiles/r1_crop_variants.md
     crop_bins_kernel<BINS, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw, D4,
                                                                          lg, extrap, reinterpret_cast<float4*>(out), level_out);
   } else {
