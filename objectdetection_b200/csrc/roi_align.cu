@@ -107,6 +107,9 @@ constexpr uintptr_t kBinSample = 0, kBinExtrapolate = 1, kBinSkip = 2;
 #ifndef OD_BIN_BINS
 #define OD_BIN_BINS 32
 #endif
+#ifndef OD_BIN_UNROLL
+#define OD_BIN_UNROLL 2
+#endif
 constexpr int kBinThreads = OD_BIN_THREADS;
 
 // packed fp32 pairs (sm_100 FADD2): IEEE add/sub on both halves, so results equal two scalar ops
@@ -333,8 +336,8 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
     const int64_t grid = (total_bins + BINS - 1) / BINS;
     if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
     // 32 bins per 128-thread CTA, 2 quads in flight per thread: best of the sweeps in profiles/r1_crop_variants.md
-    crop_bins_kernel<BINS, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw, D4,
-                                                                         lg, extrap, reinterpret_cast<float4*>(out), level_out);
+    crop_bins_kernel<BINS, OD_BIN_UNROLL, true><<<(unsigned)grid, kBinThreads, 0, st>>>(
+        src, total_bins, (int32_t)bins_per_roi, ph, pw, D4, lg, extrap, reinterpret_cast<float4*>(out), level_out);
   } else {
     // thin or non-power-of-two depth: more bins per CTA so that the table build is amortised
     constexpr int BINS = 512;
