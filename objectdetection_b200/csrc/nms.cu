@@ -21,7 +21,10 @@
 
 namespace od {
 
-constexpr int kMaskColTiles = 4;   // column tiles (of 64 boxes) per CTA
+#ifndef OD_MASK_COL_TILES
+#define OD_MASK_COL_TILES 4
+#endif
+constexpr int kMaskColTiles = OD_MASK_COL_TILES;   // column tiles (of 64 boxes) per CTA (A/B builds may override)
 constexpr int kMaskThreads = 128;  // 64 rows x 2 halves; half h owns column tiles h, h+2 of the CTA's span
 
 template <bool FAST>  // FAST: thr >= 0, division skipped when the intersection is not positive
@@ -288,31 +291,32 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
             if (acc) atomicOr(&removed[w], acc);
           }
       } else {
-        // rows straight from global memory (L2): 8 row groups x 32 word lanes, 4 words x 8 rows = up to 32 predicated
-        // loads in flight per thread
-        const int rg = warp;
-        const uint32_t kb = (uint32_t)(kept >> (rg * 8)) & 0xFFu;
-        if (kb)
-          for (int w0 = c + 1 + lane; w0 < Wn; w0 += 32 * 4) {
-            unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+        // rows straight from global memory (L2): one owner thread per word (two words per thread and pass), 16 rows x 2
+        // words = 32 unconditional loads in flight per thread, no atomics
+        for (int w0 = c + 1 + tid; w0 < Wn; w0 += 2 * kScanThreads) {
+          const int w1 = w0 + kScanThreads;
+          const int w1c = min(w1, Wn - 1);
+          unsigned long long acc0 = 0ull, acc1 = 0ull;
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t kb = (uint32_t)(kept >> (16 * q)) & 0xFFFFu;
+            if (kb == 0u) continue;   // uniform
+            unsigned long long v0[16], v1[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int w = w0 + 32 * u;
-              const int wc = min(w, Wn - 1);   // clamped: the loads are unconditional so that all 32 are in flight
-              unsigned long long v[8];
-#pragma unroll
-              for (int r = 0; r < 8; ++r) {
-                const int row = min(c * 64 + rg * 8 + r, K - 1);
-                v[r] = __ldg(&mrow[(size_t)row * Ws + wc]);
-              }
-#pragma unroll
-              for (int r = 0; r < 8; ++r) acc[u] |= ((kb >> r) & 1u) ? v[r] : 0ull;
-              if (w >= Wn) acc[u] = 0ull;
+            for (int r = 0; r < 16; ++r) {
+              const size_t row = (size_t)min(c * 64 + 16 * q + r, K - 1) * Ws;
+              v0[r] = __ldg(&mrow[row + w0]);
+              v1[r] = __ldg(&mrow[row + w1c]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (acc[u]) atomicOr(&removed[w0 + 32 * u], acc[u]);
+            for (int r = 0; r < 16; ++r) {
+              acc0 |= ((kb >> r) & 1u) ? v0[r] : 0ull;
+              acc1 |= ((kb >> r) & 1u) ? v1[r] : 0ull;
+            }
           }
+          removed[w0] |= acc0;
+          if (w1 < Wn) removed[w1] |= acc1;
+        }
       }
     }
   }

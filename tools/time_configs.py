@@ -68,6 +68,33 @@ def main():
             rows.append(("PyramidROIAlign 7x7 B=8 x 1000 ROIs", timeit(lambda: pyramid_roi_align(fm, P[:8], conf.IMAGE_SHAPE, [7, 7], out=out)), "8 images"))
             del fm, out
 
+    # dense case: RPN-like outputs clustered around 40 objects (heavy overlap: the NMS has to visit every candidate and
+    # keeps fewer than 1000) - the regime of a trained network, as opposed to the random boxes of the bench recipe
+    B = 2
+    anchors = utils.gen_anchors(conf.IMAGE_SHAPE, B, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes, conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE)
+    anc = anchors[0].cpu().numpy()
+    A = anc.shape[0]
+    probs = np.zeros((B, A, 2), np.float32)
+    bbox = np.zeros((B, A, 4), np.float32)
+    acy, acx = (anc[:, 0] + anc[:, 2]) / 2, (anc[:, 1] + anc[:, 3]) / 2
+    ah, aw = anc[:, 2] - anc[:, 0], anc[:, 3] - anc[:, 1]
+    for b in range(B):
+        objs = np.stack([rs.uniform(0.1, 0.9, 40), rs.uniform(0.1, 0.9, 40), rs.uniform(0.03, 0.3, 40), rs.uniform(0.03, 0.3, 40)], 1)
+        d2 = ((acy[:, None] - objs[None, :, 0]) / objs[None, :, 2]) ** 2 + ((acx[:, None] - objs[None, :, 1]) / objs[None, :, 3]) ** 2
+        j = d2.argmin(1)
+        fg = np.exp(-d2.min(1) * 2) * np.exp(-np.abs(np.log(ah / objs[j, 2])) - np.abs(np.log(aw / objs[j, 3])))
+        fg = np.clip(fg + rs.normal(0, 0.02, A), 0, 1).astype(np.float32)
+        probs[b, :, 1], probs[b, :, 0] = fg, 1 - fg
+        # regress towards the object (deltas / stddev), with noise
+        bbox[b, :, 0] = (objs[j, 0] - acy) / ah / 0.1 + rs.normal(0, 0.3, A)
+        bbox[b, :, 1] = (objs[j, 1] - acx) / aw / 0.1 + rs.normal(0, 0.3, A)
+        bbox[b, :, 2] = np.log(objs[j, 2] / ah) / 0.2 + rs.normal(0, 0.3, A)
+        bbox[b, :, 3] = np.log(objs[j, 3] / aw) / 0.2 + rs.normal(0, 0.3, A)
+    p, bb = cu(probs), cu(np.clip(bbox, -20, 20).astype(np.float32))
+    Pd = Proposals(conf, B, p, bb, anchors, DEBUG=True)
+    kept = Pd.num_kept.cpu().numpy().tolist()
+    rows.append((f"Proposals B=2, DENSE clustered boxes (NMS keeps {kept} of 6000, visits all)", timeit(lambda: Proposals(conf, B, p, bb, anchors)), "2 images"))
+
     # config 4: Faster R-CNN 600x1000, 12000 -> 2000, roi_pool 7x7 over 300 boxes, D=512
     h, w, na = 38, 63, 9
     fp = cu(rs.random_sample((1, h, w, 2 * na)).astype(np.float32))
