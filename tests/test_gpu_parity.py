@@ -144,6 +144,33 @@ def test_nms(n, thr):
             assert np.array_equal(keep[b, :num[b]], want) and np.all(keep[b, num[b]:] == -1)
 
 
+@pytest.mark.parametrize("K,max_out", [(6000, 1000), (12000, 2000), (20000, 500), (6000, 40)])
+def test_nms_two_rounds_on_clustered_boxes(K, max_out):
+    """max_out << K runs the NMS in two rounds (rows of the first 1.5 x max_out boxes, then - decided on the device -
+    the rest, with the scan state carried over). Heavily clustered boxes force the second round; ragged num_valid;
+    K = 20000 takes the unstaged (global-memory) scan."""
+    from objectdetection_b200.proposals import non_max_suppression
+    rs = np.random.RandomState(K + max_out)
+    B = 2
+    centers = rs.uniform(0.1, 0.9, (B, 60, 2))
+    sizes = rs.uniform(0.03, 0.2, (B, 60, 2))
+    which = rs.randint(0, 60, (B, K))
+    c = np.take_along_axis(centers, which[..., None].repeat(2, -1), 1) + rs.normal(0, 0.004, (B, K, 2))
+    hw = np.take_along_axis(sizes, which[..., None].repeat(2, -1), 1) * np.exp(rs.normal(0, 0.06, (B, K, 2)))
+    boxes = np.concatenate([c - hw / 2, c + hw / 2], -1).astype(f32)
+    scores = rs.random_sample((B, K)).astype(f32)
+    nv = np.array([K, K - 1234], np.int32)
+    keep, num = non_max_suppression(cu(boxes), cu(scores), max_out, 0.7, num_valid=nv)
+    keep, num = host(keep), host(num)
+    visited_all = False
+    for b in range(B):
+        want = oracle.nms(boxes[b, :nv[b]], scores[b, :nv[b]], max_out, 0.7)
+        assert num[b] == want.shape[0], (b, num[b], want.shape[0])
+        assert np.array_equal(keep[b, :num[b]], want) and np.all(keep[b, num[b]:] == -1)
+        visited_all |= want.shape[0] < max_out
+    assert visited_all or max_out == 40      # the clusters are dense enough that the second round had to run
+
+
 def test_nms_num_valid_and_single_image_form():
     from objectdetection_b200.proposals import non_max_suppression
     rs = np.random.RandomState(4)
