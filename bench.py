@@ -131,7 +131,7 @@ class ClockSampler:
         for fields in (self.FIELDS, self.FIELDS.replace("clocks_event_reasons", "clocks_throttle_reasons")):
             try:
                 self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={fields}",
-                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                              "--format=csv,noheader,nounits", "-lms", "20"],
                                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             except OSError:
                 self.proc = None
@@ -573,7 +573,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

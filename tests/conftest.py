@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
+def pytest_sessionstart(session):
+    """Safety net: if the in-tree CUDA library is missing (fresh checkout) and nvcc is around, build it once. The
+    package itself never builds or falls back: a missing library raises at the first call."""
+    try:
+        from objectdetection_b200 import _lib, build
+        if not os.path.exists(_lib.LIB_PATH):
+            build.build()
+    except Exception as e:   # the tests that need the library will report the real error
+        print(f"[conftest] libodhead.so not built: {e}")
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
