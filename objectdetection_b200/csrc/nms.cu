@@ -25,7 +25,11 @@ namespace od {
 #define OD_MASK_COL_TILES 4
 #endif
 constexpr int kMaskColTiles = OD_MASK_COL_TILES;   // column tiles (of 64 boxes) per CTA (A/B builds may override)
-constexpr int kMaskThreads = 128;  // 64 rows x 2 halves; half h owns column tiles h, h+2 of the CTA's span
+#ifndef OD_MASK_THREADS
+#define OD_MASK_THREADS 256
+#endif
+constexpr int kMaskThreads = OD_MASK_THREADS;            // 64 rows x kMaskGroups thread groups
+constexpr int kMaskGroups = kMaskThreads / 64;           // group h owns column tiles h, h + kMaskGroups, ... of the span
 
 template <bool FAST>  // FAST: thr >= 0, division skipped when the intersection is not positive
 __global__ void __launch_bounds__(kMaskThreads)
@@ -53,16 +57,16 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
     cgrp[q] = (group && j < n) ? group[(int64_t)b * K + j] : -1;
   }
   __syncthreads();
-  const int r = t & 63, half = t >> 6;
+  const int r = t & 63, half = t >> 6;   // (thread group)
   const int i = rb * 64 + r;
   const bool row_ok = i < n;
   const CBox my = canon_box(row_ok ? bx[i] : make_float4(0.f, 0.f, 0.f, 0.f));
   const int32_t g = (group && row_ok) ? group[(int64_t)b * K + i] : 0;
 #pragma unroll
-  for (int ct = 0; ct < kMaskColTiles / 2; ++ct) {
-    const int tile = half + 2 * ct;
+  for (int ct = 0; ct < kMaskColTiles / kMaskGroups; ++ct) {
+    const int tile = half + kMaskGroups * ct;
     const int cb = cb0 + tile;
-    if (cb * 64 >= n) break;   // uniform per half (two warps)
+    if (cb * 64 >= n) break;   // uniform per thread group (two warps)
     unsigned long long bits = 0ull;
     const float4* cbp = cbox + tile * 64;
     const float* cap = carea + tile * 64;
