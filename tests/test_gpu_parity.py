@@ -578,34 +578,38 @@ def test_rpn_targets_golden_and_coco_shape():
         assert np.array_equal(host(cls), g[case + "_cls"])                        # labels: bit-exact
         assert np.array_equal(host(pos), g[case + "_pos_anchors"])
         assert np.allclose(host(bbox), g[case + "_bbox"], rtol=1e-13, atol=0)     # fp64 deltas (log may differ by an ulp)
-    # COCO shape against the oracle
-    conf = Conf()
-    P = PreprareTrainData(conf)
-    A = P.anchors.shape[0]
-    assert A == 261888
-    rs = np.random.RandomState(21)
-    B, G = 3, 100
-    anc = host(P.anchors)
-    gt = np.zeros((B, G, 4))
-    cnt = np.array([100, 37, 1], np.int32)
-    for b in range(B):
-        pick = rs.choice(A, cnt[b], replace=False)
-        gt[b, :cnt[b]] = np.round(np.clip(anc[pick] + rs.normal(0, 3, (cnt[b], 4)), 0, 1024))
-        bad = (gt[b, :, 2] <= gt[b, :, 0]) | (gt[b, :, 3] <= gt[b, :, 1])
-        gt[b, bad] = [100, 100, 164, 164]
-    pp = np.stack([rs.permutation(A) for _ in range(B)]).astype(np.int32)
-    pn = np.stack([rs.permutation(A) for _ in range(B)]).astype(np.int32)
-    pos, cls, bbox, counts = P.build_rpn_targets(gt, perm_pos=pp, perm_neg=pn, gt_count=cnt, return_counts=True)
-    pos, cls, bbox, counts = host(pos), host(cls), host(bbox), host(counts)
-    for b in range(B):
-        w_pos, w_cls, w_bbox, w_counts = oracle.rpn_targets(anc, gt[b, :cnt[b]], pp[b], pn[b], conf.RPN_TRAIN_ANCHORS_PER_IMAGE,
-                                                            conf.RPN_BBOX_STDDEV)
-        assert np.array_equal(counts[b], w_counts), (counts[b], w_counts)
-        assert np.array_equal(cls[b], w_cls)
-        n = w_counts[2]
-        assert np.array_equal(pos[b, :n], w_pos) and not pos[b, n:].any()
-        assert np.allclose(bbox[b], w_bbox, rtol=1e-13, atol=0)
-        assert (cls[b] == 1).sum() <= 128 and (cls[b] == 1).sum() + (cls[b] == -1).sum() == 256
+    # COCO shape against the oracle: the reference's limits (100 GT, 256 targets: fused per-GT arg-max), then 300 GT
+    # (the per-GT kernel) with 16 targets so that the positives are subsampled too
+    class Few(Conf):
+        RPN_TRAIN_ANCHORS_PER_IMAGE = 16
+    for conf, G, cnt in ((Conf(), 100, [100, 37, 1]), (Few(), 300, [300, 129, 0])):
+        P = PreprareTrainData(conf)
+        A = P.anchors.shape[0]
+        assert A == 261888
+        rs = np.random.RandomState(21 + G)
+        B, T = 3, conf.RPN_TRAIN_ANCHORS_PER_IMAGE
+        anc = host(P.anchors)
+        gt = np.zeros((B, G, 4))
+        cnt = np.array(cnt, np.int32)
+        for b in range(B):
+            pick = rs.choice(A, cnt[b], replace=False)
+            gt[b, :cnt[b]] = np.round(np.clip(anc[pick] + rs.normal(0, 3, (cnt[b], 4)), 0, 1024))
+            bad = (gt[b, :, 2] <= gt[b, :, 0]) | (gt[b, :, 3] <= gt[b, :, 1])
+            gt[b, bad] = [100, 100, 164, 164]
+        pp = np.stack([rs.permutation(A) for _ in range(B)]).astype(np.int32)
+        pn = np.stack([rs.permutation(A) for _ in range(B)]).astype(np.int32)
+        pos, cls, bbox, counts = P.build_rpn_targets(gt, perm_pos=pp, perm_neg=pn, gt_count=cnt, return_counts=True)
+        pos, cls, bbox, counts = host(pos), host(cls), host(bbox), host(counts)
+        for b in range(B):
+            w_pos, w_cls, w_bbox, w_counts = oracle.rpn_targets(anc, gt[b, :cnt[b]], pp[b], pn[b], T, conf.RPN_BBOX_STDDEV)
+            assert np.array_equal(counts[b], w_counts), (counts[b], w_counts)
+            assert np.array_equal(cls[b], w_cls)
+            n = w_counts[2]
+            assert np.array_equal(pos[b, :n], w_pos) and not pos[b, n:].any()
+            assert np.allclose(bbox[b], w_bbox, rtol=1e-13, atol=0)
+            assert (cls[b] == 1).sum() <= T // 2 and (cls[b] == 1).sum() + (cls[b] == -1).sum() == T
+        if G == 300:
+            assert counts[0, 0] > T // 2 and counts[0, 2] == T // 2      # positives were dropped through perm_pos
 
 
 # ------------------------------------------------------------------ error behaviour
