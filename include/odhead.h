@@ -5,6 +5,8 @@
  * reference tree, Sardhendu/ObjectDetection):
  *
  *   od_proposal_forward            replaces  Proposals.build                MaskRCNN/building_blocks/proposals_tf.py:136-214
+ *   od_proposal_forward_levels     replaces  the same, fed by the RPN head's per-level outputs: rpn.py:50-67 (reshape +
+ *                                            softmax), training.py:146-166 (concat over P2..P6) + proposals_tf.py:136-214
  *   od_apply_box_deltas            replaces  apply_box_deltas               proposals_tf.py:23-65
  *   od_clip_boxes                  replaces  clip_boxes_to_01               proposals_tf.py:67-94
  *   od_topk                        replaces  tf.nn.top_k call sites         proposals_tf.py:169, detection.py:221
@@ -164,6 +166,22 @@ int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbo
                         const od_proposal_params* params, DLTensor* proposals,
                         const od_proposal_debug* debug,
                         void* ws, size_t ws_bytes, void* stream);
+
+/* The same layer fed by the RPN head's conv outputs in their native per-level layout: no
+ * [B,A,2] / [B,A,4] concatenation is materialised.
+ * class_logits[l]: [B,H_l,W_l,2a] f32 NHWC ('rpn_class_raw', rpn.py:50; a anchors per location, (bg,fg) pairs),
+ * bbox[l]:         [B,H_l,W_l,4a] f32 NHWC ('rpn_bbox_pred', rpn.py:63), l < num_levels.
+ * The reference reshapes each to [B,-1,2] / [B,-1,4], takes the softmax of the pairs (rpn.py:54-59) and concatenates
+ * the levels along the anchor axis (training.py:163-166); anchor i of that concatenation is what `anchors`/`spec`,
+ * debug.ix etc. refer to. The fg probability exp(fg-m)/(exp(bg-m)+exp(fg-m)), m = max(bg,fg), is computed in fp32
+ * for every anchor into the workspace ([B,A] f32) and ranked; deltas are read from their level only for the
+ * pre_nms_limit selected anchors. */
+size_t od_proposal_levels_workspace_bytes(int64_t batch, int64_t num_anchors, const od_proposal_params* p);
+int od_proposal_forward_levels(const DLTensor* const* class_logits, const DLTensor* const* bbox, int32_t num_levels,
+                               const DLTensor* anchors, const od_anchor_spec* spec,
+                               const od_proposal_params* params, DLTensor* proposals,
+                               const od_proposal_debug* debug,
+                               void* ws, size_t ws_bytes, void* stream);
 
 /* ---- PyramidROIAlign (maskrcnn.py:74-187) ---------------------------------- */
 /* fmaps[l]: [B,H_l,W_l,D] f32 NHWC for level (min_level + l), l < num_levels;

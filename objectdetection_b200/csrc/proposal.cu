@@ -15,16 +15,32 @@ struct ProposalDebugPtrs {
   float4* clipped_dbg;  // [B,K] or nullptr
 };
 
+// RPN head outputs in their native layout: one [B, n_l, C] block per pyramid level (the reshape of the conv output
+// [B,H_l,W_l,a*C], rpn.py:54/66); the reference concatenates them along the anchor axis (training.py:163-166).
+struct LevelTable {
+  const float* base[OD_MAX_LEVELS];
+  int32_t off[OD_MAX_LEVELS + 1];   // first flat anchor index of each level
+  int32_t num_levels;
+};
+template <int C>
+__device__ __forceinline__ const float* level_row(const LevelTable& t, int64_t b, int32_t i) {
+  int l = 0;
+  while (l + 1 < t.num_levels && i >= t.off[l + 1]) ++l;
+  const int64_t n_l = t.off[l + 1] - t.off[l];
+  return t.base[l] + (b * n_l + (i - t.off[l])) * C;
+}
+
 // One thread per selected anchor: 16 B delta + 16 B anchor (or fp64 regeneration) in, 16 B box out.
+template <bool LEVELS>
 __global__ void __launch_bounds__(256)
-proposal_decode_kernel(const float4* __restrict__ bbox, const float4* __restrict__ anchors, DevAnchorSpec spec,
+proposal_decode_kernel(const float4* __restrict__ bbox, LevelTable lv, const float4* __restrict__ anchors, DevAnchorSpec spec,
                        int use_spec, const int32_t* __restrict__ ix, int64_t total, int K, int A, float4 stddev,
                        float4* __restrict__ clipped, ProposalDebugPtrs dbg) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int64_t b = t / K;
   const int32_t i = ix[t];
-  const float4 raw = __ldg(&bbox[b * A + i]);
+  const float4 raw = LEVELS ? __ldg(reinterpret_cast<const float4*>(level_row<4>(lv, b, i))) : __ldg(&bbox[b * A + i]);
   const float4 d = make_float4(raw.x * stddev.x, raw.y * stddev.y, raw.z * stddev.z, raw.w * stddev.w);  // :157
   const float4 a = use_spec ? anchor_normalized(spec, i) : __ldg(&anchors[b * A + i]);
   const float4 dec = decode_box(a, d);                                            // :179
@@ -34,6 +50,20 @@ proposal_decode_kernel(const float4* __restrict__ bbox, const float4* __restrict
   if (dbg.anchors) dbg.anchors[t] = a;
   if (dbg.anchor_delta) dbg.anchor_delta[t] = dec;
   if (dbg.clipped_dbg) dbg.clipped_dbg[t] = c;
+}
+
+// Foreground probability of every anchor from the per-level class logits: softmax over the (bg, fg) pair
+// (rpn.py:58-59, tf.nn.softmax: exp(x - max) / sum) written as one contiguous [B,A] row per image for the top-k.
+__global__ void __launch_bounds__(256)
+rpn_level_scores_kernel(LevelTable lv, int A, int64_t total, float* __restrict__ scores) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t b = t / A;
+  const int32_t i = (int32_t)(t - b * A);
+  const float2 x = __ldg(reinterpret_cast<const float2*>(level_row<2>(lv, b, i)));
+  const float m = (x.x < x.y) ? x.y : x.x;
+  const float e0 = f_exp(x.x - m), e1 = f_exp(x.y - m);
+  scores[t] = e1 / (e0 + e1);
 }
 
 // proposals[b,j] = clipped[b, keep_pos[b,j]] or zeros (tf.pad, :245-246).
@@ -184,19 +214,16 @@ size_t od_proposal_workspace_bytes(int64_t batch, int64_t num_anchors, const od_
   return carve_proposal_ws(w, batch, num_anchors, K, p->post_nms_count, nullptr);
 }
 
-int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbox, const DLTensor* anchors,
-                        const od_anchor_spec* spec, const od_proposal_params* params, DLTensor* proposals,
-                        const od_proposal_debug* debug, void* ws, size_t ws_bytes, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!params) OD_FAIL(OD_ERR_NULL, "params is NULL");
-  int dev = -1;
-  OD_CHECK(check_tensor(rpn_class_probs, "rpn_class_probs", F32, 3, true, &dev));
-  OD_CHECK(check_tensor(rpn_bbox, "rpn_bbox", F32, 3, true, &dev));
-  OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
-  const int64_t B = rpn_class_probs->shape[0], A = rpn_class_probs->shape[1];
-  if (rpn_class_probs->shape[2] != 2) OD_FAIL(OD_ERR_SHAPE, "rpn_class_probs must be [B,A,2]");
-  if (rpn_bbox->shape[0] != B || rpn_bbox->shape[1] != A || rpn_bbox->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "rpn_bbox must be [B,A,4]");
-  if (params->pre_nms_limit < 0 || params->post_nms_count < 0) OD_FAIL(OD_ERR_PARAM, "negative counts");
+}  // extern "C"
+
+namespace od {
+// Shared body of od_proposal_forward / od_proposal_forward_levels. `scores` addresses the fg score of anchor i of image b at
+// scores[b * score_sb + i * score_sa]; the deltas come from `rpn_bbox4` ([B,A,4]) or, when it is NULL, from `lv`.
+// `p` is the carved workspace. Shapes B, A are those of the caller's (virtual) [B,A,.] tensors.
+static int proposal_core(const float* scores_src, int64_t score_sb, int64_t score_sa, const float4* rpn_bbox4, const LevelTable& lv,
+                         int64_t B, int64_t A, const DLTensor* anchors, const od_anchor_spec* spec,
+                         const od_proposal_params* params, DLTensor* proposals, const od_proposal_debug* debug, ProposalWs& p,
+                         int dev, cudaStream_t st) {
   const int64_t K = params->pre_nms_limit < A ? params->pre_nms_limit : A;
   const int64_t N = params->post_nms_count;
   if (proposals->shape[0] != B || proposals->shape[1] != N || proposals->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "proposals must be [B,%lld,4]", (long long)N);
@@ -213,8 +240,7 @@ int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbo
     if (dspec.offset[dspec.num_levels] != A) OD_FAIL(OD_ERR_SHAPE, "anchor spec yields %lld anchors, inputs have %lld", (long long)dspec.offset[dspec.num_levels], (long long)A);
     use_spec = 1;
   }
-  if (reinterpret_cast<uintptr_t>(dptr<float>(rpn_bbox)) % 16 || reinterpret_cast<uintptr_t>(dptr<float>(proposals)) % 16)
-    OD_FAIL(OD_ERR_LAYOUT, "rpn_bbox / proposals not 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(dptr<float>(proposals)) % 16) OD_FAIL(OD_ERR_LAYOUT, "proposals not 16-byte aligned");
   od_proposal_debug dbg;
   memset(&dbg, 0, sizeof(dbg));
   if (debug) dbg = *debug;
@@ -227,18 +253,13 @@ int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbo
   OD_CHECK(check_opt(dbg.keep_idx, "debug.keep_idx", I32, 2, &dev, {B, N}));
   OD_CHECK(check_opt(dbg.num_kept, "debug.num_kept", I32, 1, &dev, {B}));
   if (B == 0 || N == 0) return OD_OK;
-  if (!ws) OD_FAIL(OD_ERR_WORKSPACE, "workspace is NULL");
-  Workspace w(ws, ws_bytes);
-  ProposalWs p;
-  carve_proposal_ws(w, B, A, K, N, &p);
-  if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, w.off);
   int32_t* ix = dbg.ix ? dptr<int32_t>(dbg.ix) : p.ix;
   float* scores = dbg.scores ? dptr<float>(dbg.scores) : nullptr;  // only materialised on request
   int32_t* keep_pos = dbg.keep_idx ? dptr<int32_t>(dbg.keep_idx) : p.keep_pos;
   int32_t* num_kept = dbg.num_kept ? dptr<int32_t>(dbg.num_kept) : p.num_kept;
 
   // scores = probs[:,:,1]  (:153) -> top-k (:169)
-  OD_CHECK(topk_launch(dptr<float>(rpn_class_probs) + 1, B, A, 2 * A, 2, K, ix, scores, p.topk_ws, p.topk_bytes, st));
+  OD_CHECK(topk_launch(scores_src, B, A, score_sb, score_sa, K, ix, scores, p.topk_ws, p.topk_bytes, st));
   if (K > 0) {
     ProposalDebugPtrs dp;
     dp.scores = scores;
@@ -248,8 +269,12 @@ int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbo
     dp.clipped_dbg = dptr<float4>(dbg.anchor_delta_clipped);
     const int64_t total = B * K;
     const float4 sd = make_float4(params->bbox_stddev[0], params->bbox_stddev[1], params->bbox_stddev[2], params->bbox_stddev[3]);
-    proposal_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        dptr<float4>(rpn_bbox), dptr<float4>(anchors), dspec, use_spec, ix, total, (int)K, (int)A, sd, p.clipped, dp);
+    if (rpn_bbox4)
+      proposal_decode_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          rpn_bbox4, lv, dptr<float4>(anchors), dspec, use_spec, ix, total, (int)K, (int)A, sd, p.clipped, dp);
+    else
+      proposal_decode_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          nullptr, lv, dptr<float4>(anchors), dspec, use_spec, ix, total, (int)K, (int)A, sd, p.clipped, dp);
     OD_LAUNCH_CHECK("proposal_decode_kernel");
   }
   // per-image NMS over boxes already in (score desc, index asc) order (:188-196, :234)
@@ -260,6 +285,101 @@ int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbo
                                                                          dptr<float4>(proposals));
   OD_LAUNCH_CHECK("proposal_gather_kernel");
   return OD_OK;
+}
+}  // namespace od
+
+extern "C" {
+
+int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbox, const DLTensor* anchors,
+                        const od_anchor_spec* spec, const od_proposal_params* params, DLTensor* proposals,
+                        const od_proposal_debug* debug, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!params) OD_FAIL(OD_ERR_NULL, "params is NULL");
+  int dev = -1;
+  OD_CHECK(check_tensor(rpn_class_probs, "rpn_class_probs", F32, 3, true, &dev));
+  OD_CHECK(check_tensor(rpn_bbox, "rpn_bbox", F32, 3, true, &dev));
+  OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
+  const int64_t B = rpn_class_probs->shape[0], A = rpn_class_probs->shape[1];
+  if (rpn_class_probs->shape[2] != 2) OD_FAIL(OD_ERR_SHAPE, "rpn_class_probs must be [B,A,2]");
+  if (rpn_bbox->shape[0] != B || rpn_bbox->shape[1] != A || rpn_bbox->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "rpn_bbox must be [B,A,4]");
+  if (params->pre_nms_limit < 0 || params->post_nms_count < 0) OD_FAIL(OD_ERR_PARAM, "negative counts");
+  if (reinterpret_cast<uintptr_t>(dptr<float>(rpn_bbox)) % 16) OD_FAIL(OD_ERR_LAYOUT, "rpn_bbox not 16-byte aligned");
+  const int64_t K = params->pre_nms_limit < A ? params->pre_nms_limit : A;
+  const int64_t N = params->post_nms_count;
+  ProposalWs p;
+  memset(&p, 0, sizeof(p));
+  if (B != 0 && N != 0) {
+    if (!ws) OD_FAIL(OD_ERR_WORKSPACE, "workspace is NULL");
+    Workspace w(ws, ws_bytes);
+    carve_proposal_ws(w, B, A, K, N, &p);
+    if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, w.off);
+  }
+  LevelTable lv;
+  memset(&lv, 0, sizeof(lv));
+  // scores = probs[:,:,1]  (:153)
+  return proposal_core(dptr<float>(rpn_class_probs) + 1, 2 * A, 2, dptr<float4>(rpn_bbox), lv, B, A, anchors, spec, params,
+                       proposals, debug, p, dev, st);
+}
+
+size_t od_proposal_levels_workspace_bytes(int64_t batch, int64_t num_anchors, const od_proposal_params* p) {
+  if (!p) return 0;
+  const int64_t K = p->pre_nms_limit < num_anchors ? p->pre_nms_limit : num_anchors;
+  Workspace w(nullptr, 0);
+  w.take<float>((size_t)(batch * num_anchors));
+  return carve_proposal_ws(w, batch, num_anchors, K, p->post_nms_count, nullptr);
+}
+
+int od_proposal_forward_levels(const DLTensor* const* class_logits, const DLTensor* const* bbox, int32_t num_levels,
+                               const DLTensor* anchors, const od_anchor_spec* spec, const od_proposal_params* params,
+                               DLTensor* proposals, const od_proposal_debug* debug, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!params || !class_logits || !bbox) OD_FAIL(OD_ERR_NULL, "params / class_logits / bbox is NULL");
+  if (num_levels < 1 || num_levels > OD_MAX_LEVELS) OD_FAIL(OD_ERR_PARAM, "num_levels %d out of range", num_levels);
+  if (params->pre_nms_limit < 0 || params->post_nms_count < 0) OD_FAIL(OD_ERR_PARAM, "negative counts");
+  int dev = -1;
+  OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
+  LevelTable lc, lb;
+  memset(&lc, 0, sizeof(lc));
+  memset(&lb, 0, sizeof(lb));
+  lc.num_levels = lb.num_levels = num_levels;
+  int64_t B = -1, A = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    OD_CHECK(check_tensor(class_logits[l], "class_logits[l]", F32, 4, true, &dev));
+    OD_CHECK(check_tensor(bbox[l], "bbox[l]", F32, 4, true, &dev));
+    const DLTensor* c = class_logits[l];
+    const DLTensor* d = bbox[l];
+    if (B < 0) B = c->shape[0];
+    if (c->shape[0] != B || d->shape[0] != B || c->shape[1] != d->shape[1] || c->shape[2] != d->shape[2] || c->shape[3] % 2 ||
+        d->shape[3] != 2 * c->shape[3])
+      OD_FAIL(OD_ERR_SHAPE, "level %d: class_logits must be [B,H,W,2a] and bbox [B,H,W,4a] with the same B, H, W, a", l);
+    if (reinterpret_cast<uintptr_t>(dptr<float>(d)) % 16 || reinterpret_cast<uintptr_t>(dptr<float>(c)) % 8)
+      OD_FAIL(OD_ERR_LAYOUT, "level %d: class_logits / bbox not 8 / 16-byte aligned", l);
+    const int64_t n_l = c->shape[1] * c->shape[2] * (c->shape[3] / 2);
+    lc.base[l] = dptr<float>(c);
+    lb.base[l] = dptr<float>(d);
+    lc.off[l] = lb.off[l] = (int32_t)A;
+    A += n_l;
+    if (A >= (1ll << 31)) OD_FAIL(OD_ERR_PARAM, "too many anchors");
+  }
+  for (int l = num_levels; l <= OD_MAX_LEVELS; ++l) lc.off[l] = lb.off[l] = (int32_t)A;
+  const int64_t K = params->pre_nms_limit < A ? params->pre_nms_limit : A;
+  const int64_t N = params->post_nms_count;
+  ProposalWs p;
+  memset(&p, 0, sizeof(p));
+  float* scores = nullptr;
+  if (B != 0 && N != 0) {
+    if (!ws) OD_FAIL(OD_ERR_WORKSPACE, "workspace is NULL");
+    Workspace w(ws, ws_bytes);
+    scores = w.take<float>((size_t)(B * A));
+    carve_proposal_ws(w, B, A, K, N, &p);
+    if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, w.off);
+    const int64_t total = B * A;
+    if (total > 0) {
+      rpn_level_scores_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lc, (int)A, total, scores);
+      OD_LAUNCH_CHECK("rpn_level_scores_kernel");
+    }
+  }
+  return proposal_core(scores, A, 1, nullptr, lb, B, A, anchors, spec, params, proposals, debug, p, dev, st);
 }
 
 }  // extern "C"

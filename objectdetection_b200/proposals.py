@@ -46,6 +46,10 @@ class Proposals():
     the constructor (like the reference builds its graph there); otherwise call ``run(...)`` — the equivalent of
     feeding the reference's placeholders. ``anchor_spec`` (optional, from ``utils.anchor_spec``) lets the decode
     kernel regenerate anchors from their index instead of reading ``inp_anchors``.
+
+    ``run_levels(class_logits, bbox)`` takes the RPN head's conv outputs per pyramid level instead
+    (``[B,H_l,W_l,2a]`` 'rpn_class_raw' and ``[B,H_l,W_l,4a]`` 'rpn_bbox_pred', rpn.py:50-67): the reshape, the 2-way
+    softmax and the concatenation over levels of training.py:146-166 happen inside the layer, nothing is concatenated.
     """
 
     def __init__(self, conf, batch_size, rpn_class_probs=None, rpn_bbox=None, inp_anchors=None,
@@ -71,19 +75,36 @@ class Proposals():
         self.build()
         return self.proposals
 
-    def build(self):
+    def run_levels(self, rpn_class_logits_levels, rpn_bbox_levels, input_anchors=None):
+        """The layer on the per-level RPN head outputs (rpn.py:50-67 + training.py:146-166 + this class)."""
+        if len(rpn_class_logits_levels) != len(rpn_bbox_levels) or not len(rpn_bbox_levels):
+            raise ValueError("one class-logit and one bbox tensor per pyramid level expected")
+        self.input_anchors = input_anchors if input_anchors is not None else self.input_anchors
+        self.build(levels=(list(rpn_class_logits_levels), list(rpn_bbox_levels)))
+        return self.proposals
+
+    def build(self, levels=None):
         L = _lib.lib()
-        probs = _lib.as_cuda(self.rpn_class_probs, torch.float32)
-        dev = probs.device
-        bbox = _lib.as_cuda(self.rpn_bbox, torch.float32, dev)
+        if levels is None:
+            probs = _lib.as_cuda(self.rpn_class_probs, torch.float32)
+            dev = probs.device
+            bbox = _lib.as_cuda(self.rpn_bbox, torch.float32, dev)
+            if probs.dim() != 3:
+                raise ValueError("rpn_class_probs must be [batch, anchors, 2]")
+            B, A = probs.shape[0], probs.shape[1]
+        else:
+            logits = [_lib.as_cuda(t, torch.float32) for t in levels[0]]
+            dev = logits[0].device
+            deltas = [_lib.as_cuda(t, torch.float32, dev) for t in levels[1]]
+            if any(t.dim() != 4 for t in logits + deltas):
+                raise ValueError("per-level RPN outputs must be [batch, H, W, channels]")
+            B = logits[0].shape[0]
+            A = sum(t.shape[1] * t.shape[2] * (t.shape[3] // 2) for t in logits)
         anchors = None if self.input_anchors is None else _lib.as_cuda(self.input_anchors, torch.float32, dev)
         if anchors is None and self.anchor_spec is None:
             raise ValueError("Proposals needs inp_anchors or anchor_spec")
-        if probs.dim() != 3:
-            raise ValueError("rpn_class_probs must be [batch, anchors, 2]")
-        B, A = probs.shape[0], probs.shape[1]
         if B != self.batch_size:
-            raise ValueError(f"batch_size={self.batch_size} but rpn_class_probs has batch {B}")
+            raise ValueError(f"batch_size={self.batch_size} but the RPN outputs have batch {B}")
         K, N = min(int(self.num_box_before_nms), A), int(self.num_boxes_after_nms)
         self.proposals = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
         self.anchor_delta_clipped = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
@@ -101,16 +122,24 @@ class Proposals():
             dbg.ix, dbg.scores, dbg.bbox_delta = dl(self.ix), dl(self.scores), dl(self.bbox_delta)
             dbg.anchors, dbg.anchor_delta = dl(self.anchors), dl(self.anchor_delta)
             dbg.keep_idx, dbg.num_kept = dl(self.keep_idx), dl(self.num_kept)
-        nbytes = L.od_proposal_workspace_bytes(B, A, ctypes.byref(self._params))
-        ws = _lib.workspace(nbytes, dev)
         spec = ctypes.byref(self.anchor_spec) if (anchors is None) else None
-        _lib.check(L.od_proposal_forward(dl(probs), dl(bbox), dl(anchors), spec, ctypes.byref(self._params),
-                                         dl(self.proposals), ctypes.byref(dbg), ws.data_ptr(), ws.numel(),
-                                         _lib.stream_ptr(dev)), "od_proposal_forward")
+        if levels is None:
+            ws = _lib.workspace(L.od_proposal_workspace_bytes(B, A, ctypes.byref(self._params)), dev)
+            _lib.check(L.od_proposal_forward(dl(probs), dl(bbox), dl(anchors), spec, ctypes.byref(self._params),
+                                             dl(self.proposals), ctypes.byref(dbg), ws.data_ptr(), ws.numel(),
+                                             _lib.stream_ptr(dev)), "od_proposal_forward")
+            self.rpn_class_probs, self.rpn_bbox = probs, bbox
+        else:
+            ws = _lib.workspace(L.od_proposal_levels_workspace_bytes(B, A, ctypes.byref(self._params)), dev)
+            lp = (ctypes.c_void_p * len(logits))(*[dl(t) for t in logits])
+            bp = (ctypes.c_void_p * len(deltas))(*[dl(t) for t in deltas])
+            _lib.check(L.od_proposal_forward_levels(lp, bp, len(logits), dl(anchors), spec, ctypes.byref(self._params),
+                                                    dl(self.proposals), ctypes.byref(dbg), ws.data_ptr(), ws.numel(),
+                                                    _lib.stream_ptr(dev)), "od_proposal_forward_levels")
+            self.rpn_class_logits_levels, self.rpn_bbox_levels = logits, deltas
         if self.DEBUG:
             # the reference scrubs NaNs in DEBUG mode (proposals_tf.py:202-209)
             self.proposals = torch.where(torch.isnan(self.proposals), torch.zeros_like(self.proposals), self.proposals)
-        self.rpn_class_probs, self.rpn_bbox = probs, bbox
         if anchors is not None:
             self.input_anchors = anchors
 

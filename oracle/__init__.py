@@ -6,9 +6,11 @@ reference's detection-head algorithm) working on numpy arrays.  Only ``tests/``,
 reference`` legs may import this package; ``objectdetection_b200`` never does.
 
 Parity status: see the header of ``odhead_oracle.c`` — the numpy-only helpers are
-pinned by the reference's own functions (``tests/golden``); every TensorFlow-op
-layer is **parity unpinned** (TensorFlow is not installable here and the
-reference records no outputs for those layers).
+pinned by the reference's own functions (``tests/golden``); the three TensorFlow
+kernels are anchored to TensorFlow's published kernel-test vectors
+(``tests/test_tf_known_answers.py``); the four layers composed from them are
+**parity unpinned** (TensorFlow is not installable here and the reference records
+no outputs for those layers).
 """
 from __future__ import annotations
 
@@ -188,6 +190,22 @@ def proposal_forward(probs, bbox, anchors, stddev, pre_nms_limit: int, post_nms_
                                g("ix"), g("scores"), g("bbox_delta"), g("anchors"), g("anchor_delta"),
                                g("anchor_delta_clipped"), g("keep_idx"), g("num_kept"))
     return (out, d) if debug else out
+
+
+def rpn_levels_to_flat(class_logits_levels, bbox_levels):
+    """The RPN head's output plumbing (numpy): each level's conv outputs [B,H,W,2a] / [B,H,W,4a] are reshaped to
+    [B,-1,2] / [B,-1,4] (rpn.py:54-55, :66), the (bg, fg) pairs go through a softmax (rpn.py:58-59; tf.nn.softmax =
+    exp(x - max) / sum, fp32, exp rounded from fp64 like everywhere in this oracle) and the levels are concatenated
+    along the anchor axis (training.py:163-166). Returns (rpn_class_probs [B,A,2], rpn_bbox [B,A,4])."""
+    probs, boxes = [], []
+    for c, d in zip(class_logits_levels, bbox_levels):
+        c, d = _f32(c), _f32(d)
+        x = c.reshape(c.shape[0], -1, 2)
+        m = x.max(axis=-1, keepdims=True)
+        e = np.exp((x - m).astype(np.float64)).astype(np.float32)
+        probs.append(e / (e[..., :1] + e[..., 1:]))
+        boxes.append(d.reshape(d.shape[0], -1, 4))
+    return np.concatenate(probs, axis=1), np.concatenate(boxes, axis=1)
 
 
 def detection_targets(proposals, gt_class_ids, gt_boxes, perm_pos, perm_neg, rois_per_image: int, stddev):

@@ -4,7 +4,8 @@ A literal numpy transcription of the reference's TF1 graph code, layer by layer,
 each TensorFlow op replaced by a small pure-numpy emulation (``tf_*`` below).  It is
 independent of ``odhead_oracle.c`` (no shared code) so the two restatements check each
 other in ``tests/test_oracle_*.py``; it is slow (Python loops) and meant for small cases.
-**Parity unpinned** for the TF ops themselves (see ``odhead_oracle.c`` header).
+**Parity unpinned** for the layer compositions (see the ``odhead_oracle.c`` header; the TF ops
+themselves are anchored to TensorFlow's published kernel-test vectors).
 
 All float arithmetic is numpy float32 (IEEE single, no FMA); exp/log are evaluated in
 float64 and rounded to float32 — the same convention as the C oracle and the CUDA kernels.

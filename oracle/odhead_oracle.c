@@ -12,15 +12,24 @@
  *              vectors produced by importing the reference's own numpy functions
  *              (tests/golden/make_golden.py) and against the notebook constants
  *              G1–G8 of SURVEY.md §4.
- *   UNPINNED : everything whose arithmetic lives in TensorFlow kernels
- *              (tf.nn.top_k, tf.image.non_max_suppression,
- *              tf.image.crop_and_resize, and the four layers composed from
- *              them). TensorFlow (1.8–1.10, un-pinned and un-vendored by the
- *              reference) is not installable here and the reference ships no
- *              recorded outputs for these layers: "parity unpinned". The
- *              restatement follows the reference's graph code line by line
- *              (cited per function) and the published TF CPU kernels
- *              core/kernels/{topk_op,non_max_suppression_op,crop_and_resize_op}.cc.
+ *   anchored : the three TensorFlow kernels the layers call (tf.nn.top_k,
+ *              tf.image.non_max_suppression, tf.image.crop_and_resize).
+ *              TensorFlow (1.8–1.10, un-pinned and un-vendored by the
+ *              reference) is a third-party dependency absent from the tree and
+ *              not installable here, so these are restated from the published
+ *              CPU kernels core/kernels/{topk_op,non_max_suppression_op,
+ *              crop_and_resize_op}.cc and checked against the known-answer
+ *              vectors of TensorFlow's own kernel tests
+ *              (crop_and_resize_op_test.cc, non_max_suppression_op_test.cc;
+ *              restated in tests/test_tf_known_answers.py — not produced by
+ *              running TensorFlow) and against independent implementations
+ *              (torchvision NMS, torch grid_sample).
+ *   UNPINNED : the four layers composed from those kernels (ProposalLayer,
+ *              PyramidROIAlign, DetectionTargetLayer, DetectionLayer) and the
+ *              mask targets: the reference ships no recorded outputs for them
+ *              and cannot be run here: "parity unpinned". The restatement
+ *              follows the reference's graph code line by line (cited per
+ *              function).
  *
  * Numeric conventions (shared with the CUDA kernels so integer outputs are
  * bit-exact): fp32 arithmetic in the reference's operation order, no FMA

@@ -256,6 +256,36 @@ def test_proposals_coco_shape(training):
         assert not nz[b, int(host(P.num_kept)[b]):].any()
 
 
+def test_proposals_from_rpn_level_outputs():
+    """the layer fed by the RPN head's per-level conv outputs (rpn.py:50-67, training.py:146-166):
+    bit-identical to flattening them on the host (oracle.rpn_levels_to_flat) and running the [B,A,.] layer."""
+    from objectdetection_b200 import Proposals, utils
+    for conf, B, training in ((Conf(), 2, False), (ShapesConfig(), 3, True)):
+        rs = np.random.RandomState(77)
+        shapes = utils.get_resnet_stage_shapes(conf, conf.IMAGE_SHAPE)
+        na = len(conf.RPN_ANCHOR_RATIOS)
+        logits = [rs.normal(0, 2, (B, int(h), int(w), 2 * na)).astype(f32) for h, w in shapes]
+        bbox = [rs.normal(0, 1, (B, int(h), int(w), 4 * na)).astype(f32) for h, w in shapes]
+        probs, flat = oracle.rpn_levels_to_flat(logits, bbox)
+        anchors = oracle.gen_anchors(conf.IMAGE_SHAPE, B, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes,
+                                     conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE)
+        assert probs.shape[1] == anchors.shape[1]
+        P = Proposals(conf, B, training=training, DEBUG=True)
+        P.run_levels([cu(t) for t in logits], [cu(t) for t in bbox], cu(anchors))
+        want = _check_proposals(P, probs, flat, anchors, conf, training)
+        # the [B,A,.] entry point on the flattened tensors gives the same bits; so does regenerating the anchors
+        P1 = Proposals(conf, B, cu(probs), cu(flat), cu(anchors), training=training)
+        assert_bits(host(P1.get_proposals()), want, "flat entry point")
+        spec = utils.anchor_spec(conf.IMAGE_SHAPE, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes,
+                                 conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE)
+        P2 = Proposals(conf, B, training=training, anchor_spec=spec)
+        assert_bits(host(P2.run_levels(logits, bbox)), want, "levels + fused anchors (host inputs)")
+    with pytest.raises(ValueError):
+        P2.run_levels(logits[:2], bbox)
+    with pytest.raises(ValueError):                                    # bbox channel count must be twice the logits'
+        P2.run_levels(logits, [b[..., :4] for b in bbox])
+
+
 def test_proposals_toy_config_with_padding():
     """BASELINE config 1 (shapes.py): 128x128, 4092 anchors, K = min(6000, 4092); low threshold -> zero padded rows."""
     from objectdetection_b200 import Proposals, utils

@@ -307,3 +307,18 @@ def test_mask_targets_oracle_properties():
     assert np.mean(t[2] == coarse) > 0.95
     full = oracle.mask_targets(rois, cls, gt, masks, dbg, (28, 28), False)
     assert full.shape == (R, 28, 28) and (full[0] == 1).all()     # ROI 0 in image coordinates lies inside the mask
+
+
+def test_rpn_levels_to_flat_matches_reshape_softmax_concat():
+    """oracle.rpn_levels_to_flat against an independent torch reshape/softmax/concat (rpn.py:54-66, training.py:163-166)."""
+    torch = pytest.importorskip("torch")
+    rs = np.random.RandomState(3)
+    logits = [rs.normal(0, 3, (2, s, s, 6)).astype(f32) for s in (8, 4, 2)]
+    bbox = [rs.normal(0, 1, (2, s, s, 12)).astype(f32) for s in (8, 4, 2)]
+    probs, flat = oracle.rpn_levels_to_flat(logits, bbox)
+    assert probs.shape == (2, 3 * (64 + 16 + 4), 2) and flat.shape == (2, 252, 4)
+    want = torch.cat([torch.softmax(torch.from_numpy(c).reshape(2, -1, 2).double(), -1) for c in logits], 1).numpy()
+    assert np.allclose(probs, want, rtol=5e-7, atol=1e-9)          # three fp32 roundings
+    assert np.array_equal(flat, np.concatenate([d.reshape(2, -1, 4) for d in bbox], 1))
+    # anchor order inside a level: y, x, anchor (the reshape of NHWC)
+    assert np.array_equal(flat[1, (3 * 8 + 5) * 3 + 2], bbox[0][1, 3, 5, 8:12])
