@@ -18,6 +18,8 @@
  *   od_detection_forward           replaces  DetectionLayer.build           detection.py:80-260
  *   od_unmold_detections           replaces  unmold_detection + denorm_boxes   detection.py:8-53, utils.py:212-227
  *   od_rpn_target_forward          replaces  PreprareTrainData.build_rpn_targets   data_processor.py:173-294
+ *   od_rpn_loss_forward            replaces  Loss.rpn_class_loss / rpn_box_loss       loss_optimize.py:11-87
+ *   od_mrcnn_loss_forward          replaces  Loss.mrcnn_class_loss / mrcnn_box_loss   loss_optimize.py:89-201
  *   od_frcnn_proposal_forward      replaces  FasterRCNN Proposals.build     FasterRCNN/building_blocks/proposals.py:392-512
  *   od_roi_pool_forward            replaces  roi_pool                       FasterRCNN/building_blocks/fastrcnn.py:22-70
  *
@@ -259,6 +261,32 @@ int od_rpn_target_forward(const DLTensor* anchors, const DLTensor* gt_boxes, con
                           const DLTensor* perm_pos, const DLTensor* perm_neg, const od_rpn_target_params* params,
                           DLTensor* rpn_target_class, DLTensor* rpn_target_bbox, DLTensor* positive_anchors,
                           DLTensor* counts, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- head losses, forward values (loss_optimize.py:11-201) ---------- */
+/* Per-element arithmetic is fp32 in the reference's order; the sums are accumulated in fp64 in a fixed order and
+ * rounded to fp32 once (deterministic; equal to TensorFlow's fp32 reductions to ~1e-7 relative).
+ *
+ * od_rpn_loss_forward: Loss.rpn_class_loss (:11-44) and Loss.rpn_box_loss (:47-87).
+ *   rpn_target_class [B,A] or [B,A,1] i32 (+1 positive, -1 negative, 0 neutral), rpn_class_logits [B,A,2] f32 (bg,fg),
+ *   rpn_target_bbox [B,T,4] f32 zero padded, rpn_pred_box [B,A,4] f32 (both NULL: class loss only).
+ *   losses [2] f32 = (rpn_class_loss, rpn_box_loss); either is 0 when nothing contributes (K.switch).
+ *   The r-th positive anchor of image b (ascending) pairs with rpn_target_bbox[b,r]; positives beyond T rows are
+ *   ignored (the reference's shapes would not match there). pred_box_pos [P,4] f32 or NULL receives the gathered
+ *   predictions of the positives in (image, anchor) order (rows past P are dropped); num_pos [1] i32 or NULL. */
+size_t od_rpn_loss_workspace_bytes(int64_t batch, int64_t num_anchors);
+int od_rpn_loss_forward(const DLTensor* rpn_target_class, const DLTensor* rpn_class_logits,
+                        const DLTensor* rpn_target_bbox, const DLTensor* rpn_pred_box,
+                        DLTensor* losses, DLTensor* pred_box_pos, DLTensor* num_pos,
+                        void* ws, size_t ws_bytes, void* stream);
+/* od_mrcnn_loss_forward: Loss.mrcnn_class_loss (:89-151) and Loss.mrcnn_box_loss (:154-201).
+ *   mrcnn_target_class_ids [B,R] i32 zero padded; pred_logits [B,R,C] f32 with batch_active_class_ids [B,C] f32
+ *   (row 0 is the one the reference gathers, :115) and / or target_box [B,R,4] f32 with pred_box [B,R,C,4] f32.
+ *   losses [2] f32 = (sum(ce * pred_active) / sum(pred_active), mean binary cross-entropy over the positive ROIs'
+ *   boxes of their target class — K.binary_crossentropy as the reference has it — or 0 without positives);
+ *   pred_active [B,R] f32 or NULL. A pair that is not passed leaves its loss at 0. */
+int od_mrcnn_loss_forward(const DLTensor* mrcnn_target_class_ids, const DLTensor* pred_logits,
+                          const DLTensor* batch_active_class_ids, const DLTensor* target_box,
+                          const DLTensor* pred_box, DLTensor* losses, DLTensor* pred_active, void* stream);
 
 /* ---- DetectionLayer (detection.py:56-279) ---------------------------------- */
 typedef struct od_detection_params {

@@ -10,7 +10,7 @@ layouts. PyTorch is only the tensor carrier (DLPack, streams, torch.distributed)
 """
 from .config import ShapesConfig, config  # noqa: F401
 
-__all__ = ["config", "ShapesConfig", "Proposals", "MaskRCNN", "BuildDetectionTargets", "DetectionLayer"]
+__all__ = ["config", "ShapesConfig", "Proposals", "MaskRCNN", "BuildDetectionTargets", "DetectionLayer", "Loss"]
 
 
 def __getattr__(name):
@@ -27,4 +27,7 @@ def __getattr__(name):
     if name == "DetectionLayer":
         from .detection import DetectionLayer
         return DetectionLayer
+    if name == "Loss":
+        from .loss_optimize import Loss
+        return Loss
     raise AttributeError(name)

@@ -98,6 +98,9 @@ SIGNATURES = {
     "od_proposal_levels_workspace_bytes": (c_size_t, [c_int64, c_int64, POINTER(ProposalParams)]),
     "od_proposal_forward_levels": (c_int, [POINTER(_P), POINTER(_P), c_int32, _P, POINTER(AnchorSpec), POINTER(ProposalParams),
                                            _P, POINTER(ProposalDebug), _P, c_size_t, _P]),
+    "od_rpn_loss_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "od_rpn_loss_forward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "od_mrcnn_loss_forward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "od_pyramid_roi_align_forward": (c_int, [POINTER(_P), c_int32, c_int32, _P, c_int32, c_int32, c_int32, c_int32,
                                              _P, _P, _P]),
     "od_crop_and_resize": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, _P, _P]),

@@ -319,6 +319,80 @@ def rpn_targets(anchors, gt_boxes, perm_pos, perm_neg, max_rpn_targets: int, std
     return anchors[pos_idx], cls, bbox, counts
 
 
+def _exp32(x):
+    return np.exp(np.asarray(x, np.float32).astype(np.float64)).astype(np.float32)
+
+
+def _log32(x):
+    return np.log(np.asarray(x, np.float32).astype(np.float64)).astype(np.float32)
+
+
+def rpn_losses(rpn_target_class, rpn_class_logits, rpn_target_bbox, rpn_pred_box):
+    """Loss.rpn_class_loss (loss_optimize.py:11-44) and Loss.rpn_box_loss (:47-87), numpy: per-element values in fp32
+    in the reference's operation order, means over fp64 sums. Returns (class_loss, box_loss, rpn_pred_box_pos)."""
+    tc = np.asarray(rpn_target_class).reshape(np.asarray(rpn_class_logits).shape[:2]).astype(np.int32)   # squeeze (:24)
+    lg = _f32(rpn_class_logits)
+    sel = tc != 0                                                   # tf.where(not_equal(., 0)) (:28)
+    x = lg[sel]
+    label = (tc[sel] == 1).astype(np.int64)                         # (:32)
+    if x.shape[0]:
+        m = x.max(-1)
+        s = _exp32(x[:, 0] - m) + _exp32(x[:, 1] - m)
+        ce = _log32(s) - (x[np.arange(x.shape[0]), label] - m)      # sparse_categorical_crossentropy(from_logits)
+        class_loss = np.float32(ce.astype(np.float64).sum() / ce.shape[0])
+    else:
+        class_loss = np.float32(0.0)                                # K.switch (:42)
+    tb, pb = _f32(rpn_target_bbox), _f32(rpn_pred_box)
+    pos = tc == 1
+    pred_pos = pb[pos]                                              # gather_nd over tf.where: (image, anchor) order (:63-64)
+    T = tb.shape[1]
+    tgt, prd = [], []
+    for b in range(tb.shape[0]):
+        n = int(pos[b].sum())                                       # non_pad_count (:68)
+        tgt.append(tb[b, :min(n, T)])                               # rpn_target_bbox[i, :count] (:70-72)
+        prd.append(pb[b][pos[b]][:min(n, T)])
+    tgt, prd = np.concatenate(tgt, 0), np.concatenate(prd, 0)
+    if tgt.size:
+        d = np.abs(tgt - prd)
+        less = (d < np.float32(1.0)).astype(np.float32)
+        l = (np.float32(0.5) * less) * (d * d) + (d - np.float32(0.5)) * (np.float32(1.0) - less)   # (:79-81)
+        box_loss = np.float32(l.astype(np.float64).sum() / l.size)
+    else:
+        box_loss = np.float32(0.0)
+    return class_loss, box_loss, pred_pos
+
+
+def mrcnn_losses(mrcnn_target_class_ids, mrcnn_pred_logits, batch_active_class_ids, mrcnn_target_box, mrcnn_pred_box):
+    """Loss.mrcnn_class_loss (loss_optimize.py:89-151) and Loss.mrcnn_box_loss (:154-201), numpy.
+    Returns (pred_active [B,R], class_loss, box_loss)."""
+    ids = np.asarray(mrcnn_target_class_ids).astype(np.int64)
+    lg, act = _f32(mrcnn_pred_logits), _f32(batch_active_class_ids)
+    B, R, C = lg.shape
+    pred_cls = lg.argmax(-1)                                        # (:113)
+    pred_active = act[0][pred_cls]                                  # tf.gather(batch_active_class_ids[0], .) (:115)
+    m = lg.max(-1)
+    s = np.zeros((B, R), np.float32)
+    for j in range(C):                                              # fp32 sum in class order
+        s = s + _exp32(lg[..., j] - m)
+    ce = _log32(s) - (np.take_along_axis(lg, ids[..., None], -1)[..., 0] - m)   # sparse_softmax_cross_entropy (:139-142)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        class_loss = np.float32((ce * pred_active).astype(np.float64).sum() / pred_active.astype(np.float64).sum())
+    tb, pb = _f32(mrcnn_target_box), _f32(mrcnn_pred_box)
+    posm = ids > 0                                                  # (:171)
+    t = tb[posm]
+    p = pb[posm, ids[posm]]                                         # predicted box of the target class (:180-184)
+    if t.size:
+        eps = np.float32(1e-7)
+        o = np.minimum(np.maximum(p, eps), np.float32(1.0) - eps)   # K.binary_crossentropy: clip, logit, sigmoid CE
+        z = _log32(o / (np.float32(1.0) - o))
+        l1p = np.log1p(_exp32(-np.abs(z)).astype(np.float64)).astype(np.float32)
+        l = (np.maximum(z, np.float32(0.0)) - z * t) + l1p
+        box_loss = np.float32(l.astype(np.float64).sum() / l.size)
+    else:
+        box_loss = np.float32(0.0)
+    return pred_active, class_loss, box_loss
+
+
 def detection_forward(proposals, probs, bbox, window_norm, stddev, min_conf: float, nms_thr: float,
                       max_instances: int, debug: bool = False):
     """DetectionLayer.build. Returns detections [B,M,6] (and intermediates if debug)."""

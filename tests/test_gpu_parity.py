@@ -642,6 +642,67 @@ def test_rpn_targets_golden_and_coco_shape():
             assert counts[0, 0] > T // 2 and counts[0, 2] == T // 2      # positives were dropped through perm_pos
 
 
+# ------------------------------------------------------------------ head losses
+def test_head_losses():
+    """Loss.rpn_class_loss / rpn_box_loss / mrcnn_class_loss / mrcnn_box_loss (loss_optimize.py:11-201): forward values
+    against the numpy oracle, rtol 1e-6 (fp64 sums of identical fp32 terms; the order of the sums differs)."""
+    from objectdetection_b200.loss_optimize import Loss
+    from objectdetection_b200.data_processor import PreprareTrainData
+    rs = np.random.RandomState(4)
+    # (1) COCO shape: labels and targets from the RPN-target builder
+    conf = Conf()
+    P = PreprareTrainData(conf)
+    A, B, T = P.anchors.shape[0], 2, conf.RPN_TRAIN_ANCHORS_PER_IMAGE
+    anc = host(P.anchors)
+    gt = np.zeros((B, 20, 4))
+    for b in range(B):
+        gt[b] = np.round(np.clip(anc[rs.choice(A, 20, replace=False)] + rs.normal(0, 3, (20, 4)), 0, 1024))
+        bad = (gt[b, :, 2] <= gt[b, :, 0]) | (gt[b, :, 3] <= gt[b, :, 1])
+        gt[b, bad] = [100, 100, 164, 164]
+    pp = np.stack([rs.permutation(A) for _ in range(B)]).astype(np.int32)
+    _, tcls, tbox = P.build_rpn_targets(gt, perm_pos=pp, perm_neg=pp)
+    tcls, tbox = host(tcls).reshape(B, A, 1), host(tbox).astype(f32)
+    logits = rs.normal(0, 2, (B, A, 2)).astype(f32)
+    pred = rs.normal(0, 1.5, (B, A, 4)).astype(f32)
+    w_cls, w_box, w_pos = oracle.rpn_losses(tcls, logits, tbox, pred)
+    got_cls = Loss.rpn_class_loss(cu(tcls), cu(logits))
+    got_pos, got_box = Loss.rpn_box_loss(cu(tbox), cu(pred), cu(tcls), B)
+    assert np.isclose(host(got_cls), w_cls, rtol=1e-6) and w_cls > 0
+    assert np.isclose(host(got_box), w_box, rtol=1e-6) and w_box > 0
+    assert np.array_equal(host(got_pos), w_pos) and w_pos.shape[0] > 0
+    c2, b2, _ = Loss.rpn_losses(tcls, logits, tbox, pred)                       # host inputs, one pass for both
+    assert host(c2) == host(got_cls) and host(b2) == host(got_box)              # deterministic
+    # (2) ragged small case: more positives than target rows in one image, none in the other; then all neutral
+    A2, T2 = 2500, 8
+    tc = rs.choice([-1, 0, 1], size=(3, A2), p=[.3, .65, .05]).astype(np.int32)
+    tc[1][tc[1] == 1] = 0
+    lg, tb, pb = rs.normal(0, 2, (3, A2, 2)).astype(f32), rs.normal(0, 1, (3, T2, 4)).astype(f32), rs.normal(0, 1, (3, A2, 4)).astype(f32)
+    w = oracle.rpn_losses(tc, lg, tb, pb)
+    g = Loss.rpn_losses(tc, lg, tb, pb, want_pos=True)
+    assert np.isclose(host(g[0]), w[0], rtol=1e-6) and np.isclose(host(g[1]), w[1], rtol=1e-6)
+    assert np.array_equal(host(g[2]), w[2][:g[2].shape[0]]) and g[2].shape[0] == min(w[2].shape[0], 3 * T2)
+    g = Loss.rpn_losses(np.zeros_like(tc), lg, tb, pb)
+    assert host(g[0]) == 0.0 and host(g[1]) == 0.0
+    # (3) detection-head losses: the reference's debug() recipe (loss_optimize.py:209-219) and the COCO training shape
+    for Bm, R, C in ((2, 32, 4), (8, 200, 81)):
+        ids = np.zeros((Bm, R), np.int32)
+        if C == 4:
+            ids[0, 2], ids[0, 3], ids[1, 4] = 1, 2, 1
+        else:
+            ids[:, :66] = rs.randint(1, C, (Bm, 66))
+        tb2, pb2 = rs.random_sample((Bm, R, 4)).astype(f32), rs.random_sample((Bm, R, C, 4)).astype(f32)
+        pb2[0, 2, ids[0, 2]] = [0.0, 1.0, 0.5, 1e-9]                            # exercises the epsilon clip
+        lg2 = rs.normal(0, 2, (Bm, R, C)).astype(f32)
+        act = (rs.random_sample((Bm, C)) > 0.3).astype(f32)
+        act[:, 0] = 1
+        w_pa, w_c, w_b = oracle.mrcnn_losses(ids, lg2, act, tb2, pb2)
+        pa, c = Loss.mrcnn_class_loss(cu(ids), cu(lg2), cu(act))
+        bl = Loss.mrcnn_box_loss(cu(tb2), cu(pb2), cu(ids), batch_size=Bm)
+        assert np.array_equal(host(pa), w_pa)
+        assert np.isclose(host(c), w_c, rtol=1e-6) and np.isclose(host(bl), w_b, rtol=1e-6)
+        assert host(Loss.mrcnn_box_loss(tb2, pb2, np.zeros_like(ids), batch_size=Bm)) == 0.0
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_are_loud():
     from objectdetection_b200 import _lib

@@ -322,3 +322,46 @@ def test_rpn_levels_to_flat_matches_reshape_softmax_concat():
     assert np.array_equal(flat, np.concatenate([d.reshape(2, -1, 4) for d in bbox], 1))
     # anchor order inside a level: y, x, anchor (the reshape of NHWC)
     assert np.array_equal(flat[1, (3 * 8 + 5) * 3 + 2], bbox[0][1, 3, 5, 8:12])
+
+
+def test_head_losses_oracle_vs_torch():
+    """oracle.rpn_losses / mrcnn_losses (loss_optimize.py:11-201) against independent torch float64 formulas."""
+    torch = pytest.importorskip("torch")
+    F = torch.nn.functional
+    rs = np.random.RandomState(0)
+    B, A, T = 2, 500, 16
+    tc = rs.choice([-1, 0, 1], size=(B, A, 1), p=[.3, .65, .05]).astype(np.int32)
+    lg = rs.normal(0, 2, (B, A, 2)).astype(f32)
+    tb, pb = rs.normal(0, 1, (B, T, 4)).astype(f32), rs.normal(0, 1, (B, A, 4)).astype(f32)
+    cl, bl, pos = oracle.rpn_losses(tc, lg, tb, pb)
+    sel = torch.from_numpy(tc[..., 0] != 0)
+    want = F.cross_entropy(torch.from_numpy(lg)[sel].double(), torch.from_numpy(tc[..., 0] == 1)[sel].long())
+    assert np.isclose(cl, float(want), rtol=1e-6)
+    tg, pr = [], []
+    for i in range(B):
+        m = tc[i, :, 0] == 1
+        n = min(int(m.sum()), T)
+        tg.append(tb[i, :n])
+        pr.append(pb[i][m][:n])
+    want = F.smooth_l1_loss(torch.from_numpy(np.concatenate(pr)).double(), torch.from_numpy(np.concatenate(tg)).double())
+    assert np.isclose(bl, float(want), rtol=1e-6)
+    assert np.array_equal(pos, pb[tc[..., 0] == 1])
+    z = np.zeros_like(tc)
+    assert oracle.rpn_losses(z, lg, tb, pb)[:2] == (0.0, 0.0)                   # K.switch(size > 0, ., 0)
+    # the reference's debug() recipe for the detection-head losses (loss_optimize.py:209-219)
+    R, C = 32, 4
+    ids = np.zeros((2, R), np.int32)
+    ids[0, 2], ids[0, 3], ids[1, 4] = 1, 2, 1
+    tb2, pb2 = rs.random_sample((2, R, 4)).astype(f32), rs.random_sample((2, R, C, 4)).astype(f32)
+    lg2 = rs.normal(0, 2, (2, R, C)).astype(f32)
+    act = np.array([[1, 1, 0, 1], [1, 0, 0, 0]], f32)
+    pa, cl2, bl2 = oracle.mrcnn_losses(ids, lg2, act, tb2, pb2)
+    ce = F.cross_entropy(torch.from_numpy(lg2).double().reshape(-1, C), torch.from_numpy(ids).long().reshape(-1),
+                         reduction="none").reshape(2, R)
+    pa_w = torch.from_numpy(act)[0][torch.from_numpy(lg2).argmax(-1)]
+    assert np.array_equal(pa, pa_w.numpy())
+    assert np.isclose(cl2, float((ce * pa_w).sum() / pa_w.sum()), rtol=1e-6)
+    m = ids > 0
+    want = F.binary_cross_entropy(torch.from_numpy(pb2[m, ids[m]]).double(), torch.from_numpy(tb2[m]).double())
+    assert np.isclose(bl2, float(want), rtol=1e-5)
+    assert oracle.mrcnn_losses(np.zeros_like(ids), lg2, act, tb2, pb2)[2] == 0.0
