@@ -342,6 +342,179 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
   if (num_kept && tid == 0) num_kept[b] = kept_total;
 }
 
+// ---- wide scan: K too large for the shared-memory ring (K > ~12000) -------------------------------------------------
+// The serial part of greedy NMS is only the 64x64 diagonal fixed point per chunk; the OR of the kept rows into the
+// `removed` bitmap is spread over G co-resident CTAs (cooperative launch). CTA g owns words [g*S, (g+1)*S) of the bitmap:
+// it consumes the keep words the owners of earlier chunks publish (acquire/release flags, up to 32 chunks per step),
+// ORs those rows' words of its slice, then resolves its own S chunks one after the other and publishes them. The
+// hand-over between owners costs one flag round trip per S chunks; everything else overlaps.
+constexpr int kWideThreads = 256;
+constexpr int kWideBatch = 32;   // chunks consumed per step
+struct WideSync {
+  unsigned long long keep;   // kept rows of the chunk
+  int32_t cum;               // boxes kept up to and including the chunk
+  int32_t flag;              // 0 pending, 1 published, 2 published and final (max_out reached or last chunk)
+};
+__device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int32_t v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kWideThreads)
+nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned long long* __restrict__ diagT,
+                     const int32_t* __restrict__ num_valid, int K, int W, int Ws, int S, int max_out, WideSync* __restrict__ sync,
+                     int32_t* __restrict__ keep_pos, int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
+  extern __shared__ __align__(16) unsigned long long wide_smem[];
+  unsigned long long* removed = wide_smem;        // [S] my slice of the bitmap
+  __shared__ unsigned long long kb_s[kWideBatch];
+  __shared__ int32_t rows_s[kWideBatch * 64];     // kept rows of the chunks of this step
+  __shared__ int32_t ctl[4];                      // [0] chunks ready, [1] stop seen, [2] kept rows listed, [3] kept_total
+  const int b = blockIdx.y, g = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = num_valid ? min(num_valid[b], K) : K;
+  const int Wn = (n + 63) / 64;
+  const int lo = g * S, hi = min(lo + S, Wn);
+  const unsigned long long* mrow = mask + (int64_t)b * K * Ws;
+  const unsigned long long* dimg = diagT + (int64_t)b * W * 64;
+  WideSync* sy = sync + (int64_t)b * W;
+  if (Wn == 0) {   // empty image: CTA 0 reports
+    if (g == 0) {
+      if (keep_pos)
+        for (int j = tid; j < max_out; j += kWideThreads) keep_pos[(int64_t)b * max_out + j] = -1;
+      if (num_kept && tid == 0) num_kept[b] = 0;
+    }
+    return;
+  }
+  if (lo >= Wn) return;
+  for (int j = tid; j < S; j += kWideThreads) removed[j] = 0ull;
+  if (keep_flag)
+    for (int i = lo * 64 + tid; i < min(hi * 64, K); i += kWideThreads) keep_flag[(int64_t)b * K + i] = 0;
+  if (g == 0 && keep_flag)   // boxes past the valid ones belong to nobody's chunks
+    for (int i = Wn * 64 + tid; i < K; i += kWideThreads) keep_flag[(int64_t)b * K + i] = 0;
+  if (tid == 0) ctl[3] = 0;
+  __syncthreads();
+  const int Sw = hi - lo;   // live words of my slice
+
+  // ---- phase A: chunks owned by earlier CTAs
+  int c = 0;
+  while (c < lo) {
+    if (warp == 0) {
+      int f = 0;
+      if (c + lane < lo) f = ld_acquire(&sy[c + lane].flag);
+      const uint32_t ready = __ballot_sync(0xffffffffu, f != 0);
+      const int nready = (ready == 0xffffffffu) ? 32 : (__ffs((int)~ready) - 1);
+      unsigned long long kb = 0ull;
+      if (lane < nready) kb = sy[c + lane].keep;
+      const uint32_t stop = __ballot_sync(0xffffffffu, lane < nready && f == 2);
+      // list the kept rows of the ready chunks
+      const int cnt = __popcll(kb);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int base = incl - cnt;
+      unsigned long long bits = kb;
+      while (bits) {
+        const int r = __ffsll((long long)bits) - 1;
+        bits &= bits - 1ull;
+        rows_s[base++] = (c + lane) * 64 + r;
+      }
+      if (lane == 31) ctl[2] = incl;
+      if (lane == 0) {
+        ctl[0] = nready;
+        ctl[1] = stop != 0u;
+      }
+      if (nready > 0 && lane == nready - 1) ctl[3] = sy[c + lane].cum;
+    }
+    __syncthreads();
+    const int nready = ctl[0], nrows = ctl[2];
+    const bool stop = ctl[1] != 0;
+    if (stop) return;   // max_out was reached before my chunks: nothing left for me
+    if (nready > 0 && nrows > 0) {
+      // thread -> (word j of my slice, row lane q): consecutive threads read consecutive words of one row
+      const int j = tid % Sw, q0 = tid / Sw, qstep = kWideThreads / Sw;
+      if (q0 < qstep) {
+        unsigned long long acc = 0ull;
+        for (int q = q0; q < nrows; q += qstep) acc |= __ldg(&mrow[(size_t)rows_s[q] * Ws + lo + j]);
+        if (acc) atomicOr(&removed[j], acc);
+      }
+    }
+    __syncthreads();
+    c += nready;
+  }
+
+  // ---- phase B: my own chunks, one at a time
+  int kept_total = ctl[3];
+  unsigned long long nsup0 = 0ull, nsup1 = 0ull;
+  if (warp == 0) {
+    nsup0 = __ldg(&dimg[(size_t)lo * 64 + lane]);
+    nsup1 = __ldg(&dimg[(size_t)lo * 64 + lane + 32]);
+  }
+  for (c = lo; c < hi; ++c) {
+    if (warp == 0) {
+      const unsigned long long sup0 = nsup0, sup1 = nsup1;
+      if (c + 1 < hi) {
+        nsup0 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane]);
+        nsup1 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane + 32]);
+      }
+      const unsigned long long word = removed[c - lo];
+      const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
+      const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
+      unsigned long long kept = (unsigned long long)__ballot_sync(0xffffffffu, cand0) |
+                                ((unsigned long long)__ballot_sync(0xffffffffu, cand1) << 32);
+      for (int it = 0; it < 64; ++it) {
+        const bool k0 = cand0 && !(sup0 & kept);
+        const bool k1 = cand1 && !(sup1 & kept);
+        const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+        if (nk == kept) break;
+        kept = nk;
+      }
+      const int allow = max_out - kept_total;
+      while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
+      const int total = kept_total + __popcll(kept);
+      if (lane == 0) {
+        kb_s[0] = kept;
+        sy[c].keep = kept;
+        sy[c].cum = total;
+        st_release(&sy[c].flag, (total >= max_out || c == Wn - 1) ? 2 : 1);
+      }
+    }
+    __syncthreads();
+    const unsigned long long kept = kb_s[0];
+    if (tid < 64 && ((kept >> tid) & 1ull)) {
+      const int pos = kept_total + __popcll(kept & ((1ull << tid) - 1ull));
+      if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = c * 64 + tid;
+      if (keep_flag) keep_flag[(int64_t)b * K + c * 64 + tid] = 1;
+    }
+    kept_total += __popcll(kept);
+    if (kept_total >= max_out || c == Wn - 1) {   // I published the final chunk: report
+      if (keep_pos)
+        for (int j = kept_total + tid; j < max_out; j += kWideThreads) keep_pos[(int64_t)b * max_out + j] = -1;
+      if (num_kept && tid == 0) num_kept[b] = kept_total;
+      return;
+    }
+    // OR my kept rows into the rest of my slice (words c+1-lo .. Sw-1)
+    const int live = hi - c - 1;
+    if (kept != 0ull && live > 0) {
+      const int j = tid % live, q0 = tid / live, qstep = kWideThreads / live;
+      if (q0 < qstep) {
+        unsigned long long acc = 0ull;
+        for (int r = q0; r < 64; r += qstep)
+          if ((kept >> r) & 1ull) acc |= __ldg(&mrow[(size_t)(c * 64 + r) * Ws + c + 1 + j]);
+        if (acc) atomicOr(&removed[c + 1 - lo + j], acc);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // int32 words of per-image scan state for the two-round NMS: kept count (+ pad) and the removed bitmap
 static int64_t scan_state_stride(int64_t W) { return 2 + 2 * ((W + 15) & ~(int64_t)15); }
 
@@ -351,13 +524,30 @@ size_t nms_sorted_workspace_bytes(int64_t B, int64_t K) {
   w.take<unsigned long long>((size_t)(B * K * Ws));
   w.take<unsigned long long>((size_t)(B * W * 64));
   w.take<unsigned long long>((size_t)(B * scan_state_stride(W) / 2 + 1));
+  w.take<WideSync>((size_t)(B * W + 1));
   return w.off + 256;
+}
+
+// Words of the bitmap per CTA of the wide scan so that all B * ceil(W / S) CTAs are co-resident; 0 = not possible.
+static int wide_scan_slice(int64_t B, int W) {
+  int dev = 0, sms = 0, occ = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_scan_wide_kernel, kWideThreads, 128 * sizeof(unsigned long long)) != cudaSuccess)
+    return 0;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  const int64_t per_image = coop ? ((int64_t)sms * occ) / B : 0;
+  if (per_image < 1) return 0;
+  int64_t G = (W + 3) / 4;   // at least four words per CTA
+  if (G > per_image) G = per_image;
+  const int S = (int)((W + G - 1) / G);
+  return S <= 128 ? S : 0;
 }
 
 static int scan_round_launch(const unsigned long long* mask, const unsigned long long* diagT, const int32_t* num_valid,
                              int64_t B, int64_t K, int64_t mask_stride, int64_t max_out, int c_begin, int c_end,
                              int final_round, int32_t* scan_state, int32_t* keep_pos, int32_t* num_kept, int32_t* keep_flag,
-                             cudaStream_t st) {
+                             WideSync* wide, cudaStream_t st) {
   const int W = (int)((K + 63) / 64), Ws = (int)mask_stride;
   if (Ws < W) OD_FAIL(OD_ERR_PARAM, "NMS mask stride %d < %d words", Ws, W);
   const size_t plain = (size_t)((W + 15) & ~15) * sizeof(unsigned long long);
@@ -377,6 +567,17 @@ static int scan_round_launch(const unsigned long long* mask, const unsigned long
     nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, nslots, (int)max_out,
                                                                    c_begin, c_end, final_round, scan_state, stride, keep_pos,
                                                                    num_kept, keep_flag);
+  } else if (wide && !scan_state && c_begin == 0 && c_end >= W && W >= 64 && wide_scan_slice(B, W) > 0) {
+    // too many boxes for the ring: spread the OR phase over co-resident CTAs
+    int S = wide_scan_slice(B, W), Ki = (int)K, mo = (int)max_out;
+    const dim3 grid((unsigned)((W + S - 1) / S), (unsigned)B);
+    OD_CUDA(cudaMemsetAsync(wide, 0, (size_t)B * W * sizeof(WideSync), st));
+    int Wi = W, Wsi = Ws;
+    void* args[] = {(void*)&mask, (void*)&diagT, (void*)&num_valid, &Ki, &Wi, &Wsi, &S, &mo, &wide, &keep_pos, &num_kept, &keep_flag};
+    OD_CUDA(cudaLaunchCooperativeKernel((const void*)nms_scan_wide_kernel, grid, dim3(kWideThreads), args,
+                                        (size_t)S * sizeof(unsigned long long), st));
+    OD_LAUNCH_CHECK("nms_scan_wide_kernel");
+    return OD_OK;
   } else {
     const size_t smem = plain > 0 ? plain : 128;
     if (smem > 48 * 1024)
@@ -400,9 +601,10 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
   unsigned long long* mask = w.take<unsigned long long>((size_t)(B * K * Ws));
   unsigned long long* diagT = w.take<unsigned long long>((size_t)(B * W * 64));
   int32_t* state = reinterpret_cast<int32_t*>(w.take<unsigned long long>((size_t)(B * scan_state_stride(W) / 2 + 1)));
+  WideSync* wide = w.take<WideSync>((size_t)(B * W + 1));
   if (!ws || !w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "NMS workspace %zu < %zu bytes", ws_bytes, w.off);
   if (K == 0)
-    return scan_round_launch(mask, diagT, num_valid, B, K, Ws, max_out, 0, 0, 1, nullptr, keep_pos, num_kept, keep_flag, st);
+    return scan_round_launch(mask, diagT, num_valid, B, K, Ws, max_out, 0, 0, 1, nullptr, keep_pos, num_kept, keep_flag, nullptr, st);
   if (W > 65535) OD_FAIL(OD_ERR_PARAM, "NMS tile grid too large");
   // Two rounds when far fewer boxes are wanted than offered (proposals: 1000 of 6000): the first round covers the row
   // chunks that normally suffice (1.5 x max_out boxes); the second one - the remaining rows - returns at once on the
@@ -423,7 +625,7 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
                                                             stride, Ws, mask, diagT);
     OD_LAUNCH_CHECK("nms_mask_kernel");
     OD_CHECK(scan_round_launch(mask, diagT, num_valid, B, K, Ws, max_out, rb0, rb1, round == (two_rounds ? 1 : 0),
-                               two_rounds ? state : nullptr, keep_pos, num_kept, keep_flag, st));
+                               two_rounds ? state : nullptr, keep_pos, num_kept, keep_flag, wide, st));
   }
   return OD_OK;
 }
@@ -433,7 +635,7 @@ int nms_scan_launch(const unsigned long long* mask, const unsigned long long* di
                     int32_t* keep_flag, cudaStream_t st) {
   const int W = (int)((K + 63) / 64);
   return scan_round_launch(mask, diagT, num_valid, B, K, mask_stride, max_out, 0, W, 1, nullptr, keep_pos, num_kept,
-                           keep_flag, st);
+                           keep_flag, nullptr, st);
 }
 
 // ---- unsorted front-end (tf.image.non_max_suppression on arbitrary score order)

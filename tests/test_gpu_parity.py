@@ -182,6 +182,33 @@ def test_nms_num_valid_and_single_image_form():
     assert host(num)[0] == want.shape[0] and np.array_equal(host(keep)[0, :want.shape[0]], want)
 
 
+@pytest.mark.parametrize("B,K,max_out,clustered", [(2, 20000, 20000, True), (1, 30000, 21000, False), (3, 13000, 13000, False)])
+def test_nms_wide_scan(B, K, max_out, clustered):
+    """K beyond the shared-memory ring with max_out ~ K: the multi-CTA scan (bitmap slices, published keep words).
+    Clustered boxes (few survivors, all chunks visited), sparse boxes (max_out reached on the way), ragged num_valid."""
+    from objectdetection_b200.proposals import non_max_suppression
+    rs = np.random.RandomState(K + B)
+    if clustered:
+        centers, sizes = rs.uniform(0.1, 0.9, (B, 300, 2)), rs.uniform(0.02, 0.1, (B, 300, 2))
+        which = rs.randint(0, 300, (B, K))
+        c = np.take_along_axis(centers, which[..., None].repeat(2, -1), 1) + rs.normal(0, 0.004, (B, K, 2))
+        hw = np.take_along_axis(sizes, which[..., None].repeat(2, -1), 1) * np.exp(rs.normal(0, 0.06, (B, K, 2)))
+        boxes = np.concatenate([c - hw / 2, c + hw / 2], -1).astype(f32)
+    else:
+        boxes = np.stack([_synth.rois_log_uniform(rs, 1, K, image=4096, lo=4, hi=48)[0] for _ in range(B)])
+    scores = rs.random_sample((B, K)).astype(f32)
+    nv = np.array([K, K - 1777, 64][:B], np.int32)
+    keep, num = non_max_suppression(cu(boxes), cu(scores), max_out, 0.5, num_valid=nv)
+    keep, num = host(keep), host(num)
+    capped = False
+    for b in range(B):
+        want = oracle.nms(boxes[b, :nv[b]], scores[b, :nv[b]], max_out, 0.5)
+        assert num[b] == want.shape[0], (b, num[b], want.shape[0])
+        assert np.array_equal(keep[b, :num[b]], want) and np.all(keep[b, num[b]:] == -1)
+        capped |= want.shape[0] == max_out
+    assert capped == (K == 30000)
+
+
 def test_nms_stress_100k_boxes():
     """BASELINE config 5: 100,000 boxes, one image, thr 0.5; sqrt(area) log-uniform [8,256] px in 4096^2."""
     from objectdetection_b200.proposals import non_max_suppression
