@@ -350,11 +350,19 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
 // hand-over between owners costs one flag round trip per S chunks; everything else overlaps.
 constexpr int kWideThreads = 256;
 constexpr int kWideBatch = 32;   // chunks consumed per step
+constexpr int kWideMaxS = 128;   // most bitmap words per CTA
 struct WideSync {
   unsigned long long keep;   // kept rows of the chunk
   int32_t cum;               // boxes kept up to and including the chunk
   int32_t flag;              // 0 pending, 1 published, 2 published and final (max_out reached or last chunk)
 };
+// 64-bit OR into shared memory as two native 32-bit atomics (a 64-bit shared atomicOr is a compare-and-swap loop,
+// slow when ~25 threads target one word)
+__device__ __forceinline__ void smem_or64(unsigned long long* p, unsigned long long v) {
+  uint32_t* h = reinterpret_cast<uint32_t*>(p);
+  if ((uint32_t)v) atomicOr(h, (uint32_t)v);
+  if ((uint32_t)(v >> 32)) atomicOr(h + 1, (uint32_t)(v >> 32));
+}
 __device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
   int32_t v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -364,13 +372,23 @@ __device__ __forceinline__ void st_release(int32_t* p, int32_t v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+constexpr int kWidePrefetchMaxS = 16;   // S*64 rows x S words of the diagonal block in shared memory: 128 KB at S = 16
+template <bool PREFETCH>
 __global__ void __launch_bounds__(kWideThreads)
 nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned long long* __restrict__ diagT,
                      const int32_t* __restrict__ num_valid, int K, int W, int Ws, int S, int max_out, WideSync* __restrict__ sync,
-                     int32_t* __restrict__ keep_pos, int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
+                     int32_t* __restrict__ keep_pos, int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag,
+                     int two_blocks) {
   extern __shared__ __align__(16) unsigned long long wide_smem[];
   unsigned long long* removed = wide_smem;        // [S] my slice of the bitmap
-  __shared__ unsigned long long kb_s[kWideBatch];
+  // PREFETCH: my own diagonal block (rows of my chunks x words of my slice), fetched while the earlier owners work, so
+  // that the one-chunk-at-a-time phase below never waits for global memory
+  unsigned long long* dtile = wide_smem + ((S + 1) & ~1);   // [S][64] transposed diagonal tiles of my chunks
+  unsigned long long* blk = dtile + (size_t)S * 64;         // [S*64][S]
+  // two_blocks: also the previous owner's rows x my words, so that the hand-over (his last chunks -> my first fixed
+  // point) does not wait for global memory either
+  unsigned long long* blk2 = blk + (size_t)64 * S * S;      // [S*64][S]
+  __shared__ unsigned long long kb_s[kWideMaxS];   // keep words of my own chunks
   __shared__ int32_t rows_s[kWideBatch * 64];     // kept rows of the chunks of this step
   __shared__ int32_t ctl[4];                      // [0] chunks ready, [1] stop seen, [2] kept rows listed, [3] kept_total
   const int b = blockIdx.y, g = blockIdx.x;
@@ -378,6 +396,7 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
   const int n = num_valid ? min(num_valid[b], K) : K;
   const int Wn = (n + 63) / 64;
   const int lo = g * S, hi = min(lo + S, Wn);
+  const int prev_row0 = (lo - S) * 64;
   const unsigned long long* mrow = mask + (int64_t)b * K * Ws;
   const unsigned long long* dimg = diagT + (int64_t)b * W * 64;
   WideSync* sy = sync + (int64_t)b * W;
@@ -396,17 +415,33 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
   if (g == 0 && keep_flag)   // boxes past the valid ones belong to nobody's chunks
     for (int i = Wn * 64 + tid; i < K; i += kWideThreads) keep_flag[(int64_t)b * K + i] = 0;
   if (tid == 0) ctl[3] = 0;
-  __syncthreads();
   const int Sw = hi - lo;   // live words of my slice
+  for (int i = tid; i < Sw * 64; i += kWideThreads) dtile[i] = __ldg(&dimg[(size_t)lo * 64 + i]);
+  if (PREFETCH) {
+    const int nrows = Sw * 64;
+    for (int i = tid; i < nrows * Sw; i += kWideThreads) {
+      const int r = i / Sw, j = i - r * Sw;
+      blk[(size_t)r * S + j] = __ldg(&mrow[(size_t)min(lo * 64 + r, K - 1) * Ws + lo + j]);
+    }
+    if (two_blocks && lo > 0)
+      for (int i = tid; i < S * 64 * Sw; i += kWideThreads) {
+        const int r = i / Sw, j = i - r * Sw;
+        blk2[(size_t)r * S + j] = __ldg(&mrow[(size_t)(prev_row0 + r) * Ws + lo + j]);
+      }
+  }
+  __syncthreads();
 
   // ---- phase A: chunks owned by earlier CTAs
   int c = 0;
   while (c < lo) {
     if (warp == 0) {
-      int f = 0;
-      if (c + lane < lo) f = ld_acquire(&sy[c + lane].flag);
-      const uint32_t ready = __ballot_sync(0xffffffffu, f != 0);
-      const int nready = (ready == 0xffffffffu) ? 32 : (__ffs((int)~ready) - 1);
+      int f, nready;
+      do {   // the other warps wait at the barrier below; only this warp polls
+        f = 0;
+        if (c + lane < lo) f = ld_acquire(&sy[c + lane].flag);
+        const uint32_t ready = __ballot_sync(0xffffffffu, f != 0);
+        nready = (ready == 0xffffffffu) ? 32 : (__ffs((int)~ready) - 1);
+      } while (nready == 0);
       unsigned long long kb = 0ull;
       if (lane < nready) kb = sy[c + lane].keep;
       const uint32_t stop = __ballot_sync(0xffffffffu, lane < nready && f == 2);
@@ -441,8 +476,23 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
       const int j = tid % Sw, q0 = tid / Sw, qstep = kWideThreads / Sw;
       if (q0 < qstep) {
         unsigned long long acc = 0ull;
-        for (int q = q0; q < nrows; q += qstep) acc |= __ldg(&mrow[(size_t)rows_s[q] * Ws + lo + j]);
-        if (acc) atomicOr(&removed[j], acc);
+        for (int q = q0; q < nrows; q += 8 * qstep) {   // eight independent loads in flight (DRAM latency ~1 us)
+          unsigned long long v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int qq = q + u * qstep;
+            unsigned long long x = 0ull;
+            if (qq < nrows) {
+              const int row = rows_s[qq];
+              x = (PREFETCH && two_blocks && row >= prev_row0) ? blk2[(size_t)(row - prev_row0) * S + j]
+                                                                : __ldg(&mrow[(size_t)row * Ws + lo + j]);
+            }
+            v[u] = x;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc |= v[u];
+        }
+        smem_or64(&removed[j], acc);
       }
     }
     __syncthreads();
@@ -451,18 +501,11 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
 
   // ---- phase B: my own chunks, one at a time
   int kept_total = ctl[3];
-  unsigned long long nsup0 = 0ull, nsup1 = 0ull;
-  if (warp == 0) {
-    nsup0 = __ldg(&dimg[(size_t)lo * 64 + lane]);
-    nsup1 = __ldg(&dimg[(size_t)lo * 64 + lane + 32]);
-  }
+  const int kept_before = kept_total;
+  bool final_mine = false;
   for (c = lo; c < hi; ++c) {
     if (warp == 0) {
-      const unsigned long long sup0 = nsup0, sup1 = nsup1;
-      if (c + 1 < hi) {
-        nsup0 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane]);
-        nsup1 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane + 32]);
-      }
+      const unsigned long long sup0 = dtile[(c - lo) * 64 + lane], sup1 = dtile[(c - lo) * 64 + lane + 32];
       const unsigned long long word = removed[c - lo];
       const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
       const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
@@ -478,40 +521,68 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
       }
       const int allow = max_out - kept_total;
       while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
-      const int total = kept_total + __popcll(kept);
-      if (lane == 0) {
-        kb_s[0] = kept;
-        sy[c].keep = kept;
-        sy[c].cum = total;
-        st_release(&sy[c].flag, (total >= max_out || c == Wn - 1) ? 2 : 1);
-      }
+      if (lane == 0) kb_s[c - lo] = kept;   // (kb_s has kWideBatch >= S entries when the results are buffered)
     }
     __syncthreads();
-    const unsigned long long kept = kb_s[0];
-    if (tid < 64 && ((kept >> tid) & 1ull)) {
-      const int pos = kept_total + __popcll(kept & ((1ull << tid) - 1ull));
-      if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = c * 64 + tid;
-      if (keep_flag) keep_flag[(int64_t)b * K + c * 64 + tid] = 1;
-    }
+    const unsigned long long kept = kb_s[c - lo];
     kept_total += __popcll(kept);
-    if (kept_total >= max_out || c == Wn - 1) {   // I published the final chunk: report
-      if (keep_pos)
-        for (int j = kept_total + tid; j < max_out; j += kWideThreads) keep_pos[(int64_t)b * max_out + j] = -1;
-      if (num_kept && tid == 0) num_kept[b] = kept_total;
-      return;
+    if (kept_total >= max_out || c == Wn - 1) {   // the final chunk is mine
+      final_mine = true;
+      ++c;
+      break;
     }
     // OR my kept rows into the rest of my slice (words c+1-lo .. Sw-1)
     const int live = hi - c - 1;
     if (kept != 0ull && live > 0) {
-      const int j = tid % live, q0 = tid / live, qstep = kWideThreads / live;
-      if (q0 < qstep) {
-        unsigned long long acc = 0ull;
-        for (int r = q0; r < 64; r += qstep)
-          if ((kept >> r) & 1ull) acc |= __ldg(&mrow[(size_t)(c * 64 + r) * Ws + c + 1 + j]);
-        if (acc) atomicOr(&removed[c + 1 - lo + j], acc);
+      if (PREFETCH) {
+        // a warp per word, a lane per row (two rows each): OR-reduce across the warp, no atomics
+        const bool r0 = (kept >> lane) & 1ull, r1 = (kept >> (lane + 32)) & 1ull;
+        for (int j = warp; j < live; j += kWideThreads / 32) {
+          const unsigned long long* col = blk + (size_t)((c - lo) * 64) * S + c + 1 - lo + j;
+          const unsigned long long v = (r0 ? col[(size_t)lane * S] : 0ull) | (r1 ? col[(size_t)(lane + 32) * S] : 0ull);
+          const uint32_t vlo = __reduce_or_sync(0xffffffffu, (uint32_t)v), vhi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+          if (lane == 0) removed[c + 1 - lo + j] |= ((unsigned long long)vhi << 32) | vlo;
+        }
+      } else {
+        const int j = tid % live, q0 = tid / live, qstep = kWideThreads / live;
+        if (q0 < qstep) {
+          unsigned long long acc = 0ull;
+          for (int r = q0; r < 64; r += qstep)
+            if ((kept >> r) & 1ull) acc |= __ldg(&mrow[(size_t)(c * 64 + r) * Ws + c + 1 + j]);
+          smem_or64(&removed[c + 1 - lo + j], acc);
+        }
       }
     }
     __syncthreads();
+  }
+  // My chunks lo .. c-1 are resolved (keep words in kb_s): publish them together - a release per chunk would sit on the
+  // critical path - then write the outputs, which nobody waits for.
+  const int done = c - lo;
+  if (tid < done) {
+    int cum = kept_before;
+    for (int i = 0; i <= tid; ++i) cum += __popcll(kb_s[i]);
+    sy[lo + tid].keep = kb_s[tid];
+    sy[lo + tid].cum = cum;
+    st_release(&sy[lo + tid].flag, (final_mine && tid == done - 1) ? 2 : 1);
+  }
+  for (int i = warp; i < done; i += kWideThreads / 32) {
+    int base = kept_before;
+    for (int q = 0; q < i; ++q) base += __popcll(kb_s[q]);
+    const unsigned long long kept = kb_s[i];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lane + 32 * h;
+      if ((kept >> r) & 1ull) {
+        const int pos = base + __popcll(kept & ((1ull << r) - 1ull));
+        if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = (lo + i) * 64 + r;
+        if (keep_flag) keep_flag[(int64_t)b * K + (lo + i) * 64 + r] = 1;
+      }
+    }
+  }
+  if (final_mine) {
+    if (keep_pos)
+      for (int j = kept_total + tid; j < max_out; j += kWideThreads) keep_pos[(int64_t)b * max_out + j] = -1;
+    if (num_kept && tid == 0) num_kept[b] = kept_total;
   }
 }
 
@@ -529,19 +600,44 @@ size_t nms_sorted_workspace_bytes(int64_t B, int64_t K) {
 }
 
 // Words of the bitmap per CTA of the wide scan so that all B * ceil(W / S) CTAs are co-resident; 0 = not possible.
-static int wide_scan_slice(int64_t B, int W) {
-  int dev = 0, sms = 0, occ = 0;
+// *prefetch: the slice is small enough for the diagonal block to live in shared memory.
+static size_t wide_scan_smem(int S, int blocks) {   // blocks of S*64 rows x S words staged in shared memory: 0, 1 or 2
+  return ((size_t)((S + 1) & ~1) + (size_t)64 * S + (size_t)blocks * 64 * S * S) * sizeof(unsigned long long);
+}
+static int wide_scan_blocks(int S) { return wide_scan_smem(S, 2) <= 200 * 1024 ? 2 : 1; }
+static int wide_scan_slice(int64_t B, int W, bool* prefetch) {
+  int dev = 0, sms = 0, coop = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_scan_wide_kernel, kWideThreads, 128 * sizeof(unsigned long long)) != cudaSuccess)
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop)
     return 0;
-  int coop = 0;
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  const int64_t per_image = coop ? ((int64_t)sms * occ) / B : 0;
-  if (per_image < 1) return 0;
-  int64_t G = (W + 3) / 4;   // at least four words per CTA
-  if (G > per_image) G = per_image;
-  const int S = (int)((W + G - 1) / G);
-  return S <= 128 ? S : 0;
+  for (int pf = 1; pf >= 0; --pf) {
+    // with the block in shared memory one CTA per SM is the plan; without it, whatever fits
+    int occ = 1;
+    if (!pf && cudaFuncSetAttribute(nms_scan_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)wide_scan_smem(kWideMaxS, 0)) != cudaSuccess)
+      return 0;
+    if (!pf && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_scan_wide_kernel<false>, kWideThreads, wide_scan_smem(kWideMaxS, 0)) != cudaSuccess)
+      return 0;
+    const int64_t per_image = ((int64_t)sms * occ) / B;
+    if (per_image < 1) continue;
+    int64_t G = (W + 3) / 4;   // at least four words per CTA
+    if (G > per_image) G = per_image;
+    const int S = (int)((W + G - 1) / G);
+    if (pf) {
+      if (S > kWidePrefetchMaxS) continue;
+      const size_t smem = wide_scan_smem(S, wide_scan_blocks(S));
+      if (smem > 48 * 1024 &&
+          cudaFuncSetAttribute(nms_scan_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        continue;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_scan_wide_kernel<true>, kWideThreads, smem) != cudaSuccess || occ < 1)
+        continue;
+    } else if (S > kWideMaxS) {
+      continue;
+    }
+    *prefetch = pf != 0;
+    return S;
+  }
+  return 0;
 }
 
 static int scan_round_launch(const unsigned long long* mask, const unsigned long long* diagT, const int32_t* num_valid,
@@ -555,6 +651,7 @@ static int scan_round_launch(const unsigned long long* mask, const unsigned long
   const size_t kSmemBudget = 200 * 1024;
   const int stride = (int)scan_state_stride(W);
   int nslots = 0;
+  bool wide_prefetch = false;
   if (W > 0 && Ws % 2 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 && reinterpret_cast<uintptr_t>(diagT) % 16 == 0 &&
       plain + 2 * per_slot <= kSmemBudget) {
     nslots = (int)((kSmemBudget - plain) / per_slot);
@@ -567,15 +664,17 @@ static int scan_round_launch(const unsigned long long* mask, const unsigned long
     nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, nslots, (int)max_out,
                                                                    c_begin, c_end, final_round, scan_state, stride, keep_pos,
                                                                    num_kept, keep_flag);
-  } else if (wide && !scan_state && c_begin == 0 && c_end >= W && W >= 64 && wide_scan_slice(B, W) > 0) {
+  } else if (wide && !scan_state && c_begin == 0 && c_end >= W && W >= 64 && wide_scan_slice(B, W, &wide_prefetch) > 0) {
     // too many boxes for the ring: spread the OR phase over co-resident CTAs
-    int S = wide_scan_slice(B, W), Ki = (int)K, mo = (int)max_out;
+    int S = wide_scan_slice(B, W, &wide_prefetch), Ki = (int)K, mo = (int)max_out;
     const dim3 grid((unsigned)((W + S - 1) / S), (unsigned)B);
     OD_CUDA(cudaMemsetAsync(wide, 0, (size_t)B * W * sizeof(WideSync), st));
     int Wi = W, Wsi = Ws;
-    void* args[] = {(void*)&mask, (void*)&diagT, (void*)&num_valid, &Ki, &Wi, &Wsi, &S, &mo, &wide, &keep_pos, &num_kept, &keep_flag};
-    OD_CUDA(cudaLaunchCooperativeKernel((const void*)nms_scan_wide_kernel, grid, dim3(kWideThreads), args,
-                                        (size_t)S * sizeof(unsigned long long), st));
+    const int blocks = wide_prefetch ? wide_scan_blocks(S) : 0;
+    int two = blocks == 2;
+    void* args[] = {(void*)&mask, (void*)&diagT, (void*)&num_valid, &Ki, &Wi, &Wsi, &S, &mo, &wide, &keep_pos, &num_kept, &keep_flag, &two};
+    OD_CUDA(cudaLaunchCooperativeKernel(wide_prefetch ? (const void*)nms_scan_wide_kernel<true> : (const void*)nms_scan_wide_kernel<false>,
+                                        grid, dim3(kWideThreads), args, wide_scan_smem(S, blocks), st));
     OD_LAUNCH_CHECK("nms_scan_wide_kernel");
     return OD_OK;
   } else {

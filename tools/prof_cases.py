@@ -1,0 +1,51 @@
+"""Per-kernel CUDA times (torch.profiler) of the non-headline cases: python tools/prof_cases.py [nms100k] [frcnn] (developer aid)."""
+import os
+import sys
+
+import numpy as np
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from objectdetection_b200 import fasterrcnn  # noqa: E402
+from objectdetection_b200.proposals import non_max_suppression  # noqa: E402
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def run(name, fn, iters=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+    print(f"== {name} ({iters} iterations)")
+    for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:12]:
+        print(f"{e.device_time_total / iters:10.1f} us/iter  x{e.count / iters:<5.1f} {e.key[:100]}")
+
+
+def main():
+    cases = sys.argv[1:] or ["nms100k", "frcnn"]
+    rs = np.random.RandomState(0)
+    if "nms100k" in cases:
+        n = 100000
+        s = np.exp(rs.uniform(np.log(8), np.log(256), n))
+        cy, cx = rs.uniform(0, 4096, n), rs.uniform(0, 4096, n)
+        bx = cu((np.stack([cy - s / 2, cx - s / 2, cy + s / 2, cx + s / 2], 1) / 4096).astype(np.float32))[None]
+        sc = cu(rs.random_sample(n).astype(np.float32))[None]
+        run("NMS 100k boxes", lambda: non_max_suppression(bx, sc, n, 0.5))
+    if "frcnn" in cases:
+        h, w, na = 38, 63, 9
+        fp = cu(rs.random_sample((1, h, w, 2 * na)).astype(np.float32))
+        fb = cu(rs.normal(0, 0.5, size=(1, h, w, 4 * na)).astype(np.float32))
+        run("FasterRCNN proposals 12000 -> 2000", lambda: fasterrcnn.Proposals('train', fp, fb, image_shape=(600, 1000, 3), nms_threshold=0.7))
+
+
+if __name__ == "__main__":
+    main()
