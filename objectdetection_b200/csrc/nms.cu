@@ -141,7 +141,21 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0u;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  if (mbar_test(bar, parity)) return;   // usually landed long ago: the blocking form costs ~300 cycles even then
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -161,6 +175,20 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 
 constexpr int kScanThreads = 256;
 constexpr int kScanMaxSlots = 8;
+#ifndef OD_SCAN_PIPE
+#define OD_SCAN_PIPE 1   // staged scan: warp 0 resolves chunks while the other warps OR one chunk behind (0: lock-step loop)
+#endif
+// named barriers (ids 1..4; 0 is __syncthreads): bar.arrive does not block, bar.sync does; both order shared memory
+__device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kScanThreads) : "memory"); }
+__device__ __forceinline__ void nb_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kScanThreads) : "memory"); }
+// 64-bit OR into shared memory as two native 32-bit atomics (a 64-bit shared atomicOr is a compare-and-swap loop)
+__device__ __forceinline__ void smem_or64(unsigned long long* p, unsigned long long v) {
+  uint32_t* h = reinterpret_cast<uint32_t*>(p);
+  if ((uint32_t)v) atomicOr(h, (uint32_t)v);
+  if ((uint32_t)(v >> 32)) atomicOr(h + 1, (uint32_t)(v >> 32));
+}
 
 // STAGED: nslots >= 2 ring slots of (64 rows x Ws words + the diagonal tile) fit in shared memory (K <= ~12000);
 // otherwise the rows are read from global memory (L2).
@@ -177,6 +205,10 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
   const size_t slot_words = (size_t)64 * Ws + 64;
   __shared__ __align__(8) unsigned long long full_bar[kScanMaxSlots];
   __shared__ unsigned long long kept_word;
+  __shared__ unsigned long long kept_ring[2];   // pipelined loop: keep word of chunk c in slot c & 1 ...
+  __shared__ int32_t stop_ring[2];              // ... whether max_out was reached with it ...
+  __shared__ int32_t base_ring[2];              // ... and the number of boxes kept before it
+  __shared__ int32_t pipe_out[2];               // kept_total, last chunk waited for
   const int b = blockIdx.x;
   const int n = num_valid ? min(num_valid[b], K) : K;
   const int Wn = (n + 63) / 64;
@@ -222,12 +254,136 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     for (int c = c_first; c < c_first + nslots - 1; ++c) stage_chunk(c);
 
   int c_waited = c_first - 1;
+#if OD_SCAN_PIPE
+  if (STAGED) {
+    // Only removed[c] is needed to resolve chunk c. Warp 0 resolves chunk c, ORs word c+1 of its kept rows itself and
+    // goes on to chunk c+1; warps 1-7 OR the kept rows of chunk c into the words >= c+2 meanwhile, so the per-chunk
+    // critical path is the 64x64 fixed point and one warp-wide OR instead of the whole row pass and two CTA barriers.
+    // Warp 7 only issues the bulk copies. Barrier 1 + (c&1): keep word of chunk c published (all warps). Barrier
+    // 3 + (c&1): the workers are done with chunk c (warp 0 waits for it before chunk c+2, whose word is the first one
+    // they might still be updating).
+    if (warp == 0) {
+      unsigned long long own = 0ull;   // word c of the rows kept in chunk c-1: computed here, never leaves the warp
+      int c = c_first;
+      for (; c < c_last; ++c) {
+        const int i = c - c_first;
+        mbar_wait(&full_bar[i % nslots], (uint32_t)((i / nslots) & 1));   // chunk c has landed
+        c_waited = c;
+        if (i >= 2) nb_sync_n(3 + (c & 1), kScanThreads - 32);   // (workers + this warp; the producer warp is not part of it)
+        const unsigned long long* rows = stage + (size_t)(i % nslots) * slot_words;
+        const unsigned long long* dt = rows + (size_t)64 * Ws;
+        const unsigned long long sup0 = dt[lane], sup1 = dt[lane + 32];
+        // next word of my two rows: loaded now (unconditionally), masked once the keep word is known
+        const int wn = min(c + 1, Wn - 1);
+        const unsigned long long nx0 = rows[(size_t)lane * Ws + wn], nx1 = rows[(size_t)(lane + 32) * Ws + wn];
+        const unsigned long long word = removed[c] | own;
+        const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
+        const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
+        unsigned long long kept = (unsigned long long)__ballot_sync(0xffffffffu, cand0) |
+                                  ((unsigned long long)__ballot_sync(0xffffffffu, cand1) << 32);
+        for (int it = 0; it < 64; ++it) {
+          const bool k0 = cand0 && !(sup0 & kept);
+          const bool k1 = cand1 && !(sup1 & kept);
+          const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+          if (nk == kept) break;
+          kept = nk;
+        }
+        const int allow = max_out - kept_total;
+        while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
+        const int total = kept_total + __popcll(kept);
+        const bool stop = total >= max_out;
+        if (lane == 0) {
+          kept_ring[c & 1] = kept;
+          base_ring[c & 1] = kept_total;
+          stop_ring[c & 1] = stop;
+        }
+        nb_arrive(1 + (c & 1));
+        kept_total = total;
+        own = 0ull;
+        if (stop) break;
+        if (c + 1 < Wn) {   // (rows beyond n are never kept; whatever their slots hold is masked out)
+          const unsigned long long v = (nx0 & (0ull - ((kept >> lane) & 1ull))) | (nx1 & (0ull - ((kept >> (lane + 32)) & 1ull)));
+          own = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)v);
+        }
+      }
+      if (lane == 0) {
+        if (own) smem_or64(&removed[c], own);   // round boundary: the bitmap that is carried over must be complete
+        pipe_out[0] = kept_total;
+        pipe_out[1] = c_waited;
+      }
+    } else if (warp == kScanThreads / 32 - 1) {
+      // producer warp: refills the slot of chunk c-1 as soon as everybody has left it (issuing a bulk copy costs its
+      // thread ~700 cycles, so the rows and the diagonal tile go out from two lanes and nobody else waits for them)
+      for (int c = c_first; c < c_last; ++c) {
+        nb_sync(1 + (c & 1));
+        const int cn = c + nslots - 1;
+        if (cn < c_last && lane < 2) {
+          const int slot = (cn - c_first) % nslots;
+          unsigned long long* bar = &full_bar[slot];
+          unsigned long long* dst = stage + (size_t)slot * slot_words;
+          const uint32_t row_bytes = (uint32_t)min(64, n - cn * 64) * (uint32_t)Ws * 8u;
+          if (lane == 0) {
+            mbar_expect_tx(bar, row_bytes + 512u);
+            bulk_g2s(dst, mrow + (size_t)cn * 64 * Ws, row_bytes, bar);
+          } else {
+            bulk_g2s(dst + (size_t)64 * Ws, dimg + (size_t)cn * 64, 512u, bar);
+          }
+        }
+        __syncwarp();
+        if (stop_ring[c & 1]) break;
+      }
+    } else {
+      constexpr int kHalf = (kScanThreads - 64) / 2;   // warps 1-6: two threads per word (rows 0-31 / 32-63)
+      const int wt = tid - 32, half = wt / kHalf, idx = wt - half * kHalf;
+      for (int c = c_first; c < c_last; ++c) {
+        const int i = c - c_first;
+        nb_sync(1 + (c & 1));        // keep word of chunk c is there; everybody is done with chunk c-1 and its slot
+        const unsigned long long kept = kept_ring[c & 1];
+        if (warp == 1) {   // the outputs of chunk c, off warp 0's path
+          const int base = base_ring[c & 1];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = lane + 32 * h;
+            if ((kept >> r) & 1ull) {
+              const int pos = base + __popcll(kept & ((1ull << r) - 1ull));
+              if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = c * 64 + r;
+              if (keep_flag) keep_flag[(int64_t)b * K + c * 64 + r] = 1;
+            }
+          }
+        }
+        if (stop_ring[c & 1]) break;
+        if (kept != 0ull && c + 2 < Wn) {
+          mbar_wait(&full_bar[i % nslots], (uint32_t)((i / nslots) & 1));   // (already complete: makes the rows visible here)
+          const unsigned long long* rows = stage + (size_t)(i % nslots) * slot_words;
+          const uint32_t kbits = half ? (uint32_t)(kept >> 32) : (uint32_t)kept;
+          if (kbits)
+            for (int w = c + 2 + idx; w < Wn; w += kHalf) {
+              const unsigned long long* col = rows + (size_t)(32 * half) * Ws + w;
+              unsigned long long acc = 0ull;
+#pragma unroll 16
+              for (int r = 0; r < 32; ++r)   // unconditional loads (independent, pipelined), masked afterwards
+                acc |= col[(size_t)r * Ws] & (0ull - (unsigned long long)((kbits >> r) & 1u));
+              smem_or64(&removed[w], acc);
+            }
+        }
+        nb_arrive_n(3 + (c & 1), kScanThreads - 32);
+      }
+    }
+    __syncthreads();
+    kept_total = pipe_out[0];
+    c_waited = pipe_out[1];
+  }
+  const int c_loop = STAGED ? c_last : c_first;   // the lock-step loop below is the global-memory path only
+#else
+  const int c_loop = c_first;
+#endif
   unsigned long long nsup0 = 0ull, nsup1 = 0ull;
   if (!STAGED && warp == 0 && c_first < c_last) {
     nsup0 = __ldg(&dimg[(size_t)c_first * 64 + lane]);
     nsup1 = __ldg(&dimg[(size_t)c_first * 64 + lane + 32]);
   }
-  for (int c = c_first; c < c_last; ++c) {
+  for (int c = c_loop; c < c_last; ++c) {
     if (STAGED) {
       mbar_wait(&full_bar[(c - c_first) % nslots], (uint32_t)(((c - c_first) / nslots) & 1));   // chunk c has landed
       c_waited = c;
@@ -291,7 +447,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
             const unsigned long long* col = rows + (size_t)r0 * Ws + w;
             unsigned long long acc = 0ull;
 #pragma unroll 16
-            for (int r = 0; r < 32; ++r) acc |= ((kbits >> r) & 1u) ? col[(size_t)r * Ws] : 0ull;
+            for (int r = 0; r < 32; ++r) acc |= col[(size_t)r * Ws] & (0ull - (unsigned long long)((kbits >> r) & 1u));
             if (acc) atomicOr(&removed[w], acc);
           }
       } else {
@@ -356,13 +512,6 @@ struct WideSync {
   int32_t cum;               // boxes kept up to and including the chunk
   int32_t flag;              // 0 pending, 1 published, 2 published and final (max_out reached or last chunk)
 };
-// 64-bit OR into shared memory as two native 32-bit atomics (a 64-bit shared atomicOr is a compare-and-swap loop,
-// slow when ~25 threads target one word)
-__device__ __forceinline__ void smem_or64(unsigned long long* p, unsigned long long v) {
-  uint32_t* h = reinterpret_cast<uint32_t*>(p);
-  if ((uint32_t)v) atomicOr(h, (uint32_t)v);
-  if ((uint32_t)(v >> 32)) atomicOr(h + 1, (uint32_t)(v >> 32));
-}
 __device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
   int32_t v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
