@@ -33,7 +33,7 @@ struct FrcnnDev {
 template <typename T>
 __global__ void frcnn_decode_kernel(const T* __restrict__ probs, const T* __restrict__ bbox, FrcnnDev p, int64_t total,
                                     int64_t n_pow2, double* __restrict__ boxes, Key128* __restrict__ keys,
-                                    int32_t* __restrict__ counters) {
+                                    int32_t* __restrict__ counters, float* __restrict__ fscore) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   Key128 k;
   k.hi = 0ull;                                            // filtered-out rows: below every valid key, still unique
@@ -67,7 +67,11 @@ __global__ void frcnn_decode_kernel(const T* __restrict__ probs, const T* __rest
       k.lo = 0xFFFFFFFFFFFFFFFFull - (unsigned long long)i;
     }
   }
-  if (i < n_pow2) keys[i] = k;
+  if (fscore) {   // fp32 inputs: the radix-select top-k orders (score desc, index asc) like the 128-bit keys do
+    if (i < total) fscore[i] = valid ? (float)probs[(i / p.num_anchors) * 2 * p.num_anchors + (i % p.num_anchors)] : -INFINITY;
+  } else if (i < n_pow2) {
+    keys[i] = k;
+  }
   const uint32_t bal = __ballot_sync(0xffffffffu, valid);
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&counters[0], __popc(bal));
 }
@@ -81,7 +85,7 @@ constexpr int kFrRankTile = 1024;
 __global__ void __launch_bounds__(kFrRankThreads)
 frcnn_rank_gather_kernel(const Key128* __restrict__ keys, const double* __restrict__ boxes, int64_t total, int pre_n, int K,
                          double* __restrict__ sorted, int32_t* __restrict__ counters) {
-  __shared__ unsigned long long tile_hi[kFrRankTile];   // score keys; the index half is only read on equal scores
+  __shared__ unsigned long long tile_hi[kFrRankTile];   // score keys
   __shared__ unsigned long long tile_lo[kFrRankTile];
   __shared__ int32_t partial[kFrRankThreads];
   constexpr int kParts = kFrRankThreads / kFrRankMine;
@@ -107,9 +111,8 @@ frcnn_rank_gather_kernel(const Key128* __restrict__ keys, const double* __restri
     const int j0 = part * (kFrRankTile / kParts);
 #pragma unroll 8
     for (int j = j0; j < j0 + kFrRankTile / kParts; ++j) {
-      const unsigned long long h = tile_hi[j];
-      rank += (h > mine.hi) ? 1 : 0;
-      if (h == mine.hi) rank += (tile_lo[j] > mine.lo) ? 1 : 0;
+      const unsigned long long h = tile_hi[j], l = tile_lo[j];   // both loads unconditional: a load behind a branch serialises
+      rank += ((h > mine.hi) | ((h == mine.hi) & (l > mine.lo))) ? 1 : 0;
     }
   }
   partial[threadIdx.x] = rank;
@@ -144,26 +147,43 @@ frcnn_mask_kernel(const double* __restrict__ boxes, const int32_t* __restrict__ 
   const int n = min(counters[1], K);
   if (rb * 64 >= n || cb * 64 >= n) return;
   __shared__ PBox cbox[64];
+  __shared__ float cf[64][5];   // fp32 copies for the screening pass: x1, y1, x2 + 1, y2 + 1, area
   const int t = threadIdx.x;
   {
     const int j = cb * 64 + t;
-    if (j < n) cbox[t] = load_pbox(boxes + 4 * (int64_t)j);
+    if (j < n) {
+      const PBox p = load_pbox(boxes + 4 * (int64_t)j);
+      cbox[t] = p;
+      cf[t][0] = (float)p.x1; cf[t][1] = (float)p.y1; cf[t][2] = (float)(p.x2 + 1); cf[t][3] = (float)(p.y2 + 1);
+      cf[t][4] = (float)p.area;
+    }
   }
   __syncthreads();
   const int i = rb * 64 + t;
   unsigned long long bits = 0ull;
+  // Screening in fp32: with pixel coordinates below 2^13 (rounding <= 5e-4 px per corner) and sides >= 1 px (the +1
+  // convention) the fp32 overlap is within ~2.5e-3 of the fp64 one for the smallest boxes and ~1e-5 for typical ones, so
+  // only pairs within kMargin of the threshold (and NaNs) take the exact fp64 path of the reference.
+  constexpr float kMargin = 4e-3f;
+  const float thr_hi = (float)thr + kMargin, thr_lo = (float)thr - kMargin;
   if (i < n) {
     const PBox my = load_pbox(boxes + 4 * (int64_t)i);
+    const float mx1 = (float)my.x1, my1 = (float)my.y1, mx2 = (float)(my.x2 + 1), my2 = (float)(my.y2 + 1), ma = (float)my.area;
     for (int jj = 0; jj < 64; ++jj) {
       const int j = cb * 64 + jj;
       if (j > i && j < n) {
-        const PBox o = cbox[jj];
-        const double xx1 = d_max(my.x1, o.x1), yy1 = d_max(my.y1, o.y1);
-        const double xx2 = d_min(my.x2, o.x2), yy2 = d_min(my.y2, o.y2);
-        const double w = d_max(0.0, xx2 - xx1 + 1), h = d_max(0.0, yy2 - yy1 + 1);
-        const double inter = w * h;
-        // inter == 0 gives ovr = +-0 (or NaN for a zero union), never >= a positive threshold: skip the fp64 divide
-        if (inter != 0.0 || !(thr > 0.0)) {
+        const float fw = fmaxf(0.0f, fminf(mx2, cf[jj][2]) - fmaxf(mx1, cf[jj][0]));
+        const float fh = fmaxf(0.0f, fminf(my2, cf[jj][3]) - fmaxf(my1, cf[jj][1]));
+        const float fi = fw * fh;
+        const float fo = __fdividef(fi, ma + cf[jj][4] - fi);
+        if (fo > thr_hi) {
+          bits |= 1ull << jj;
+        } else if (!(fo < thr_lo)) {   // too close to call (or NaN): the reference's arithmetic
+          const PBox o = cbox[jj];
+          const double xx1 = d_max(my.x1, o.x1), yy1 = d_max(my.y1, o.y1);
+          const double xx2 = d_min(my.x2, o.x2), yy2 = d_min(my.y2, o.y2);
+          const double w = d_max(0.0, xx2 - xx1 + 1), h = d_max(0.0, yy2 - yy1 + 1);
+          const double inter = w * h;
           const double ovr = inter / (my.area + o.area - inter);
           if (ovr >= thr) bits |= 1ull << jj;
         }
@@ -179,6 +199,19 @@ frcnn_mask_kernel(const double* __restrict__ boxes, const int32_t* __restrict__ 
       if (lane == 0) dt[jj * 2 + warp] = bal;
     }
   }
+}
+
+// fp32 path: position p of the visiting order holds box ix[p] (zeros past the valid ones); counters[1] = npre.
+__global__ void frcnn_gather_kernel(const int32_t* __restrict__ ix, const double* __restrict__ boxes, int pre_n, int K,
+                                    double* __restrict__ sorted, int32_t* __restrict__ counters) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npre = min(counters[0], pre_n);
+  if (p == 0) counters[1] = npre;
+  if (p >= K) return;
+  const bool valid = p < npre;
+  const int64_t src = valid ? ix[p] : 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sorted[4 * (int64_t)p + c] = valid ? boxes[4 * src + c] : 0.0;
 }
 
 __global__ void frcnn_emit_kernel(const double* __restrict__ sorted, const int32_t* __restrict__ keep_pos,
@@ -202,6 +235,10 @@ struct FrcnnWs {
   int32_t* keep_pos;
   unsigned long long* mask;
   unsigned long long* diagT;
+  float* fscore;
+  int32_t* ix;
+  void* topk_ws;
+  size_t topk_bytes;
 };
 static size_t carve_frcnn_ws(Workspace& w, int64_t total, int64_t K, int64_t post_n, FrcnnWs* out) {
   FrcnnWs f;
@@ -214,6 +251,10 @@ static size_t carve_frcnn_ws(Workspace& w, int64_t total, int64_t K, int64_t pos
   f.keep_pos = w.take<int32_t>((size_t)post_n);
   f.mask = w.take<unsigned long long>((size_t)(K * nms_mask_stride(K)));
   f.diagT = w.take<unsigned long long>((size_t)(W * 64));
+  f.fscore = w.take<float>((size_t)(total > 0 ? total : 1));
+  f.ix = w.take<int32_t>((size_t)(K > 0 ? K : 1));
+  f.topk_bytes = topk_workspace_bytes(1, total, K);
+  f.topk_ws = w.take<char>(f.topk_bytes);
   if (out) *out = f;
   return w.off + 256;
 }
@@ -268,15 +309,21 @@ int od_frcnn_proposal_forward(const DLTensor* rpn_box_class_prob, const DLTensor
   const int64_t n_pow2 = next_pow2(total > 0 ? total : 1);
   const unsigned blocks = (unsigned)((n_pow2 + 255) / 256);
   if (f64)
-    frcnn_decode_kernel<double><<<blocks, 256, 0, st>>>(dptr<double>(rpn_box_class_prob), dptr<double>(rpn_bbox), d, total, n_pow2, f.boxes, f.keys, f.counters);
+    frcnn_decode_kernel<double><<<blocks, 256, 0, st>>>(dptr<double>(rpn_box_class_prob), dptr<double>(rpn_bbox), d, total, n_pow2, f.boxes, f.keys, f.counters, nullptr);
   else
-    frcnn_decode_kernel<float><<<blocks, 256, 0, st>>>(dptr<float>(rpn_box_class_prob), dptr<float>(rpn_bbox), d, total, n_pow2, f.boxes, f.keys, f.counters);
+    frcnn_decode_kernel<float><<<blocks, 256, 0, st>>>(dptr<float>(rpn_box_class_prob), dptr<float>(rpn_bbox), d, total, n_pow2, f.boxes, f.keys, f.counters, f.fscore);
   OD_LAUNCH_CHECK("frcnn_decode_kernel");
   const int W = (int)((K + 63) / 64);
   if (K > 0) {
-    frcnn_rank_gather_kernel<<<(unsigned)((total + kFrRankMine - 1) / kFrRankMine), kFrRankThreads, 0, st>>>(
-        f.keys, f.boxes, total, params->pre_nms_top_n, (int)K, f.sorted, f.counters);
-    OD_LAUNCH_CHECK("frcnn_rank_gather_kernel");
+    if (f64) {   // fp64 scores: 128-bit keys, rank sort
+      frcnn_rank_gather_kernel<<<(unsigned)((total + kFrRankMine - 1) / kFrRankMine), kFrRankThreads, 0, st>>>(
+          f.keys, f.boxes, total, params->pre_nms_top_n, (int)K, f.sorted, f.counters);
+      OD_LAUNCH_CHECK("frcnn_rank_gather_kernel");
+    } else {     // fp32 scores: the radix-select top-k of the Mask R-CNN path, filtered-out boxes at -inf
+      OD_CHECK(topk_launch(f.fscore, 1, total, total, 1, K, f.ix, nullptr, f.topk_ws, f.topk_bytes, st));
+      frcnn_gather_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(f.ix, f.boxes, params->pre_nms_top_n, (int)K, f.sorted, f.counters);
+      OD_LAUNCH_CHECK("frcnn_gather_kernel");
+    }
     const dim3 grid((unsigned)W, (unsigned)W, 1);
     frcnn_mask_kernel<<<grid, 64, 0, st>>>(f.sorted, f.counters, (int)K, W, (int)nms_mask_stride(K), params->nms_threshold, f.mask,
                                            f.diagT);

@@ -567,6 +567,16 @@ def test_frcnn_proposals_and_roi_pool(golden):
         want = oracle.frcnn_proposals(probs, bbox, 600, 1000, 12000, 2000, thr)
         assert got.shape == want.shape and np.all(got[:, 0] == 0)
         assert np.allclose(got, want, rtol=1e-6, atol=1e-4)
+    # float32 inputs take the radix-select top-k instead of the 128-bit rank sort: same visiting order, ties (scores
+    # quantised to 3 decimals) go to the lower index, filtered-out boxes never enter
+    p32 = np.round(probs, 3).astype(f32)
+    b32 = bbox.astype(f32)
+    for thr, pre in ((0.7, 12000), (0.2, 3000)):
+        P = fasterrcnn.Proposals('train', cu(p32), cu(b32), image_shape=(600, 1000, 3), nms_threshold=thr, pre_nms_top_n=pre)
+        got32 = host(P.get_proposals())
+        want32 = oracle.frcnn_proposals(p32.astype(np.float64), b32.astype(np.float64), 600, 1000, pre, 2000, thr)
+        assert got32.shape == want32.shape
+        assert np.allclose(got32, want32, rtol=1e-6, atol=1e-4)
     assert np.array_equal(fasterrcnn.get_anchors(), golden["frcnn_base_anchors"])
     # golden: the reference's own decode -> clip -> filter -> NMS on the small 6x9 case
     gp = np.zeros((1, 6, 9, 18))
