@@ -175,6 +175,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 
 constexpr int kScanThreads = 256;
 constexpr int kScanMaxSlots = 8;
+#ifndef OD_SCAN_COPY_PARTS
+#define OD_SCAN_COPY_PARTS 4   // bulk copies per chunk of 64 mask rows (issued by different lanes of the producer warp)
+#endif
 #ifndef OD_SCAN_PIPE
 #define OD_SCAN_PIPE 1   // staged scan: warp 0 resolves chunks while the other warps OR one chunk behind (0: lock-step loop)
 #endif
@@ -264,18 +267,27 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     // they might still be updating).
     if (warp == 0) {
       unsigned long long own = 0ull;   // word c of the rows kept in chunk c-1: computed here, never leaves the warp
-      int c = c_first;
-      for (; c < c_last; ++c) {
+      // Everything of chunk c that does not depend on removed[c] - the phase test of its slot, its diagonal tile, word
+      // c+1 of my two rows - is fetched one chunk ahead, so that only one shared load sits between the workers' barrier
+      // and the fixed point.
+      unsigned long long sup0 = 0ull, sup1 = 0ull, nx0 = 0ull, nx1 = 0ull;
+      auto fetch = [&](int c) {
         const int i = c - c_first;
         mbar_wait(&full_bar[i % nslots], (uint32_t)((i / nslots) & 1));   // chunk c has landed
         c_waited = c;
-        if (i >= 2) nb_sync_n(3 + (c & 1), kScanThreads - 32);   // (workers + this warp; the producer warp is not part of it)
         const unsigned long long* rows = stage + (size_t)(i % nslots) * slot_words;
         const unsigned long long* dt = rows + (size_t)64 * Ws;
-        const unsigned long long sup0 = dt[lane], sup1 = dt[lane + 32];
-        // next word of my two rows: loaded now (unconditionally), masked once the keep word is known
         const int wn = min(c + 1, Wn - 1);
-        const unsigned long long nx0 = rows[(size_t)lane * Ws + wn], nx1 = rows[(size_t)(lane + 32) * Ws + wn];
+        sup0 = dt[lane];
+        sup1 = dt[lane + 32];
+        nx0 = rows[(size_t)lane * Ws + wn];
+        nx1 = rows[(size_t)(lane + 32) * Ws + wn];
+      };
+      int c = c_first;
+      if (c < c_last) fetch(c);
+      for (; c < c_last; ++c) {
+        const int i = c - c_first;
+        if (i >= 2) nb_sync_n(3 + (c & 1), kScanThreads - 32);   // (workers + this warp; the producer warp is not part of it)
         const unsigned long long word = removed[c] | own;
         const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
         const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
@@ -302,10 +314,10 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
         kept_total = total;
         own = 0ull;
         if (stop) break;
-        if (c + 1 < Wn) {   // (rows beyond n are never kept; whatever their slots hold is masked out)
-          const unsigned long long v = (nx0 & (0ull - ((kept >> lane) & 1ull))) | (nx1 & (0ull - ((kept >> (lane + 32)) & 1ull)));
+        const unsigned long long v = (nx0 & (0ull - ((kept >> lane) & 1ull))) | (nx1 & (0ull - ((kept >> (lane + 32)) & 1ull)));
+        if (c + 1 < c_last) fetch(c + 1);   // (its latency overlaps the reduction below and the workers' barrier)
+        if (c + 1 < Wn)   // (rows beyond n are never kept; whatever their slots hold is masked out)
           own = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)v);
-        }
       }
       if (lane == 0) {
         if (own) smem_or64(&removed[c], own);   // round boundary: the bitmap that is carried over must be complete
@@ -318,16 +330,18 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       for (int c = c_first; c < c_last; ++c) {
         nb_sync(1 + (c & 1));
         const int cn = c + nslots - 1;
-        if (cn < c_last && lane < 2) {
+        if (cn < c_last && lane <= OD_SCAN_COPY_PARTS) {
           const int slot = (cn - c_first) % nslots;
           unsigned long long* bar = &full_bar[slot];
           unsigned long long* dst = stage + (size_t)slot * slot_words;
-          const uint32_t row_bytes = (uint32_t)min(64, n - cn * 64) * (uint32_t)Ws * 8u;
+          const int rows = min(64, n - cn * 64);
           if (lane == 0) {
-            mbar_expect_tx(bar, row_bytes + 512u);
-            bulk_g2s(dst, mrow + (size_t)cn * 64 * Ws, row_bytes, bar);
-          } else {
+            mbar_expect_tx(bar, (uint32_t)rows * (uint32_t)Ws * 8u + 512u);
             bulk_g2s(dst + (size_t)64 * Ws, dimg + (size_t)cn * 64, 512u, bar);
+          } else {   // the rows in OD_SCAN_COPY_PARTS pieces, one lane each
+            constexpr int kPart = 64 / OD_SCAN_COPY_PARTS;
+            const int r0 = (lane - 1) * kPart, nr = min(kPart, rows - r0);
+            if (nr > 0) bulk_g2s(dst + (size_t)r0 * Ws, mrow + ((size_t)cn * 64 + r0) * Ws, (uint32_t)nr * (uint32_t)Ws * 8u, bar);
           }
         }
         __syncwarp();
@@ -338,6 +352,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       const int wt = tid - 32, half = wt / kHalf, idx = wt - half * kHalf;
       for (int c = c_first; c < c_last; ++c) {
         const int i = c - c_first;
+        mbar_wait(&full_bar[i % nslots], (uint32_t)((i / nslots) & 1));   // (landed long ago; makes the rows visible to this thread)
         nb_sync(1 + (c & 1));        // keep word of chunk c is there; everybody is done with chunk c-1 and its slot
         const unsigned long long kept = kept_ring[c & 1];
         if (warp == 1) {   // the outputs of chunk c, off warp 0's path
@@ -354,16 +369,20 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
         }
         if (stop_ring[c & 1]) break;
         if (kept != 0ull && c + 2 < Wn) {
-          mbar_wait(&full_bar[i % nslots], (uint32_t)((i / nslots) & 1));   // (already complete: makes the rows visible here)
           const unsigned long long* rows = stage + (size_t)(i % nslots) * slot_words;
           const uint32_t kbits = half ? (uint32_t)(kept >> 32) : (uint32_t)kept;
           if (kbits)
             for (int w = c + 2 + idx; w < Wn; w += kHalf) {
               const unsigned long long* col = rows + (size_t)(32 * half) * Ws + w;
               unsigned long long acc = 0ull;
-#pragma unroll 16
-              for (int r = 0; r < 32; ++r)   // unconditional loads (independent, pipelined), masked afterwards
-                acc |= col[(size_t)r * Ws] & (0ull - (unsigned long long)((kbits >> r) & 1u));
+#pragma unroll
+              for (int r0 = 0; r0 < 32; r0 += 16) {   // 16 unconditional loads in flight, masked afterwards
+                unsigned long long v[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = col[(size_t)(r0 + r) * Ws];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) acc |= v[r] & (0ull - (unsigned long long)((kbits >> (r0 + r)) & 1u));
+              }
               smem_or64(&removed[w], acc);
             }
         }
@@ -446,8 +465,14 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
           for (int w = c + 1 + (tid & (kScanThreads / 2 - 1)); w < Wn; w += kScanThreads / 2) {
             const unsigned long long* col = rows + (size_t)r0 * Ws + w;
             unsigned long long acc = 0ull;
-#pragma unroll 16
-            for (int r = 0; r < 32; ++r) acc |= col[(size_t)r * Ws] & (0ull - (unsigned long long)((kbits >> r) & 1u));
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 16) {
+              unsigned long long v[16];
+#pragma unroll
+              for (int r = 0; r < 16; ++r) v[r] = col[(size_t)(r0 + r) * Ws];
+#pragma unroll
+              for (int r = 0; r < 16; ++r) acc |= v[r] & (0ull - (unsigned long long)((kbits >> (r0 + r)) & 1u));
+            }
             if (acc) atomicOr(&removed[w], acc);
           }
       } else {
