@@ -826,6 +826,7 @@ static int scan_round_launch(const unsigned long long* mask, const unsigned long
   const int stride = (int)scan_state_stride(W);
   int nslots = 0;
   bool wide_prefetch = false;
+  int wide_S = 0;
   if (W > 0 && Ws % 2 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 && reinterpret_cast<uintptr_t>(diagT) % 16 == 0 &&
       plain + 2 * per_slot <= kSmemBudget) {
     nslots = (int)((kSmemBudget - plain) / per_slot);
@@ -838,9 +839,9 @@ static int scan_round_launch(const unsigned long long* mask, const unsigned long
     nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, nslots, (int)max_out,
                                                                    c_begin, c_end, final_round, scan_state, stride, keep_pos,
                                                                    num_kept, keep_flag);
-  } else if (wide && !scan_state && c_begin == 0 && c_end >= W && W >= 64 && wide_scan_slice(B, W, &wide_prefetch) > 0) {
+  } else if (wide && !scan_state && c_begin == 0 && c_end >= W && W >= 64 && (wide_S = wide_scan_slice(B, W, &wide_prefetch)) > 0) {
     // too many boxes for the ring: spread the OR phase over co-resident CTAs
-    int S = wide_scan_slice(B, W, &wide_prefetch), Ki = (int)K, mo = (int)max_out;
+    int S = wide_S, Ki = (int)K, mo = (int)max_out;
     const dim3 grid((unsigned)((W + S - 1) / S), (unsigned)B);
     OD_CUDA(cudaMemsetAsync(wide, 0, (size_t)B * W * sizeof(WideSync), st));
     int Wi = W, Wsi = Ws;

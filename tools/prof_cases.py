@@ -40,6 +40,16 @@ def main():
         bx = cu((np.stack([cy - s / 2, cx - s / 2, cy + s / 2, cx + s / 2], 1) / 4096).astype(np.float32))[None]
         sc = cu(rs.random_sample(n).astype(np.float32))[None]
         run("NMS 100k boxes", lambda: non_max_suppression(bx, sc, n, 0.5))
+    if "props64" in cases:   # 64 scan CTAs: long enough for ncu's PC sampler (python tools/prof_cases.py props64 under ncu -k regex:nms_scan)
+        import _synth
+        from objectdetection_b200 import Proposals, config, utils
+        conf = config()
+        shapes = utils.get_resnet_stage_shapes(conf, conf.IMAGE_SHAPE)
+        B = 64
+        anchors = utils.gen_anchors(conf.IMAGE_SHAPE, B, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes, conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE)
+        probs, bbox = _synth.rpn_outputs(rs, B, anchors.shape[1])
+        p, bb = cu(probs), cu(bbox)
+        run("Proposals B=64", lambda: Proposals(conf, B, p, bb, anchors), iters=2)
     if "frcnn" in cases:
         h, w, na = 38, 63, 9
         fp = cu(rs.random_sample((1, h, w, 2 * na)).astype(np.float32))
