@@ -50,6 +50,17 @@ def main():
         probs, bbox = _synth.rpn_outputs(rs, B, anchors.shape[1])
         p, bb = cu(probs), cu(bbox)
         run("Proposals B=64", lambda: Proposals(conf, B, p, bb, anchors), iters=2)
+    if "propsK" in cases:   # same 16 chunks scanned, different row length (bytes per chunk): K = 6000 / 3072 / 1536
+        import _synth
+        from objectdetection_b200 import Proposals, config, utils
+        for Kpre in (6000, 3072, 1536):
+            conf = config()
+            conf.PRE_NMS_ROIS_COUNT = Kpre
+            shapes = utils.get_resnet_stage_shapes(conf, conf.IMAGE_SHAPE)
+            anchors = utils.gen_anchors(conf.IMAGE_SHAPE, 2, conf.RPN_ANCHOR_SCALES, conf.RPN_ANCHOR_RATIOS, shapes, conf.RESNET_STRIDES, conf.RPN_ANCHOR_STRIDE)
+            probs, bbox = _synth.rpn_outputs(np.random.RandomState(0), 2, anchors.shape[1])
+            p, bb = cu(probs), cu(bbox)
+            run(f"Proposals B=2 pre-NMS {Kpre}", lambda: Proposals(conf, 2, p, bb, anchors), iters=5)
     if "frcnn" in cases:
         h, w, na = 38, 63, 9
         fp = cu(rs.random_sample((1, h, w, 2 * na)).astype(np.float32))
