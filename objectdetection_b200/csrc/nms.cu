@@ -271,11 +271,18 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       // c+1 of my two rows - is fetched one chunk ahead, so that only one shared load sits between the workers' barrier
       // and the fixed point.
       unsigned long long sup0 = 0ull, sup1 = 0ull, nx0 = 0ull, nx1 = 0ull;
+      // (ring slot and phase parity of the chunk to fetch are advanced by hand: `% nslots` and `/ nslots` on a run-time
+      //  value cost ~60 dependent instructions on the one warp everybody waits for)
+      int f_slot = 0;
+      uint32_t f_par = 0u;
       auto fetch = [&](int c) {
-        const int i = c - c_first;
-        mbar_wait(&full_bar[i % nslots], (uint32_t)((i / nslots) & 1));   // chunk c has landed
+        mbar_wait(&full_bar[f_slot], f_par);   // chunk c has landed
         c_waited = c;
-        const unsigned long long* rows = stage + (size_t)(i % nslots) * slot_words;
+        const unsigned long long* rows = stage + (size_t)f_slot * slot_words;
+        if (++f_slot == nslots) {
+          f_slot = 0;
+          f_par ^= 1u;
+        }
         const unsigned long long* dt = rows + (size_t)64 * Ws;
         const int wn = min(c + 1, Wn - 1);
         sup0 = dt[lane];
@@ -327,11 +334,11 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     } else if (warp == kScanThreads / 32 - 1) {
       // producer warp: refills the slot of chunk c-1 as soon as everybody has left it (issuing a bulk copy costs its
       // thread ~700 cycles, so the rows and the diagonal tile go out from two lanes and nobody else waits for them)
+      int slot = nslots - 1;   // slot of chunk c + nslots - 1
       for (int c = c_first; c < c_last; ++c) {
         nb_sync(1 + (c & 1));
         const int cn = c + nslots - 1;
         if (cn < c_last && lane <= OD_SCAN_COPY_PARTS) {
-          const int slot = (cn - c_first) % nslots;
           unsigned long long* bar = &full_bar[slot];
           unsigned long long* dst = stage + (size_t)slot * slot_words;
           const int rows = min(64, n - cn * 64);
@@ -345,14 +352,16 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
           }
         }
         __syncwarp();
+        if (++slot == nslots) slot = 0;
         if (stop_ring[c & 1]) break;
       }
     } else {
       constexpr int kHalf = (kScanThreads - 64) / 2;   // warps 1-6: two threads per word (rows 0-31 / 32-63)
       const int wt = tid - 32, half = wt / kHalf, idx = wt - half * kHalf;
+      int w_slot = 0;
+      uint32_t w_par = 0u;
       for (int c = c_first; c < c_last; ++c) {
-        const int i = c - c_first;
-        mbar_wait(&full_bar[i % nslots], (uint32_t)((i / nslots) & 1));   // (landed long ago; makes the rows visible to this thread)
+        mbar_wait(&full_bar[w_slot], w_par);   // (landed long ago; makes the rows visible to this thread)
         nb_sync(1 + (c & 1));        // keep word of chunk c is there; everybody is done with chunk c-1 and its slot
         const unsigned long long kept = kept_ring[c & 1];
         if (warp == 1) {   // the outputs of chunk c, off warp 0's path
@@ -369,7 +378,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
         }
         if (stop_ring[c & 1]) break;
         if (kept != 0ull && c + 2 < Wn) {
-          const unsigned long long* rows = stage + (size_t)(i % nslots) * slot_words;
+          const unsigned long long* rows = stage + (size_t)w_slot * slot_words;
           const uint32_t kbits = half ? (uint32_t)(kept >> 32) : (uint32_t)kept;
           if (kbits)
             for (int w = c + 2 + idx; w < Wn; w += kHalf) {
@@ -387,6 +396,10 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
             }
         }
         nb_arrive_n(3 + (c & 1), kScanThreads - 32);
+        if (++w_slot == nslots) {
+          w_slot = 0;
+          w_par ^= 1u;
+        }
       }
     }
     __syncthreads();
