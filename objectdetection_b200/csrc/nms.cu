@@ -208,9 +208,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
   const size_t slot_words = (size_t)64 * Ws + 64;
   __shared__ __align__(8) unsigned long long full_bar[kScanMaxSlots];
   __shared__ unsigned long long kept_word;
-  __shared__ unsigned long long kept_ring[2];   // pipelined loop: keep word of chunk c in slot c & 1 ...
-  __shared__ int32_t stop_ring[2];              // ... whether max_out was reached with it ...
-  __shared__ int32_t base_ring[2];              // ... and the number of boxes kept before it
+  __shared__ uint4 pipe_ring[2];   // pipelined loop, slot c & 1: keep word of chunk c (x, y), boxes kept before it (z), max_out reached (w)
   __shared__ int32_t pipe_out[2];               // kept_total, last chunk waited for
   const int b = blockIdx.x;
   const int n = num_valid ? min(num_valid[b], K) : K;
@@ -266,11 +264,13 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     // 3 + (c&1): the workers are done with chunk c (warp 0 waits for it before chunk c+2, whose word is the first one
     // they might still be updating).
     if (warp == 0) {
-      unsigned long long own = 0ull;   // word c of the rows kept in chunk c-1: computed here, never leaves the warp
+      // All 64-bit words are handled as 32-bit halves (lane l owns boxes l and l + 32 of the chunk): this warp's
+      // instruction count is the critical path of the whole kernel.
+      uint32_t own_lo = 0u, own_hi = 0u;   // word c of the rows kept in chunk c-1: computed here, never leaves the warp
       // Everything of chunk c that does not depend on removed[c] - the phase test of its slot, its diagonal tile, word
       // c+1 of my two rows - is fetched one chunk ahead, so that only one shared load sits between the workers' barrier
       // and the fixed point.
-      unsigned long long sup0 = 0ull, sup1 = 0ull, nx0 = 0ull, nx1 = 0ull;
+      uint2 sup0 = make_uint2(0u, 0u), sup1 = sup0, nx0 = sup0, nx1 = sup0;
       // (ring slot and phase parity of the chunk to fetch are advanced by hand: `% nslots` and `/ nslots` on a run-time
       //  value cost ~60 dependent instructions on the one warp everybody waits for)
       int f_slot = 0;
@@ -278,56 +278,63 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       auto fetch = [&](int c) {
         mbar_wait(&full_bar[f_slot], f_par);   // chunk c has landed
         c_waited = c;
-        const unsigned long long* rows = stage + (size_t)f_slot * slot_words;
+        const uint2* rows = reinterpret_cast<const uint2*>(stage + (size_t)f_slot * slot_words);
         if (++f_slot == nslots) {
           f_slot = 0;
           f_par ^= 1u;
         }
-        const unsigned long long* dt = rows + (size_t)64 * Ws;
+        const uint2* dt = rows + (size_t)64 * Ws;
         const int wn = min(c + 1, Wn - 1);
         sup0 = dt[lane];
         sup1 = dt[lane + 32];
         nx0 = rows[(size_t)lane * Ws + wn];
         nx1 = rows[(size_t)(lane + 32) * Ws + wn];
       };
+      const uint32_t lbit = 1u << lane;
+      const uint2* removed2 = reinterpret_cast<const uint2*>(removed);
       int c = c_first;
       if (c < c_last) fetch(c);
       for (; c < c_last; ++c) {
-        const int i = c - c_first;
-        if (i >= 2) nb_sync_n(3 + (c & 1), kScanThreads - 32);   // (workers + this warp; the producer warp is not part of it)
-        const unsigned long long word = removed[c] | own;
-        const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
-        const bool cand1 = (c * 64 + lane + 32 < n) && !((word >> (lane + 32)) & 1ull);
-        unsigned long long kept = (unsigned long long)__ballot_sync(0xffffffffu, cand0) |
-                                  ((unsigned long long)__ballot_sync(0xffffffffu, cand1) << 32);
+        if (c - c_first >= 2) nb_sync_n(3 + (c & 1), kScanThreads - 32);   // (workers + this warp; the producer warp is not part of it)
+        const uint2 w = removed2[c];
+        const int nrem = n - c * 64;
+        const bool cand0 = (lane < nrem) && !((w.x | own_lo) & lbit);
+        const bool cand1 = (lane + 32 < nrem) && !((w.y | own_hi) & lbit);
+        uint32_t k_lo = __ballot_sync(0xffffffffu, cand0), k_hi = __ballot_sync(0xffffffffu, cand1);
         for (int it = 0; it < 64; ++it) {
-          const bool k0 = cand0 && !(sup0 & kept);
-          const bool k1 = cand1 && !(sup1 & kept);
-          const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
-                                        ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
-          if (nk == kept) break;
-          kept = nk;
+          const bool k0 = cand0 && !((sup0.x & k_lo) | (sup0.y & k_hi));
+          const bool k1 = cand1 && !((sup1.x & k_lo) | (sup1.y & k_hi));
+          const uint32_t n_lo = __ballot_sync(0xffffffffu, k0), n_hi = __ballot_sync(0xffffffffu, k1);
+          if (n_lo == k_lo && n_hi == k_hi) break;
+          k_lo = n_lo;
+          k_hi = n_hi;
         }
+        int cnt = __popc(k_lo) + __popc(k_hi);
         const int allow = max_out - kept_total;
-        while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
-        const int total = kept_total + __popcll(kept);
-        const bool stop = total >= max_out;
-        if (lane == 0) {
-          kept_ring[c & 1] = kept;
-          base_ring[c & 1] = kept_total;
-          stop_ring[c & 1] = stop;
+        if (cnt > allow) {   // respect max_out: drop the highest set bits beyond the allowance
+          unsigned long long kept = ((unsigned long long)k_hi << 32) | k_lo;
+          while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
+          k_lo = (uint32_t)kept;
+          k_hi = (uint32_t)(kept >> 32);
+          cnt = allow;
         }
+        const int total = kept_total + cnt;
+        const bool stop = total >= max_out;
+        if (lane == 0) pipe_ring[c & 1] = make_uint4(k_lo, k_hi, (uint32_t)kept_total, stop ? 1u : 0u);
         nb_arrive(1 + (c & 1));
         kept_total = total;
-        own = 0ull;
+        own_lo = own_hi = 0u;
         if (stop) break;
-        const unsigned long long v = (nx0 & (0ull - ((kept >> lane) & 1ull))) | (nx1 & (0ull - ((kept >> (lane + 32)) & 1ull)));
+        const uint32_t m0 = 0u - ((k_lo >> lane) & 1u), m1 = 0u - ((k_hi >> lane) & 1u);
+        const uint32_t v_lo = (nx0.x & m0) | (nx1.x & m1), v_hi = (nx0.y & m0) | (nx1.y & m1);
         if (c + 1 < c_last) fetch(c + 1);   // (its latency overlaps the reduction below and the workers' barrier)
-        if (c + 1 < Wn)   // (rows beyond n are never kept; whatever their slots hold is masked out)
-          own = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)v);
+        if (c + 1 < Wn) {   // (rows beyond n are never kept; whatever their slots hold is masked out)
+          own_lo = __reduce_or_sync(0xffffffffu, v_lo);
+          own_hi = __reduce_or_sync(0xffffffffu, v_hi);
+        }
       }
       if (lane == 0) {
-        if (own) smem_or64(&removed[c], own);   // round boundary: the bitmap that is carried over must be complete
+        if (own_lo | own_hi) smem_or64(&removed[c], ((unsigned long long)own_hi << 32) | own_lo);   // round boundary: the carried bitmap must be complete
         pipe_out[0] = kept_total;
         pipe_out[1] = c_waited;
       }
@@ -353,7 +360,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
         }
         __syncwarp();
         if (++slot == nslots) slot = 0;
-        if (stop_ring[c & 1]) break;
+        if (pipe_ring[c & 1].w) break;
       }
     } else {
       constexpr int kHalf = (kScanThreads - 64) / 2;   // warps 1-6: two threads per word (rows 0-31 / 32-63)
@@ -363,9 +370,10 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       for (int c = c_first; c < c_last; ++c) {
         mbar_wait(&full_bar[w_slot], w_par);   // (landed long ago; makes the rows visible to this thread)
         nb_sync(1 + (c & 1));        // keep word of chunk c is there; everybody is done with chunk c-1 and its slot
-        const unsigned long long kept = kept_ring[c & 1];
+        const uint4 pr = pipe_ring[c & 1];
+        const unsigned long long kept = ((unsigned long long)pr.y << 32) | pr.x;
         if (warp == 1) {   // the outputs of chunk c, off warp 0's path
-          const int base = base_ring[c & 1];
+          const int base = (int)pr.z;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int r = lane + 32 * h;
@@ -376,7 +384,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
             }
           }
         }
-        if (stop_ring[c & 1]) break;
+        if (pr.w) break;
         if (kept != 0ull && c + 2 < Wn) {
           const unsigned long long* rows = stage + (size_t)w_slot * slot_words;
           const uint32_t kbits = half ? (uint32_t)(kept >> 32) : (uint32_t)kept;
