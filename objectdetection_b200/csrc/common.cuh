@@ -93,6 +93,36 @@ struct Workspace {
   bool ok() const { return dry || off <= size; }
 };
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// The proposal front is a chain of ~12 short kernels. Launched with programmatic stream serialisation, the CTAs of kernel
+// N+1 become resident while kernel N still runs and block in griddepcontrol.wait until N has completed and flushed, so
+// the launch latency of every link overlaps its predecessor. Every kernel on the chain calls pdl_prologue() first, on
+// every path (a kernel that finished without waiting would release its own dependents too early). Without the launch
+// attribute both instructions are no-ops.
+#ifndef OD_PDL
+#define OD_PDL 1
+#endif
+__device__ __forceinline__ void pdl_prologue() {
+#if OD_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = OD_PDL;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------- exact math
 __device__ __forceinline__ float f_min(float a, float b) { return (b < a) ? b : a; }
 __device__ __forceinline__ float f_max(float a, float b) { return (a < b) ? b : a; }

@@ -37,6 +37,7 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
                 const int32_t* __restrict__ group, int K, int W, int rb_begin, float thr, int max_out,
                 const int32_t* __restrict__ scan_state, int state_stride, int Ws, unsigned long long* __restrict__ mask,
                 unsigned long long* __restrict__ diagT) {
+  pdl_prologue();
   const int rb = rb_begin + blockIdx.y, b = blockIdx.z;
   const int cb0 = rb + blockIdx.x * kMaskColTiles;
   const int n = num_valid ? min(num_valid[b], K) : K;
@@ -201,6 +202,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
                 const int32_t* __restrict__ num_valid, int K, int W, int Ws, int nslots, int max_out, int c_begin, int c_end,
                 int final_round, int32_t* __restrict__ scan_state, int state_stride, int32_t* __restrict__ keep_pos,
                 int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
+  pdl_prologue();
   extern __shared__ __align__(128) unsigned long long smem_u64[];
   const int Wr = (W + 15) & ~15;                 // keeps the ring 128-byte aligned
   unsigned long long* removed = smem_u64;        // [Wr]
@@ -857,9 +859,9 @@ static int scan_round_launch(const unsigned long long* mask, const unsigned long
     const size_t smem = plain + (size_t)nslots * per_slot;
     if (smem > 48 * 1024)
       OD_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<true><<<(unsigned)B, kScanThreads, smem, st>>>(mask, diagT, num_valid, (int)K, W, Ws, nslots, (int)max_out,
+    OD_CUDA(launch_pdl(nms_scan_kernel<true>, dim3((unsigned)B), dim3(kScanThreads), smem, st, mask, diagT, num_valid, (int)K, W, Ws, nslots, (int)max_out,
                                                                    c_begin, c_end, final_round, scan_state, stride, keep_pos,
-                                                                   num_kept, keep_flag);
+                                                                   num_kept, keep_flag));
   } else if (wide && !scan_state && c_begin == 0 && c_end >= W && W >= 64 && (wide_S = wide_scan_slice(B, W, &wide_prefetch)) > 0) {
     // too many boxes for the ring: spread the OR phase over co-resident CTAs
     int S = wide_S, Ki = (int)K, mo = (int)max_out;
@@ -913,11 +915,11 @@ int nms_sorted_launch(const float4* boxes, const int32_t* num_valid, const int32
     const dim3 grid((unsigned)((W - rb0 + kMaskColTiles - 1) / kMaskColTiles), (unsigned)(rb1 - rb0), (unsigned)B);
     const int32_t* st_in = round == 0 ? nullptr : state;
     if (thr >= 0.0f)
-      nms_mask_kernel<true><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
-                                                           stride, Ws, mask, diagT);
+      OD_CUDA(launch_pdl(nms_mask_kernel<true>, grid, dim3(kMaskThreads), 0, st, boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
+                                                           stride, Ws, mask, diagT));
     else
-      nms_mask_kernel<false><<<grid, kMaskThreads, 0, st>>>(boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
-                                                            stride, Ws, mask, diagT);
+      OD_CUDA(launch_pdl(nms_mask_kernel<false>, grid, dim3(kMaskThreads), 0, st, boxes, num_valid, group, (int)K, W, rb0, thr, (int)max_out, st_in,
+                                                            stride, Ws, mask, diagT));
     OD_LAUNCH_CHECK("nms_mask_kernel");
     OD_CHECK(scan_round_launch(mask, diagT, num_valid, B, K, Ws, max_out, rb0, rb1, round == (two_rounds ? 1 : 0),
                                two_rounds ? state : nullptr, keep_pos, num_kept, keep_flag, wide, st));

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256)
 proposal_decode_kernel(const float4* __restrict__ bbox, LevelTable lv, const float4* __restrict__ anchors, DevAnchorSpec spec,
                        int use_spec, const int32_t* __restrict__ ix, int64_t total, int K, int A, float4 stddev,
                        float4* __restrict__ clipped, ProposalDebugPtrs dbg) {
+  pdl_prologue();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int64_t b = t / K;
@@ -69,6 +70,7 @@ rpn_level_scores_kernel(LevelTable lv, int A, int64_t total, float* __restrict__
 // proposals[b,j] = clipped[b, keep_pos[b,j]] or zeros (tf.pad, :245-246).
 __global__ void proposal_gather_kernel(const float4* __restrict__ clipped, const int32_t* __restrict__ keep_pos, int K,
                                        int N, int64_t total, float4* __restrict__ proposals) {
+  pdl_prologue();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int64_t b = t / N;
@@ -270,19 +272,19 @@ static int proposal_core(const float* scores_src, int64_t score_sb, int64_t scor
     const int64_t total = B * K;
     const float4 sd = make_float4(params->bbox_stddev[0], params->bbox_stddev[1], params->bbox_stddev[2], params->bbox_stddev[3]);
     if (rpn_bbox4)
-      proposal_decode_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-          rpn_bbox4, lv, dptr<float4>(anchors), dspec, use_spec, ix, total, (int)K, (int)A, sd, p.clipped, dp);
+      OD_CUDA(launch_pdl(proposal_decode_kernel<false>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+          rpn_bbox4, lv, dptr<float4>(anchors), dspec, use_spec, ix, total, (int)K, (int)A, sd, p.clipped, dp));
     else
-      proposal_decode_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-          nullptr, lv, dptr<float4>(anchors), dspec, use_spec, ix, total, (int)K, (int)A, sd, p.clipped, dp);
+      OD_CUDA(launch_pdl(proposal_decode_kernel<true>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+          (const float4*)nullptr, lv, dptr<float4>(anchors), dspec, use_spec, ix, total, (int)K, (int)A, sd, p.clipped, dp));
     OD_LAUNCH_CHECK("proposal_decode_kernel");
   }
   // per-image NMS over boxes already in (score desc, index asc) order (:188-196, :234)
   OD_CHECK(nms_sorted_launch(p.clipped, nullptr, nullptr, B, K, params->nms_threshold, N, keep_pos, num_kept, nullptr,
                              p.nms_ws, p.nms_bytes, st));
   const int64_t total = B * N;
-  proposal_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.clipped, keep_pos, (int)K, (int)N, total,
-                                                                         dptr<float4>(proposals));
+  OD_CUDA(launch_pdl(proposal_gather_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p.clipped, keep_pos, (int)K, (int)N, total,
+                                                                         dptr<float4>(proposals)));
   OD_LAUNCH_CHECK("proposal_gather_kernel");
   return OD_OK;
 }

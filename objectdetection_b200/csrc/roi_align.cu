@@ -208,6 +208,7 @@ template <int BINS, int UNROLL, bool POW2>
 __global__ void __launch_bounds__(kBinThreads, OD_BIN_MINB)
 crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_t ph, int32_t pw, int32_t D4,
                  int32_t lgD4, float extrap, float4* __restrict__ out, int32_t* __restrict__ level_out) {
+  pdl_prologue();
   __shared__ BinTaps s_taps[BINS];
   __shared__ BinInfo s_info[BINS];
   const int32_t t = threadIdx.x;
@@ -336,8 +337,8 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
     const int64_t grid = (total_bins + BINS - 1) / BINS;
     if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
     // 32 bins per 128-thread CTA, 2 quads in flight per thread: best of the sweeps in profiles/r1_crop_variants.md
-    crop_bins_kernel<BINS, OD_BIN_UNROLL, true><<<(unsigned)grid, kBinThreads, 0, st>>>(
-        src, total_bins, (int32_t)bins_per_roi, ph, pw, D4, lg, extrap, reinterpret_cast<float4*>(out), level_out);
+    OD_CUDA(launch_pdl(crop_bins_kernel<BINS, OD_BIN_UNROLL, true>, dim3((unsigned)grid), dim3(kBinThreads), 0, st,
+        src, total_bins, (int32_t)bins_per_roi, ph, pw, D4, lg, extrap, reinterpret_cast<float4*>(out), level_out));
   } else {
     // thin or non-power-of-two depth: more bins per CTA so that the table build is amortised
     constexpr int BINS = 512;

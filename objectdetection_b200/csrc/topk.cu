@@ -81,6 +81,7 @@ topk_collect_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_
 __global__ void __launch_bounds__(kSelThreads)
 topk_hist1_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
                   int shift, uint32_t* __restrict__ hist) {
+  pdl_prologue();
   __shared__ uint32_t sh[kBins];
   const int row = blockIdx.y;
   for (int b = threadIdx.x; b < kBins; b += kSelThreads) sh[b] = 0;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(kSelThreads)
 topk_split_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib, int k,
                   int shift, int64_t buf_stride, int64_t cand_cap, const uint32_t* __restrict__ hist,
                   SelState* __restrict__ states, unsigned long long* __restrict__ buf, unsigned long long* __restrict__ cand) {
+  pdl_prologue();
   __shared__ uint32_t warp_sums[kSelThreads / 32];
   __shared__ BucketPick s_pick;
   __shared__ uint32_t s_base[2];
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(kTailThreads)
 topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_stride, int64_t col_stride, int ib,
                  int64_t buf_stride, int64_t cand_cap, SelState* __restrict__ states, unsigned long long* __restrict__ buf,
                  const unsigned long long* __restrict__ cand) {
+  pdl_prologue();
   __shared__ uint32_t sh[kBins];
   __shared__ uint32_t warp_sums[kTailThreads / 32];
   __shared__ BucketPick s_pick;
@@ -320,6 +323,7 @@ constexpr int64_t kMergeMaxK = 16384;
 // no barrier), the rest go through shared memory.
 __global__ void __launch_bounds__(kTileSortThreads)
 topk_tile_sort_kernel(unsigned long long* __restrict__ buf, int64_t buf_stride, int k) {
+  pdl_prologue();
   __shared__ unsigned long long skeys[kTileKeys];
   const int row = blockIdx.y, t0 = blockIdx.x * kTileKeys, t = threadIdx.x;
   unsigned long long* seg = buf + (int64_t)row * buf_stride + t0;
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(kMergeThreads)
 topk_merge_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_stride, int k, int ib,
                        const float* __restrict__ scores, int64_t row_stride, int64_t col_stride,
                        int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  pdl_prologue();
   extern __shared__ unsigned long long sk[];   // [k] the row's sorted tiles
   const int row = blockIdx.y;
   const unsigned long long* in = buf + (int64_t)row * buf_stride;
@@ -479,23 +484,23 @@ int topk_launch(const float* scores, int64_t rows, int64_t cols, int64_t row_str
     OD_LAUNCH_CHECK("topk_collect_kernel");
   } else {
     const int shift1 = total_bits - kDigitBits;   // total_bits >= 33
-    topk_hist1_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, shift1, hist);
+    OD_CUDA(launch_pdl(topk_hist1_kernel, grid, dim3(kSelThreads), 0, st, scores, cols, row_stride, col_stride, ib, shift1, hist));
     OD_LAUNCH_CHECK("topk_hist1_kernel");
-    topk_split_kernel<<<grid, kSelThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, (int)k, shift1, n_pow2, cap, hist,
-                                                    states, buf, cand);
+    OD_CUDA(launch_pdl(topk_split_kernel, grid, dim3(kSelThreads), 0, st, scores, cols, row_stride, col_stride, ib, (int)k, shift1, n_pow2, cap, hist,
+                                                    states, buf, cand));
     OD_LAUNCH_CHECK("topk_split_kernel");
-    topk_tail_kernel<<<(unsigned)rows, kTailThreads, 0, st>>>(scores, cols, row_stride, col_stride, ib, n_pow2, cap, states, buf, cand);
+    OD_CUDA(launch_pdl(topk_tail_kernel, dim3((unsigned)rows), dim3(kTailThreads), 0, st, scores, cols, row_stride, col_stride, ib, n_pow2, cap, states, buf, cand));
     OD_LAUNCH_CHECK("topk_tail_kernel");
   }
   if (k <= kMergeMaxK) {
     const int ntiles = (int)((k + kTileKeys - 1) / kTileKeys);
-    topk_tile_sort_kernel<<<dim3((unsigned)ntiles, (unsigned)rows), kTileSortThreads, 0, st>>>(buf, n_pow2, (int)k);
+    OD_CUDA(launch_pdl(topk_tile_sort_kernel, dim3((unsigned)ntiles, (unsigned)rows), dim3(kTileSortThreads), 0, st, buf, n_pow2, (int)k));
     OD_LAUNCH_CHECK("topk_tile_sort_kernel");
     const size_t smem = (size_t)k * sizeof(unsigned long long);
     if (smem > 48 * 1024)
       OD_CUDA(cudaFuncSetAttribute(topk_merge_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_merge_emit_kernel<<<dim3((unsigned)((k + kMergeThreads - 1) / kMergeThreads), (unsigned)rows), kMergeThreads, smem, st>>>(
-        buf, n_pow2, (int)k, ib, scores, row_stride, col_stride, idx_out, val_out);
+    OD_CUDA(launch_pdl(topk_merge_emit_kernel, dim3((unsigned)((k + kMergeThreads - 1) / kMergeThreads), (unsigned)rows), dim3(kMergeThreads), smem, st, 
+        buf, n_pow2, (int)k, ib, scores, row_stride, col_stride, idx_out, val_out));
     OD_LAUNCH_CHECK("topk_merge_emit_kernel");
   } else {
     // zero the padding, sort in global memory, then emit
