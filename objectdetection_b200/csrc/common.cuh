@@ -102,11 +102,19 @@ struct Workspace {
 #ifndef OD_PDL
 #define OD_PDL 1
 #endif
-__device__ __forceinline__ void pdl_prologue() {
+__device__ __forceinline__ void pdl_launch_dependents() {
 #if OD_PDL
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if OD_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
+}
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

@@ -202,7 +202,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
                 const int32_t* __restrict__ num_valid, int K, int W, int Ws, int nslots, int max_out, int c_begin, int c_end,
                 int final_round, int32_t* __restrict__ scan_state, int state_stride, int32_t* __restrict__ keep_pos,
                 int32_t* __restrict__ num_kept, int32_t* __restrict__ keep_flag) {
-  pdl_prologue();
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned long long smem_u64[];
   const int Wr = (W + 15) & ~15;                 // keeps the ring 128-byte aligned
   unsigned long long* removed = smem_u64;        // [Wr]
@@ -213,9 +213,18 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
   __shared__ uint4 pipe_ring[2];   // pipelined loop, slot c & 1: keep word of chunk c (x, y), boxes kept before it (z), max_out reached (w)
   __shared__ int32_t pipe_out[2];               // kept_total, last chunk waited for
   const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Shared-memory set-up touches nothing the previous kernel writes: done while that kernel is still running (the CTA
+  // is resident early under programmatic dependent launch), global memory only after pdl_wait().
+  for (int w = tid; w < Wr; w += kScanThreads) removed[w] = 0ull;
+  if (STAGED && tid == 0) {
+    for (int s = 0; s < nslots; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  pdl_wait();
   const int n = num_valid ? min(num_valid[b], K) : K;
   const int Wn = (n + 63) / 64;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // scan_state (two-round NMS): [0] = boxes kept so far, then the `removed` bitmap as 2*Wr 32-bit halves
   int32_t* state = scan_state ? scan_state + (int64_t)b * state_stride : nullptr;
   const bool resume = state != nullptr && c_begin > 0;
@@ -223,15 +232,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
   if (resume) {
     const unsigned long long* sr = reinterpret_cast<const unsigned long long*>(state + 2);
     for (int w = tid; w < Wr; w += kScanThreads) removed[w] = sr[w];
-  } else {
-    for (int w = tid; w < Wr; w += kScanThreads) removed[w] = 0ull;
-    if (keep_flag)
-      for (int i = tid; i < K; i += kScanThreads) keep_flag[(int64_t)b * K + i] = 0;
-  }
-  if (STAGED && tid == 0) {
-    for (int s = 0; s < nslots; ++s) mbar_init(&full_bar[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  } else if (keep_flag) {
+    for (int i = tid; i < K; i += kScanThreads) keep_flag[(int64_t)b * K + i] = 0;
   }
   __syncthreads();
   const unsigned long long* mrow = mask + (int64_t)b * K * Ws;
