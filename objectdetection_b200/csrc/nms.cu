@@ -179,9 +179,6 @@ constexpr int kScanMaxSlots = 8;
 #ifndef OD_SCAN_COPY_PARTS
 #define OD_SCAN_COPY_PARTS 4   // bulk copies per chunk of 64 mask rows (issued by different lanes of the producer warp)
 #endif
-#ifndef OD_SCAN_PIPE
-#define OD_SCAN_PIPE 1   // staged scan: warp 0 resolves chunks while the other warps OR one chunk behind (0: lock-step loop)
-#endif
 // named barriers (ids 1..4; 0 is __syncthreads): bar.arrive does not block, bar.sync does; both order shared memory
 __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kScanThreads) : "memory"); }
 __device__ __forceinline__ void nb_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -259,7 +256,6 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     for (int c = c_first; c < c_first + nslots - 1; ++c) stage_chunk(c);
 
   int c_waited = c_first - 1;
-#if OD_SCAN_PIPE
   if (STAGED) {
     // Only removed[c] is needed to resolve chunk c. Warp 0 resolves chunk c, ORs word c+1 of its kept rows itself and
     // goes on to chunk c+1; warps 1-7 OR the kept rows of chunk c into the words >= c+2 meanwhile, so the per-chunk
@@ -418,36 +414,21 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     kept_total = pipe_out[0];
     c_waited = pipe_out[1];
   }
-  const int c_loop = STAGED ? c_last : c_first;   // the lock-step loop below is the global-memory path only
-#else
-  const int c_loop = c_first;
-#endif
+  // ---- global-memory path (!STAGED; K beyond the ring in a two-round call): lock-step loop, rows read through L2
+  const int c_loop = STAGED ? c_last : c_first;
   unsigned long long nsup0 = 0ull, nsup1 = 0ull;
   if (!STAGED && warp == 0 && c_first < c_last) {
     nsup0 = __ldg(&dimg[(size_t)c_first * 64 + lane]);
     nsup1 = __ldg(&dimg[(size_t)c_first * 64 + lane + 32]);
   }
   for (int c = c_loop; c < c_last; ++c) {
-    if (STAGED) {
-      mbar_wait(&full_bar[(c - c_first) % nslots], (uint32_t)(((c - c_first) / nslots) & 1));   // chunk c has landed
-      c_waited = c;
-    }
-    __syncthreads();   // removed[c] is final; slot (c-1) % nslots is free again
-    const unsigned long long* rows =
-        STAGED ? stage + (size_t)((c - c_first) % nslots) * slot_words : mrow + (size_t)c * 64 * Ws;
+    __syncthreads();   // removed[c] is final
     if (warp == 0) {
-      unsigned long long sup0, sup1;   // transposed diagonal tile
-      if (STAGED) {
-        const unsigned long long* dt = rows + (size_t)64 * Ws;
-        sup0 = dt[lane];
-        sup1 = dt[lane + 32];
-      } else {   // global path: the tile of the next chunk is loaded one chunk ahead
-        sup0 = nsup0;
-        sup1 = nsup1;
-        if (c + 1 < c_last) {
-          nsup0 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane]);
-          nsup1 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane + 32]);
-        }
+      // transposed diagonal tile: the one of the next chunk is loaded one chunk ahead
+      const unsigned long long sup0 = nsup0, sup1 = nsup1;
+      if (c + 1 < c_last) {
+        nsup0 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane]);
+        nsup1 = __ldg(&dimg[(size_t)(c + 1) * 64 + lane + 32]);
       }
       const unsigned long long word = removed[c];
       const bool cand0 = (c * 64 + lane < n) && !((word >> lane) & 1ull);
@@ -468,9 +449,6 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       if (lane == 0) kept_word = kept;
     }
     __syncthreads();
-    // (issuing the two bulk copies costs their thread ~1400 cycles: done here, next to the OR phase in which the last
-    //  warp is otherwise idle, and not between the two barriers where everybody would wait for it)
-    stage_chunk(c + nslots - 1);
     const unsigned long long kept = kept_word;
     if (kept != 0ull) {
       if (tid < 64 && ((kept >> tid) & 1ull)) {
@@ -480,27 +458,9 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
       }
       kept_total += __popcll(kept);
       if (kept_total >= max_out) break;
-      // removed[w] |= OR of word w over the kept rows, for every later word w: two threads per word (rows 0-31 / 32-63,
-      // in different warps), conflict-free shared-memory reads, one 64-bit atomicOr each. Rows beyond n are never
-      // kept, so their (unwritten) words are never selected.
-      if (STAGED) {
-        const uint32_t kbits = (tid < kScanThreads / 2) ? (uint32_t)kept : (uint32_t)(kept >> 32);
-        const int r0 = (tid < kScanThreads / 2) ? 0 : 32;
-        if (kbits)
-          for (int w = c + 1 + (tid & (kScanThreads / 2 - 1)); w < Wn; w += kScanThreads / 2) {
-            const unsigned long long* col = rows + (size_t)r0 * Ws + w;
-            unsigned long long acc = 0ull;
-#pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += 16) {
-              unsigned long long v[16];
-#pragma unroll
-              for (int r = 0; r < 16; ++r) v[r] = col[(size_t)(r0 + r) * Ws];
-#pragma unroll
-              for (int r = 0; r < 16; ++r) acc |= v[r] & (0ull - (unsigned long long)((kbits >> (r0 + r)) & 1u));
-            }
-            if (acc) atomicOr(&removed[w], acc);
-          }
-      } else {
+      // removed[w] |= OR of word w over the kept rows, for every later word w. Rows beyond n are never kept, so their
+      // (unwritten) words are never selected.
+      {
         // rows straight from global memory (L2): one owner thread per word (two words per thread and pass), 16 rows x 2
         // words = 32 unconditional loads in flight per thread, no atomics
         for (int w0 = c + 1 + tid; w0 < Wn; w0 += 2 * kScanThreads) {
