@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kRpnThreads)
 rpn_anchor_best_kernel(const double* __restrict__ anchors, int A, const double* __restrict__ gt, const int32_t* __restrict__ gt_count,
                        int G, double* __restrict__ iou_max, int32_t* __restrict__ iou_arg, float4* __restrict__ anchors_c,
                        double* __restrict__ part_v, int32_t* __restrict__ part_i) {
+  pdl_prologue();
   extern __shared__ double s_gt[];   // [G][5]: y1,x1,y2,x2,area; [G] float4 conservative copies; FUSED: [warps][G] best IoU, anchor
   float4* s_gc = reinterpret_cast<float4*>(s_gt + (size_t)G * 5 + (G & 1));
   double* s_wv = reinterpret_cast<double*>(s_gc + G);
@@ -146,6 +147,7 @@ rpn_anchor_best_kernel(const double* __restrict__ anchors, int A, const double* 
 __global__ void __launch_bounds__(kRpnThreads)
 rpn_gt_reduce_kernel(const double* __restrict__ part_v, const int32_t* __restrict__ part_i, int nchunk,
                      const int32_t* __restrict__ gt_count, int G, int32_t* __restrict__ gt_best) {
+  pdl_prologue();
   __shared__ double s_v[kRpnThreads];
   __shared__ int32_t s_i[kRpnThreads];
   const int j = blockIdx.x, b = blockIdx.y;
@@ -182,6 +184,7 @@ rpn_gt_reduce_kernel(const double* __restrict__ part_v, const int32_t* __restric
 __global__ void __launch_bounds__(kRpnThreads)
 rpn_gt_best_kernel(const double* __restrict__ anchors, const float4* __restrict__ anchors_c, int A,
                    const double* __restrict__ gt, const int32_t* __restrict__ gt_count, int G, int32_t* __restrict__ gt_best) {
+  pdl_prologue();
   __shared__ double s_v[kRpnThreads];
   __shared__ int32_t s_i[kRpnThreads];
   const int j = blockIdx.x, b = blockIdx.y;
@@ -225,12 +228,14 @@ rpn_gt_best_kernel(const double* __restrict__ anchors, const float4* __restrict_
 }
 
 __global__ void rpn_label_kernel(const double* __restrict__ iou_max, int64_t total, int32_t* __restrict__ cls) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const double m = iou_max[i];
   cls[i] = (m >= 0.7) ? 1 : ((m < 0.3) ? -1 : 0);
 }
 __global__ void rpn_label_best_kernel(const int32_t* __restrict__ gt_best, int G, int A, int32_t* __restrict__ cls) {
+  pdl_prologue();
   const int j = threadIdx.x + blockIdx.x * blockDim.x, b = blockIdx.y;
   if (j >= G) return;
   const int a = gt_best[(int64_t)b * G + j];
@@ -354,6 +359,7 @@ __device__ __forceinline__ int cta_scan_packed(int v, int* scratch, int* total) 
 
 __global__ void __launch_bounds__(kRpnThreads)
 rpn_count_kernel(const int32_t* __restrict__ cls, int A, int2* __restrict__ cnt) {
+  pdl_prologue();
   __shared__ int scratch[kRpnWarps];
   const int b = blockIdx.y, i0 = blockIdx.x * kChunk + 4 * threadIdx.x;
   const int32_t* c = cls + (int64_t)b * A;
@@ -373,6 +379,7 @@ rpn_count_kernel(const int32_t* __restrict__ cls, int A, int2* __restrict__ cnt)
 __global__ void __launch_bounds__(kRpnThreads)
 rpn_compact_kernel(const int32_t* __restrict__ cls, int A, const int2* __restrict__ cnt, int max_targets,
                    int32_t* __restrict__ list_pos, int32_t* __restrict__ list_neg, int32_t* __restrict__ counts) {
+  pdl_prologue();
   __shared__ int scratch[32];
   const int b = blockIdx.y, i0 = blockIdx.x * kChunk + 4 * threadIdx.x;
   const int32_t* c = cls + (int64_t)b * A;
@@ -410,6 +417,7 @@ __global__ void __launch_bounds__(kRpnThreads)
 rpn_perm_kernel(const int32_t* __restrict__ perm_pos, const int32_t* __restrict__ perm_neg, int A, const int2* __restrict__ cnt,
                 int2* __restrict__ pcnt, int max_targets, const int32_t* __restrict__ list_pos,
                 const int32_t* __restrict__ list_neg, int32_t* __restrict__ cls) {
+  pdl_prologue();
   __shared__ int scratch[32];
   const int b = blockIdx.y, i0 = blockIdx.x * kChunk + 4 * threadIdx.x;
   int2 total, before;
@@ -460,6 +468,7 @@ rpn_emit_kernel(const double* __restrict__ anchors, int A, const double* __restr
                 const int32_t* __restrict__ iou_arg, const int32_t* __restrict__ cls, const int32_t* __restrict__ list_pos,
                 const int32_t* __restrict__ counts, int max_targets, double sd0, double sd1, double sd2, double sd3,
                 double* __restrict__ target_bbox, double* __restrict__ positive_anchors) {
+  pdl_prologue();
   __shared__ int scratch[33];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int32_t* c = cls + (int64_t)b * A;
@@ -577,31 +586,31 @@ int od_rpn_target_forward(const DLTensor* anchors, const DLTensor* gt_boxes, con
     size_t smem = ((size_t)g1 * 5 + 1) * sizeof(double) + (size_t)g1 * sizeof(float4);
     if (fused) {
       smem += (size_t)kRpnWarps * G * (sizeof(double) + sizeof(int32_t));
-      rpn_anchor_best_kernel<true><<<grid, kRpnThreads, smem, st>>>(an, (int)A, gt, gc, (int)G, r.iou_max, r.iou_arg, r.anchors_c,
-                                                                     r.part_v, r.part_i);
+      OD_CUDA(launch_pdl(rpn_anchor_best_kernel<true>, grid, dim3(kRpnThreads), smem, st, an, (int)A, gt, gc, (int)G, r.iou_max, r.iou_arg, r.anchors_c,
+                                                                     r.part_v, r.part_i));
     } else {
       if (smem > 48 * 1024)
         OD_CUDA(cudaFuncSetAttribute(rpn_anchor_best_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      rpn_anchor_best_kernel<false><<<grid, kRpnThreads, smem, st>>>(an, (int)A, gt, gc, (int)G, r.iou_max, r.iou_arg, r.anchors_c,
-                                                                      nullptr, nullptr);
+      OD_CUDA(launch_pdl(rpn_anchor_best_kernel<false>, grid, dim3(kRpnThreads), smem, st, an, (int)A, gt, gc, (int)G, r.iou_max, r.iou_arg, r.anchors_c,
+                                                                      nullptr, nullptr));
     }
     OD_LAUNCH_CHECK("rpn_anchor_best_kernel");
     if (fused) {
-      rpn_gt_reduce_kernel<<<dim3((unsigned)G, (unsigned)B), kRpnThreads, 0, st>>>(r.part_v, r.part_i, (int)grid.x, gc, (int)G, r.gt_best);
+      OD_CUDA(launch_pdl(rpn_gt_reduce_kernel, dim3((unsigned)G, (unsigned)B), dim3(kRpnThreads), 0, st, r.part_v, r.part_i, (int)grid.x, gc, (int)G, r.gt_best));
       OD_LAUNCH_CHECK("rpn_gt_reduce_kernel");
     } else if (G > 0) {
-      rpn_gt_best_kernel<<<dim3((unsigned)G, (unsigned)B), kRpnThreads, 0, st>>>(an, r.anchors_c, (int)A, gt, gc, (int)G, r.gt_best);
+      OD_CUDA(launch_pdl(rpn_gt_best_kernel, dim3((unsigned)G, (unsigned)B), dim3(kRpnThreads), 0, st, an, r.anchors_c, (int)A, gt, gc, (int)G, r.gt_best));
       OD_LAUNCH_CHECK("rpn_gt_best_kernel");
     }
   }
   {
     const int64_t total = B * A;
-    rpn_label_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r.iou_max, total, cls);
+    OD_CUDA(launch_pdl(rpn_label_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, r.iou_max, total, cls));
     OD_LAUNCH_CHECK("rpn_label_kernel");
   }
   if (G > 0) {
     const dim3 grid((unsigned)((G + 127) / 128), (unsigned)B);
-    rpn_label_best_kernel<<<grid, 128, 0, st>>>(r.gt_best, (int)G, (int)A, cls);
+    OD_CUDA(launch_pdl(rpn_label_best_kernel, grid, dim3(128), 0, st, r.gt_best, (int)G, (int)A, cls));
     OD_LAUNCH_CHECK("rpn_label_best_kernel");
   }
   {
@@ -609,18 +618,18 @@ int od_rpn_target_forward(const DLTensor* anchors, const DLTensor* gt_boxes, con
     const int32_t* pp = dptr<int32_t>(perm_pos);
     const int32_t* pn = dptr<int32_t>(perm_neg);
     int32_t* cnts = dptr<int32_t>(counts);
-    rpn_count_kernel<<<grid, kRpnThreads, 0, st>>>(cls, (int)A, r.cnt);
+    OD_CUDA(launch_pdl(rpn_count_kernel, grid, dim3(kRpnThreads), 0, st, cls, (int)A, r.cnt));
     OD_LAUNCH_CHECK("rpn_count_kernel");
-    rpn_compact_kernel<<<grid, kRpnThreads, 0, st>>>(cls, (int)A, r.cnt, (int)T, r.list_pos, r.list_neg, cnts);
+    OD_CUDA(launch_pdl(rpn_compact_kernel, grid, dim3(kRpnThreads), 0, st, cls, (int)A, r.cnt, (int)T, r.list_pos, r.list_neg, cnts));
     OD_LAUNCH_CHECK("rpn_compact_kernel");
-    rpn_perm_kernel<false><<<grid, kRpnThreads, 0, st>>>(pp, pn, (int)A, r.cnt, r.pcnt, (int)T, r.list_pos, r.list_neg, cls);
+    OD_CUDA(launch_pdl(rpn_perm_kernel<false>, grid, dim3(kRpnThreads), 0, st, pp, pn, (int)A, r.cnt, r.pcnt, (int)T, r.list_pos, r.list_neg, cls));
     OD_LAUNCH_CHECK("rpn_perm_kernel<count>");
-    rpn_perm_kernel<true><<<grid, kRpnThreads, 0, st>>>(pp, pn, (int)A, r.cnt, r.pcnt, (int)T, r.list_pos, r.list_neg, cls);
+    OD_CUDA(launch_pdl(rpn_perm_kernel<true>, grid, dim3(kRpnThreads), 0, st, pp, pn, (int)A, r.cnt, r.pcnt, (int)T, r.list_pos, r.list_neg, cls));
     OD_LAUNCH_CHECK("rpn_perm_kernel<apply>");
-    rpn_emit_kernel<<<(unsigned)B, kRpnSubThreads, 0, st>>>(an, (int)A, gt, (int)G, r.iou_arg, cls, r.list_pos, cnts, (int)T,
+    OD_CUDA(launch_pdl(rpn_emit_kernel, dim3((unsigned)B), dim3(kRpnSubThreads), 0, st, an, (int)A, gt, (int)G, r.iou_arg, cls, r.list_pos, cnts, (int)T,
                                                             params->bbox_stddev[0], params->bbox_stddev[1], params->bbox_stddev[2],
                                                             params->bbox_stddev[3], dptr<double>(rpn_target_bbox),
-                                                            dptr<double>(positive_anchors));
+                                                            dptr<double>(positive_anchors)));
     OD_LAUNCH_CHECK("rpn_emit_kernel");
   }
   return OD_OK;
