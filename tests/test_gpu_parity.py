@@ -144,11 +144,12 @@ def test_nms(n, thr):
             assert np.array_equal(keep[b, :num[b]], want) and np.all(keep[b, num[b]:] == -1)
 
 
-@pytest.mark.parametrize("K,max_out", [(6000, 1000), (12000, 2000), (20000, 500), (6000, 40)])
+@pytest.mark.parametrize("K,max_out", [(6000, 1000), (12000, 2000), (20000, 500), (6000, 40), (8000, 8000), (3000, 3000), (200, 200)])
 def test_nms_two_rounds_on_clustered_boxes(K, max_out):
     """max_out << K runs the NMS in two rounds (rows of the first 1.5 x max_out boxes, then - decided on the device -
     the rest, with the scan state carried over). Heavily clustered boxes force the second round; ragged num_valid;
-    K = 20000 takes the unstaged (global-memory) scan."""
+    K = 20000 takes the unstaged (global-memory) scan; max_out = K is a single round with 3 (K = 8000), 8 (K = 3000) or
+    more ring slots than chunks (K = 200)."""
     from objectdetection_b200.proposals import non_max_suppression
     rs = np.random.RandomState(K + max_out)
     B = 2
@@ -159,7 +160,7 @@ def test_nms_two_rounds_on_clustered_boxes(K, max_out):
     hw = np.take_along_axis(sizes, which[..., None].repeat(2, -1), 1) * np.exp(rs.normal(0, 0.06, (B, K, 2)))
     boxes = np.concatenate([c - hw / 2, c + hw / 2], -1).astype(f32)
     scores = rs.random_sample((B, K)).astype(f32)
-    nv = np.array([K, K - 1234], np.int32)
+    nv = np.array([K, K - min(1234, K // 3)], np.int32)
     keep, num = non_max_suppression(cu(boxes), cu(scores), max_out, 0.7, num_valid=nv)
     keep, num = host(keep), host(num)
     visited_all = False
