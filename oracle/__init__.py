@@ -459,6 +459,15 @@ def norm_boxes(box, img_shape):
     return np.divide((np.asarray(box) - shift), scale).astype(np.float32)
 
 
+def norm_boxes_tf(boxes, img_shape):
+    """utils.norm_boxes_tf (utils.py:198-210), the in-graph fp32 normalisation of the GT boxes (training.py:135):
+    scale = float32([h, w, h, w]) - 1.0f; (boxes - [0,0,1,1]) / scale, every operation in float32."""
+    h, w = (np.float32(v) for v in img_shape)
+    scale = np.array([h, w, h, w], np.float32) - np.float32(1.0)
+    shift = np.array([0., 0., 1., 1.], np.float32)
+    return (np.asarray(boxes, np.float32) - shift) / scale
+
+
 def denorm_boxes(boxes, shape):
     """utils.denorm_boxes (utils.py:212-227)."""
     h, w = shape
