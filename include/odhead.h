@@ -9,6 +9,7 @@
  *                                            softmax), training.py:146-166 (concat over P2..P6) + proposals_tf.py:136-214
  *   od_apply_box_deltas            replaces  apply_box_deltas               proposals_tf.py:23-65
  *   od_clip_boxes                  replaces  clip_boxes_to_01               proposals_tf.py:67-94
+ *   od_norm_boxes                  replaces  norm_boxes / norm_boxes_tf     utils.py:181-210
  *   od_topk                        replaces  tf.nn.top_k call sites         proposals_tf.py:169, detection.py:221
  *   od_nms                         replaces  tf.image.non_max_suppression   proposals_tf.py:234, detection.py:177
  *   od_gen_anchors                 replaces  gen_anchors / gen_anchors_pixel_coord   utils.py:336-369
@@ -118,6 +119,12 @@ int od_gen_anchors(const od_anchor_spec* spec, int normalized, DLTensor* anchors
 int od_apply_box_deltas(const DLTensor* boxes, const DLTensor* deltas, DLTensor* out, void* stream);
 /* window: [4] (shared) or [B,4] f32; out = max(min(v, hi), lo) per coordinate. */
 int od_clip_boxes(const DLTensor* boxes, const DLTensor* window, DLTensor* out, void* stream);
+/* Pixel -> normalised coordinates, (box - [0,0,1,1]) / (h-1, w-1, h-1, w-1), out [...,4] f32.
+ * tf_float32 == 0: utils.norm_boxes (utils.py:181-196; boxes i32 | f32 | f64, evaluated in float64, rounded once) -
+ *                  the window of DetectionLayer (detection.py:66) and of unmold_detection (detection.py:17);
+ * tf_float32 != 0: utils.norm_boxes_tf (utils.py:198-210; boxes f32, every operation in float32 with
+ *                  scale = float32(h) - 1.0f) - the in-graph normalisation of the GT boxes (training.py:135). */
+int od_norm_boxes(const DLTensor* boxes, int32_t image_h, int32_t image_w, int32_t tf_float32, DLTensor* out, void* stream);
 
 /* ---- top-k: k largest per row, sorted descending, ties -> lower index ------ */
 size_t od_topk_workspace_bytes(int64_t rows, int64_t cols, int64_t k);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "od_gen_anchors": (c_int, [POINTER(AnchorSpec), c_int, _P, _P]),
     "od_apply_box_deltas": (c_int, [_P, _P, _P, _P]),
     "od_clip_boxes": (c_int, [_P, _P, _P, _P]),
+    "od_norm_boxes": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P]),
     "od_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "od_topk": (c_int, [_P, c_int64, _P, _P, _P, c_size_t, _P]),
     "od_nms_workspace_bytes": (c_size_t, [c_int64, c_int64]),
@@ -181,16 +182,35 @@ def stream_ptr(device=None) -> int:
 
 
 _workspaces = {}
+_retired = []     # superseded workspaces: never freed, a captured CUDA graph may still hold their addresses
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """A per-device scratch buffer that only grows. Safe to reuse across calls on the same stream."""
+    """A per-(device, stream) scratch buffer that only grows.
+
+    Lifetime rules (CUDA graphs keep raw pointers):
+      * a buffer that was ever handed out is never freed: when a call needs more, the old tensor is parked in
+        ``_retired`` and stays valid for every graph captured against it;
+      * growth is refused DURING stream capture (the new tensor would come from the graph's private pool and then be
+        cached for eager use): run the call once eagerly on the capture stream first, as the docstrings say, or
+        pre-size with ``reserve_workspace``.
+    """
     key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise OdHeadError(-6, f"workspace of {nbytes} bytes would have to be (re)allocated during CUDA graph "
+                                  "capture: run the call once eagerly on the capture stream first")
+        if buf is not None:
+            _retired.append(buf)
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+def reserve_workspace(nbytes: int, device) -> None:
+    """Pre-size the current stream's workspace (e.g. before capturing a graph with larger shapes)."""
+    workspace(nbytes, device)
 
 
 def as_cuda(x, dtype, device=None) -> torch.Tensor:
@@ -212,20 +232,25 @@ def as_cuda(x, dtype, device=None) -> torch.Tensor:
 
 
 _const_cache = {}
+_CONST_CACHE_MAX = 4096
 
 
 def const_cuda(arr, dtype, device) -> torch.Tensor:
     """Small host constants (e.g. a normalised window) as CUDA tensors, cached by content, so that repeated calls
-    with the same values issue no H2D copy (and the call can be captured in a CUDA graph after one eager run)."""
+    with the same values issue no H2D copy (and the call can be captured in a CUDA graph after one eager run).
+    Cached tensors are never evicted (a captured graph may hold their address); past ``_CONST_CACHE_MAX`` distinct
+    constants new ones are simply not cached, and a miss during stream capture raises instead of copying."""
     import numpy as np
     a = np.ascontiguousarray(arr)
     key = (torch.device(device).index, str(dtype), a.dtype.str, a.shape, a.tobytes())
     t = _const_cache.get(key)
     if t is None:
-        if len(_const_cache) > 256:
-            _const_cache.clear()
+        if torch.cuda.is_current_stream_capturing():
+            raise OdHeadError(-6, "a host constant (window / image shape) would have to be copied to the device during "
+                                  "CUDA graph capture: run the call once eagerly first, or pass a CUDA tensor")
         t = torch.from_numpy(a.copy()).to(device).to(dtype).contiguous()
-        _const_cache[key] = t
+        if len(_const_cache) < _CONST_CACHE_MAX:
+            _const_cache[key] = t
     return t
 
 

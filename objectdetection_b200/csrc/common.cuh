@@ -55,6 +55,20 @@ void count_launches(int n);
     OD_LAUNCH_CHECK_NC(name);                                                                 \
   } while (0)
 
+// ----------------------------------------------------------------------------- device selection
+// Every entry point declares one DeviceScope before it validates its tensors. check_tensor() activates it with the
+// device id of the first tensor it sees: if that is not the calling thread's current device, the scope switches to it
+// (kernel launches, cudaFuncSetAttribute and cooperative-launch queries then address the tensors' GPU) and the
+// destructor restores the caller's device.
+struct DeviceScope {
+  int prev = -1;
+  bool active = false, switched = false;
+  DeviceScope* outer;
+  DeviceScope();
+  ~DeviceScope();
+  static void activate(int device_id);
+};
+
 // ----------------------------------------------------------------------------- DLPack checks
 enum DType { F32, F64, I32 };
 int check_tensor(const DLTensor* t, const char* name, DType dt, int ndim, bool need_contig, int* device);

@@ -6,6 +6,20 @@ namespace od {
 static thread_local char g_detail[512] = "";
 static unsigned long long g_launches = 0;
 
+static thread_local DeviceScope* g_scope = nullptr;
+DeviceScope::DeviceScope() : outer(g_scope) { g_scope = this; }
+DeviceScope::~DeviceScope() {
+  if (switched) cudaSetDevice(prev);
+  g_scope = outer;
+}
+void DeviceScope::activate(int device_id) {
+  DeviceScope* s = g_scope;
+  if (!s || s->active) return;
+  s->active = true;
+  if (cudaGetDevice(&s->prev) != cudaSuccess) return;
+  if (s->prev != device_id && cudaSetDevice(device_id) == cudaSuccess) s->switched = true;
+}
+
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error_detail(const char* fmt, ...) {
@@ -30,8 +44,10 @@ int check_tensor(const DLTensor* t, const char* name, DType dt, int ndim, bool n
   if (t->device.device_type != kDLCUDA)
     OD_FAIL(OD_ERR_DEVICE, "%s: device_type %d is not kDLCUDA (there is no CPU path)", name, (int)t->device.device_type);
   if (device) {
-    if (*device < 0) *device = t->device.device_id;
-    else if (*device != t->device.device_id)
+    if (*device < 0) {
+      *device = t->device.device_id;
+      DeviceScope::activate(*device);
+    } else if (*device != t->device.device_id)
       OD_FAIL(OD_ERR_DEVICE, "%s is on cuda:%d, expected cuda:%d", name, t->device.device_id, *device);
   }
   const uint8_t code = (dt == I32) ? (uint8_t)kDLInt : (uint8_t)kDLFloat;

@@ -370,6 +370,7 @@ int od_detection_forward(const DLTensor* proposals, const DLTensor* mrcnn_class_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!params) OD_FAIL(OD_ERR_NULL, "params is NULL");
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
   OD_CHECK(check_tensor(mrcnn_class_probs, "mrcnn_class_probs", F32, 3, true, &dev));
   OD_CHECK(check_tensor(mrcnn_bbox, "mrcnn_bbox", F32, 4, true, &dev));
@@ -453,6 +454,7 @@ int od_detection_forward(const DLTensor* proposals, const DLTensor* mrcnn_class_
 int od_unmold_detections(const DLTensor* detections, const DLTensor* window_norm, const DLTensor* original_shape,
                          DLTensor* boxes, DLTensor* class_ids, DLTensor* scores, DLTensor* counts, void* stream) {
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(detections, "detections", F32, 3, true, &dev));
   OD_CHECK(check_tensor(window_norm, "window_norm", F32, 2, true, &dev));
   OD_CHECK(check_tensor(original_shape, "original_shape", I32, 2, true, &dev));

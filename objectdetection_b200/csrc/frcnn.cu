@@ -280,6 +280,7 @@ int od_frcnn_proposal_forward(const DLTensor* rpn_box_class_prob, const DLTensor
   if (!rpn_box_class_prob || !rpn_bbox) OD_FAIL(OD_ERR_NULL, "inputs are NULL");
   const bool f64 = rpn_box_class_prob->dtype.bits == 64;
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(rpn_box_class_prob, "rpn_box_class_prob", f64 ? F64 : F32, 4, true, &dev));
   OD_CHECK(check_tensor(rpn_bbox, "rpn_bbox", f64 ? F64 : F32, 4, true, &dev));
   OD_CHECK(check_tensor(proposals, "proposals", F32, 2, true, &dev));

@@ -246,6 +246,7 @@ int od_rpn_loss_forward(const DLTensor* rpn_target_class, const DLTensor* rpn_cl
                         size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(rpn_target_class, "rpn_target_class", I32, -1, true, &dev));
   OD_CHECK(check_tensor(rpn_class_logits, "rpn_class_logits", F32, 3, true, &dev));
   OD_CHECK(check_tensor(losses, "losses", F32, 1, true, &dev));
@@ -306,6 +307,7 @@ int od_mrcnn_loss_forward(const DLTensor* target_class_ids, const DLTensor* pred
                           void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(target_class_ids, "mrcnn_target_class_ids", I32, 2, true, &dev));
   OD_CHECK(check_tensor(losses, "losses", F32, 1, true, &dev));
   const bool with_cls = pred_logits && active_class_ids, with_box = target_box && pred_box;   // either pair may be NULL

@@ -945,6 +945,7 @@ int od_nms(const DLTensor* boxes, const DLTensor* scores, const DLTensor* num_va
            int64_t max_out, DLTensor* keep_idx, DLTensor* num_kept, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(boxes, "boxes", F32, 3, true, &dev));
   OD_CHECK(check_tensor(scores, "scores", F32, 2, true, &dev));
   OD_CHECK(check_tensor(keep_idx, "keep_idx", I32, 2, true, &dev));

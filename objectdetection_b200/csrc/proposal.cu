@@ -103,6 +103,31 @@ __global__ void gen_anchors_pixel_kernel(DevAnchorSpec spec, int64_t A, double* 
   for (int c = 0; c < 4; ++c) out[i * 4 + c] = p[c];
 }
 
+// utils.norm_boxes (utils.py:181-196: fp64 divide, cast to fp32) and utils.norm_boxes_tf (utils.py:198-210: fp32
+// throughout, scale = float32(h) - 1.0f). One thread per box.
+template <typename TIn, bool TF32>
+__global__ void norm_boxes_kernel(const TIn* __restrict__ in, int64_t n, int32_t image_h, int32_t image_w,
+                                  float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const TIn* p = in + 4 * i;
+  float4 r;
+  if (TF32) {
+    const float sh = __fsub_rn((float)image_h, 1.0f), sw = __fsub_rn((float)image_w, 1.0f);
+    r.x = __fdiv_rn(__fsub_rn((float)p[0], 0.0f), sh);
+    r.y = __fdiv_rn(__fsub_rn((float)p[1], 0.0f), sw);
+    r.z = __fdiv_rn(__fsub_rn((float)p[2], 1.0f), sh);
+    r.w = __fdiv_rn(__fsub_rn((float)p[3], 1.0f), sw);
+  } else {
+    const double sh = (double)(image_h - 1), sw = (double)(image_w - 1);
+    r.x = (float)(((double)p[0] - 0.0) / sh);
+    r.y = (float)(((double)p[1] - 0.0) / sw);
+    r.z = (float)(((double)p[2] - 1.0) / sh);
+    r.w = (float)(((double)p[3] - 1.0) / sw);
+  }
+  out[i] = r;
+}
+
 struct ProposalWs {
   int32_t* ix;
   float* scores;
@@ -158,6 +183,7 @@ int od_gen_anchors(const od_anchor_spec* spec, int normalized, DLTensor* anchors
   OD_CHECK(make_dev_anchor_spec(spec, &d));
   const int64_t A = d.offset[d.num_levels];
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   if (normalized) {
     OD_CHECK(check_tensor(anchors, "anchors", F32, 3, true, &dev));
     if (anchors->shape[1] != A || anchors->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "anchors must be [B,%lld,4]", (long long)A);
@@ -175,6 +201,7 @@ int od_gen_anchors(const od_anchor_spec* spec, int normalized, DLTensor* anchors
 
 int od_apply_box_deltas(const DLTensor* boxes, const DLTensor* deltas, DLTensor* out, void* stream) {
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(boxes, "boxes", F32, 3, true, &dev));
   OD_CHECK(check_tensor(deltas, "deltas", F32, 3, true, &dev));
   OD_CHECK(check_tensor(out, "out", F32, 3, true, &dev));
@@ -191,6 +218,7 @@ int od_apply_box_deltas(const DLTensor* boxes, const DLTensor* deltas, DLTensor*
 
 int od_clip_boxes(const DLTensor* boxes, const DLTensor* window, DLTensor* out, void* stream) {
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(boxes, "boxes", F32, 3, true, &dev));
   OD_CHECK(check_tensor(window, "window", F32, -1, true, &dev));
   OD_CHECK(check_tensor(out, "out", F32, 3, true, &dev));
@@ -206,6 +234,31 @@ int od_clip_boxes(const DLTensor* boxes, const DLTensor* window, DLTensor* out, 
   clip_boxes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dptr<float4>(boxes), dptr<float4>(window), per_image, boxes->shape[1], total, dptr<float4>(out));
   OD_LAUNCH_CHECK("clip_boxes_kernel");
+  return OD_OK;
+}
+
+int od_norm_boxes(const DLTensor* boxes, int32_t image_h, int32_t image_w, int32_t tf_float32, DLTensor* out, void* stream) {
+  int dev = -1;
+  DeviceScope dev_scope;
+  if (!boxes) OD_FAIL(OD_ERR_NULL, "boxes is NULL");
+  const bool is_i32 = boxes->dtype.code == kDLInt && boxes->dtype.bits == 32;
+  const bool is_f64 = boxes->dtype.code == kDLFloat && boxes->dtype.bits == 64;
+  OD_CHECK(check_tensor(boxes, "boxes", is_i32 ? I32 : (is_f64 ? F64 : F32), -1, true, &dev));
+  OD_CHECK(check_tensor(out, "out", F32, boxes->ndim, true, &dev));
+  if (boxes->ndim < 1 || boxes->shape[boxes->ndim - 1] != 4) OD_FAIL(OD_ERR_SHAPE, "boxes must be [...,4]");
+  for (int i = 0; i < boxes->ndim; ++i)
+    if (boxes->shape[i] != out->shape[i]) OD_FAIL(OD_ERR_SHAPE, "boxes/out shapes differ");
+  if (tf_float32 && !(!is_i32 && !is_f64)) OD_FAIL(OD_ERR_DTYPE, "norm_boxes_tf takes float32 boxes");
+  if (reinterpret_cast<uintptr_t>(dptr<float>(out)) % 16) OD_FAIL(OD_ERR_LAYOUT, "out not 16-byte aligned");
+  const int64_t n = numel(boxes) / 4;
+  if (n == 0) return OD_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (tf_float32) norm_boxes_kernel<float, true><<<grid, 128, 0, st>>>(dptr<float>(boxes), n, image_h, image_w, dptr<float4>(out));
+  else if (is_i32) norm_boxes_kernel<int32_t, false><<<grid, 128, 0, st>>>(dptr<int32_t>(boxes), n, image_h, image_w, dptr<float4>(out));
+  else if (is_f64) norm_boxes_kernel<double, false><<<grid, 128, 0, st>>>(dptr<double>(boxes), n, image_h, image_w, dptr<float4>(out));
+  else norm_boxes_kernel<float, false><<<grid, 128, 0, st>>>(dptr<float>(boxes), n, image_h, image_w, dptr<float4>(out));
+  OD_LAUNCH_CHECK("norm_boxes_kernel");
   return OD_OK;
 }
 
@@ -298,6 +351,7 @@ int od_proposal_forward(const DLTensor* rpn_class_probs, const DLTensor* rpn_bbo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!params) OD_FAIL(OD_ERR_NULL, "params is NULL");
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(rpn_class_probs, "rpn_class_probs", F32, 3, true, &dev));
   OD_CHECK(check_tensor(rpn_bbox, "rpn_bbox", F32, 3, true, &dev));
   OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
@@ -339,6 +393,7 @@ int od_proposal_forward_levels(const DLTensor* const* class_logits, const DLTens
   if (num_levels < 1 || num_levels > OD_MAX_LEVELS) OD_FAIL(OD_ERR_PARAM, "num_levels %d out of range", num_levels);
   if (params->pre_nms_limit < 0 || params->post_nms_count < 0) OD_FAIL(OD_ERR_PARAM, "negative counts");
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
   LevelTable lc, lb;
   memset(&lc, 0, sizeof(lc));

@@ -370,6 +370,7 @@ int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_level
   if (num_levels < 1 || num_levels > OD_MAX_LEVELS) OD_FAIL(OD_ERR_PARAM, "num_levels %d not in [1,%d]", num_levels, OD_MAX_LEVELS);
   if (pool_h < 1 || pool_w < 1) OD_FAIL(OD_ERR_PARAM, "pool shape %dx%d unsupported", pool_h, pool_w);
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(rois, "rois", F32, 3, true, &dev));
   if (rois->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "rois must be [B,N,4]");
   const int64_t B = rois->shape[0], N = rois->shape[1];
@@ -419,6 +420,7 @@ int od_crop_and_resize(const DLTensor* image, const DLTensor* boxes, const DLTen
                        int32_t crop_w, float extrapolation_value, DLTensor* out, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(image, "image", F32, 4, true, &dev));
   OD_CHECK(check_tensor(boxes, "boxes", F32, 2, true, &dev));
   OD_CHECK(check_tensor(box_ind, "box_ind", I32, 1, true, &dev));
@@ -449,6 +451,7 @@ int od_roi_pool_forward(const DLTensor* feature_map, const DLTensor* proposals, 
                         DLTensor* out, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(feature_map, "feature_map", F32, 4, true, &dev));
   OD_CHECK(check_tensor(proposals, "proposals", F32, 2, true, &dev));
   OD_CHECK(check_tensor(out, "out", F32, 4, true, &dev));

@@ -549,6 +549,7 @@ int od_rpn_target_forward(const DLTensor* anchors, const DLTensor* gt_boxes, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!params) OD_FAIL(OD_ERR_NULL, "params is NULL");
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(anchors, "anchors", F64, 2, true, &dev));
   OD_CHECK(check_tensor(gt_boxes, "gt_boxes", F64, 3, true, &dev));
   OD_CHECK(check_tensor(gt_count, "gt_count", I32, 1, true, &dev));

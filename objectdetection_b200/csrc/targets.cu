@@ -292,6 +292,7 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!params) OD_FAIL(OD_ERR_NULL, "params is NULL");
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(proposals, "proposals", F32, 3, true, &dev));
   OD_CHECK(check_tensor(gt_class_ids, "gt_class_ids", I32, 2, true, &dev));
   OD_CHECK(check_tensor(gt_boxes, "gt_boxes", F32, 3, true, &dev));

@@ -525,6 +525,7 @@ size_t od_topk_workspace_bytes(int64_t rows, int64_t cols, int64_t k) { return t
 int od_topk(const DLTensor* scores, int64_t k, DLTensor* values, DLTensor* indices, void* ws, size_t ws_bytes,
             void* stream) {
   int dev = -1;
+  DeviceScope dev_scope;  // launches go to the tensors' device; the caller's current device is restored on return
   OD_CHECK(check_tensor(scores, "scores", F32, 2, false, &dev));
   OD_CHECK(check_tensor(indices, "indices", I32, 2, true, &dev));
   const int64_t rows = scores->shape[0], cols = scores->shape[1];

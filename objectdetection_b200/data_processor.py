@@ -82,7 +82,7 @@ class BuildDetectionTargets():
                      gt_assignment=torch.empty((B, R), dtype=torch.int32, device=dev))
             for k, v in d.items():
                 setattr(dbg, k, dl(v))
-            self.debug_dict = d
+            self.debug_raw = d
         ws = _lib.workspace(L.od_detection_target_workspace_bytes(B, N, G), dev)
         _lib.check(L.od_detection_target_forward(dl(props), dl(cls), dl(gtb), dl(pp), dl(pn), ctypes.byref(params),
                                                  dl(rois), dl(rcls), dl(deltas), dl(masks), dl(mtargets), ctypes.byref(dbg),
@@ -94,6 +94,38 @@ class BuildDetectionTargets():
             self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas = rois[0], rcls, deltas[0]   # cls is [1,R] (:627)
         else:
             self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas = rois, rcls, deltas
+        if self.DEBUG:
+            per_image = [self._reference_debug_dict(b, props[b], cls[b], gtb[b], rois[b], rcls[b], deltas[b])
+                         for b in range(B)]
+            self.debug_dict = per_image[0] if single else per_image
+
+    def _reference_debug_dict(self, b, props, gt_cls, gt_box, rois, rcls, deltas):
+        """The 21 named intermediates of data_processor.py:629-652 for image ``b``, with the reference's shapes and
+        dtypes, assembled (DEBUG only; this synchronises) from what the kernel recorded: the IoU matrix in compacted
+        row/column order, its row maxima, the sampled index lists, the GT assignment and the counts. As in the
+        reference, ``pos_indices_05more`` / ``neg_indices_05more`` alias the lists AFTER shuffling + truncation (the
+        variable is reassigned at :587 / :597 before the dict is built)."""
+        raw = self.debug_raw
+        n_prop, n_gt, _, _, pos_count, neg_count = (int(v) for v in raw["counts"][b].tolist())
+        nzp = (props != 0).any(dim=1)                           # cast(reduce_sum(abs(p)), bool), :564
+        nzg = gt_cls != 0                                       # :568
+        sp = raw["sampled_pos"][b, :pos_count].to(torch.int64)
+        sn = raw["sampled_neg"][b, :neg_count].to(torch.int64)
+        iou = raw["iou"][b, :n_prop, :n_gt]
+        assign = raw["gt_assignment"][b, :pos_count].to(torch.int64)
+        gt_boxes_nz, gt_cls_nz = gt_box[nzg], gt_cls[nzg]
+        R = int(self.train_rois_per_image)
+        one_third = torch.tensor(1 / 0.33, dtype=torch.float32)          # float32(1/0.33) * float32(pos_count), :593
+        neg_cnt = int((one_third * torch.tensor(float(pos_count), dtype=torch.float32)).to(torch.int32)) - pos_count
+        return dict(
+            non_zero_proposals=nzp, prop_corresponding_gt_non_zero=props[nzp], non_zeros_gt_box=nzg,
+            gt_boxes_non_zero=gt_boxes_nz, gt_class_ids_non_zero=gt_cls_nz, iou=iou,
+            roi_iou_max=raw["roi_iou_max"][b, :n_prop], pos_indices_05more=sp, neg_indices_05more=sn,
+            num_pos_inst=int(R * 0.33), pos_indices=sp,
+            pos_count=torch.tensor(pos_count, dtype=torch.int32), neg_cnt=torch.tensor(neg_cnt, dtype=torch.int32),
+            neg_indices=sn, pos_rois=rois[:pos_count], neg_rois=rois[pos_count:pos_count + neg_count],
+            pos_iou=iou[sp], roi_gt_box_assignment=assign, roi_gt_class_ids=rcls[:pos_count],
+            roi_gt_boxes=gt_boxes_nz[assign], roi_gt_box_deltas=deltas[:pos_count])
 
     def get_target_rois(self):
         return self.rois, self.roi_gt_class_ids, self.roi_gt_box_deltas
@@ -104,6 +136,9 @@ class BuildDetectionTargets():
         return self.roi_gt_masks
 
     def debug_outputs(self):
+        """The reference's debug dict (data_processor.py:629-652, 21 keys) - one dict for a per-image call, a list of
+        dicts for a batched one. ``debug_raw`` keeps the kernel's own batched arrays (pre-shuffle index lists,
+        counts [B,6], ...)."""
         return self.debug_dict
 
 

@@ -8,34 +8,21 @@ import torch
 
 from . import _lib
 from .proposals import _stddev4
-from .utils import denorm_boxes, norm_boxes
+from .utils import norm_boxes
 
 
 def unmold_detection(original_image_shape, image_shape, detections, image_window):
-    """detection.py:8-53 — host post-processing of ONE image's [M,6] detections (numpy, like the reference):
-    trim at the first class_id == 0, map from the normalised window back to original-image pixels, drop
-    zero-area boxes. Returns (boxes [n,4] int32, class_ids [n] int32, scores [n])."""
-    if isinstance(detections, torch.Tensor):
-        detections = detections.detach().cpu().numpy()
-    image_window = norm_boxes(image_window, image_shape[:2])
-    zero_ix = np.where(detections[:, 4] == 0)[0]
-    N = zero_ix[0] if zero_ix.shape[0] > 0 else detections.shape[0]
-    boxes = detections[:N, :4]
-    class_ids = detections[:N, 4].astype(np.int32)
-    scores = detections[:N, 5]
-    wy1, wx1, wy2, wx2 = image_window
-    shift = np.array([wy1, wx1, wy1, wx1])
-    wh = wy2 - wy1
-    ww = wx2 - wx1
-    scale = np.array([wh, ww, wh, ww])
-    boxes = np.divide(boxes - shift, scale)
-    boxes = denorm_boxes(boxes, original_image_shape[:2])
-    exclude_ix = np.where((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]) <= 0)[0]
-    if exclude_ix.shape[0] > 0:
-        boxes = np.delete(boxes, exclude_ix, axis=0)
-        class_ids = np.delete(class_ids, exclude_ix, axis=0)
-        scores = np.delete(scores, exclude_ix, axis=0)
-    return boxes, class_ids, scores
+    """detection.py:8-53 for ONE image's [M,6] detections: trim at the first class_id == 0, map from the normalised
+    window back to original-image pixels (``denorm_boxes``), drop zero-area boxes. Same signature and return values as
+    the reference - (boxes [n,4] int32, class_ids [n] int32, scores [n] float32) as numpy arrays - computed by the
+    device kernel ``od_unmold_detections`` (the numpy restatement lives in ``oracle/`` as the checker)."""
+    det = _lib.as_cuda(detections, torch.float32)
+    if det.dim() != 2 or det.shape[1] != 6:
+        raise ValueError("detections must be [num_detections, 6] for one image")
+    boxes, cls, scores, counts = unmold_detections_batch(np.asarray(original_image_shape).reshape(1, -1), image_shape,
+                                                         det[None], np.asarray(image_window).reshape(1, 4))
+    n = int(counts[0].item())
+    return boxes[0, :n].cpu().numpy(), cls[0, :n].cpu().numpy(), scores[0, :n].cpu().numpy()
 
 
 def unmold_detections_batch(original_image_shapes, image_shape, detections, image_windows):
@@ -46,13 +33,18 @@ def unmold_detections_batch(original_image_shapes, image_shape, detections, imag
     det = _lib.as_cuda(detections, torch.float32)
     dev = det.device
     B, M = det.shape[0], det.shape[1]
-    win = norm_boxes(np.asarray(image_windows).reshape(-1, 4), image_shape[:2])          # detection.py:17, host, tiny
-    if win.shape[0] == 1 and B > 1:
-        win = np.repeat(win, B, 0)
+    if isinstance(image_windows, torch.Tensor) and image_windows.is_cuda:
+        win_t = norm_boxes(image_windows.reshape(-1, 4), image_shape[:2])               # detection.py:17, on the device
+        if win_t.shape[0] == 1 and B > 1:
+            win_t = win_t.expand(B, 4).contiguous()
+    else:
+        win = norm_boxes(np.asarray(image_windows).reshape(-1, 4), image_shape[:2])      # detection.py:17, host, tiny
+        if win.shape[0] == 1 and B > 1:
+            win = np.repeat(win, B, 0)
+        win_t = _lib.const_cuda(np.ascontiguousarray(win, np.float32), torch.float32, dev)
     shp = np.asarray(original_image_shapes, np.int32).reshape(-1, np.asarray(original_image_shapes).shape[-1])[:, :2]
     if shp.shape[0] == 1 and B > 1:
         shp = np.repeat(shp, B, 0)
-    win_t = _lib.const_cuda(np.ascontiguousarray(win, np.float32), torch.float32, dev)
     shp_t = _lib.const_cuda(np.ascontiguousarray(shp, np.int32), torch.int32, dev)
     boxes = torch.empty((B, M, 4), dtype=torch.int32, device=dev)
     cls = torch.empty((B, M), dtype=torch.int32, device=dev)
@@ -76,9 +68,12 @@ class DetectionLayer():
         self.detection_min_thresh = conf.DETECTION_MIN_THRESHOLD
         self.detection_nms_threshold = conf.DETECTION_NMS_THRESHOLD
         self.DEBUG = DEBUG
-        if isinstance(window, torch.Tensor):
-            window = window.detach().cpu().numpy()
-        window = norm_boxes(np.asarray(window), image_shape[:2])   # detection.py:66
+        # detection.py:66. A CUDA window is normalised on the device (no host synchronisation); a host window with
+        # the reference's numpy formula, then cached on the device by value.
+        if isinstance(window, torch.Tensor) and window.is_cuda:
+            window = norm_boxes(window.reshape(-1, 4), image_shape[:2])
+        else:
+            window = norm_boxes(np.asarray(window.numpy() if isinstance(window, torch.Tensor) else window), image_shape[:2])
         self.window = window
         self.detections = self.build(window, proposals, mrcnn_class_probs, mrcnn_bbox)
 
@@ -88,7 +83,10 @@ class DetectionLayer():
         dev = props.device
         probs = _lib.as_cuda(mrcnn_class_probs, torch.float32, dev)
         bbox = _lib.as_cuda(mrcnn_bbox, torch.float32, dev)
-        win = _lib.const_cuda(np.asarray(window, np.float32).reshape(-1, 4), torch.float32, dev)
+        if isinstance(window, torch.Tensor):
+            win = _lib.as_cuda(window, torch.float32, dev).reshape(-1, 4)
+        else:
+            win = _lib.const_cuda(np.asarray(window, np.float32).reshape(-1, 4), torch.float32, dev)
         B, N, C = probs.shape
         if B != self.num_batches:
             raise ValueError(f"num_batches={self.num_batches} but mrcnn_class_probs has batch {B}")
@@ -119,13 +117,20 @@ class DetectionLayer():
         return self.detections
 
     def debug_outputs(self):
-        """Same order as detection.py:268-279. The index-plumbing tensors of the TF graph (indices, mesh, ixs) have
-        no counterpart; the per-image pre-NMS lists are derived from keep_mask on request."""
+        """The 11 items of detection.py:268-279, same order, same shapes and dtypes. ``class_ids``, ``class_scores``,
+        ``bbox_delta``, ``refined_proposals`` and the clipped boxes come straight from the kernels; the index plumbing
+        of the TF graph (``indices``, ``mesh``, ``ixs``, :119-125) carries no information beyond ``class_ids`` and is
+        synthesised here on request; the per-image pre-NMS lists are the rows selected by the kernel's keep mask
+        (class > 0 and score > threshold, ascending ROI index like ``set_intersection``)."""
         keep = self.keep_mask.bool()
-        B = keep.shape[0]
+        B, N = keep.shape
+        dev = keep.device
+        indices = torch.arange(N, dtype=torch.int32, device=dev).repeat(B, 1)                 # detection.py:120-124
+        mesh = torch.arange(B, dtype=torch.int32, device=dev)[:, None].repeat(1, N)           # detection.py:119
+        ixs = torch.stack([mesh, indices, self.class_ids], dim=2)                             # detection.py:125
         clipped_list = [self.clipped_proposals[b][None] for b in range(B)]
         pre_cls = [self.class_ids[b][keep[b]] for b in range(B)]
         pre_scores = [self.class_scores[b][keep[b]] for b in range(B)]
         pre_props = [self.clipped_proposals[b][keep[b]] for b in range(B)]
-        return (self.class_ids, None, None, None, self.class_scores, self.bbox_delta, self.refined_proposals,
+        return (self.class_ids, indices, mesh, ixs, self.class_scores, self.bbox_delta, self.refined_proposals,
                 clipped_list, pre_cls, pre_scores, pre_props)

@@ -79,14 +79,23 @@ class MaskRCNN():
 
     def roi_pooling(self, image_shape, pool_shape, levels, proposals, feature_maps):
         """maskrcnn.py:74-187. The reference's per-level where/gather, concat and re-sort are fused away: each
-        ROI is written straight to row b*N+n. ``box_to_level`` / ``sorting_tensor`` / ``ix`` therefore do not exist
-        as tensors; DEBUG exposes ``roi_level`` (the only one of the four that is data)."""
+        ROI is written straight to row b*N+n, and ``roi_level`` is the only one of the four DEBUG tensors that is
+        data. ``box_to_level`` / ``sorting_tensor`` / ``ix`` (maskrcnn.py:128-173) are pure index plumbing - functions
+        of ``roi_level`` - and are synthesised from it when DEBUG is set, with the reference's shapes and dtypes."""
         res = pyramid_roi_align(feature_maps, proposals, image_shape, pool_shape, levels, return_levels=self.DEBUG)
         if self.DEBUG:
             self.pooled_rois, self.roi_level = res
+            per_level = [torch.nonzero(self.roi_level == int(lv)) for lv in levels]         # tf.where: row-major
+            b2l = torch.cat(per_level, dim=0).to(torch.int32)                               # [B*N, (batch, box)]
+            box_range = torch.arange(b2l.shape[0], dtype=torch.int32, device=b2l.device)[:, None]
+            self.box_to_level = torch.cat([b2l, box_range], dim=1)                          # maskrcnn.py:161-163
+            self.sorting_tensor = self.box_to_level[:, 0] * 100000 + self.box_to_level[:, 1]   # maskrcnn.py:168
+            # top_k(k = all).indices[::-1] (:171): descending with ties to the lower position, then reversed
+            order = torch.sort(-self.sorting_tensor.to(torch.int64), stable=True).indices
+            self.ix = torch.flip(order, dims=[0]).to(torch.int32)
         else:
             self.pooled_rois, self.roi_level = res, []
-        self.box_to_level, self.sorting_tensor, self.ix = [], [], []
+            self.box_to_level, self.sorting_tensor, self.ix = [], [], []
 
     def get_pooled_rois(self):
         return self.pooled_rois

@@ -1,8 +1,8 @@
 """Box / anchor utilities with the reference's names (MaskRCNN/building_blocks/utils.py:155-369).
 
-Anchor generation runs on the GPU (``od_gen_anchors``: fp64 per anchor, bit-exact with numpy); the three
-box-normalisation helpers are the same tiny host-side numpy arithmetic as in the reference (they prepare a
-4-element window / post-process <= 100 detection rows and are not part of the device path).
+Anchor generation runs on the GPU (``od_gen_anchors``: fp64 per anchor, bit-exact with numpy). ``norm_boxes`` /
+``norm_boxes_tf`` run on the GPU (``od_norm_boxes``) when they are handed a CUDA tensor; for host inputs
+``norm_boxes`` / ``denorm_boxes`` stay the reference's own two-line numpy formulas (a 4-element window).
 """
 from __future__ import annotations
 
@@ -20,8 +20,33 @@ def get_resnet_stage_shapes(conf, image_shape):
                      for stride in conf.RESNET_STRIDES])
 
 
+def _norm_boxes_cuda(box, img_shape, tf_float32):
+    h, w = int(img_shape[0]), int(img_shape[1])
+    if not (box.dtype in (torch.int32, torch.float32, torch.float64)):
+        box = box.to(torch.float32 if box.dtype.is_floating_point else torch.int32)
+    box = box.contiguous()
+    out = torch.empty(box.shape, dtype=torch.float32, device=box.device)
+    dl = _lib.DL()
+    _lib.check(_lib.lib().od_norm_boxes(dl(box), h, w, 1 if tf_float32 else 0, dl(out), _lib.stream_ptr(box.device)),
+               "od_norm_boxes")
+    return out
+
+
+def norm_boxes_tf(boxes, img_shape) -> torch.Tensor:
+    """utils.py:198-210: the in-graph float32 normalisation of the GT boxes (training.py:135),
+    (boxes - [0,0,1,1]) / (float32([h,w,h,w]) - 1), every operation in float32, on the GPU. Not bit-identical to
+    ``norm_boxes`` (float64 divide, one rounding) - a training caller must use this one to reproduce the
+    reference's GT inputs of BuildDetectionTargets."""
+    return _norm_boxes_cuda(_lib.as_cuda(boxes, torch.float32), img_shape, True)
+
+
 def norm_boxes(box, img_shape):
-    """utils.py:181-196: pixel -> normalised coordinates (fp64 divide, float32 result)."""
+    """utils.py:181-196: pixel -> normalised coordinates (fp64 divide, float32 result). A CUDA tensor is
+    normalised on the device (no host round trip); anything else on the host with numpy like the reference."""
+    if isinstance(box, torch.Tensor) and box.is_cuda:
+        return _norm_boxes_cuda(box, img_shape, False)
+    if isinstance(box, torch.Tensor):
+        box = box.numpy()
     h, w = img_shape
     scale = np.array([h - 1, w - 1, h - 1, w - 1])
     shift = np.array([0, 0, 1, 1])

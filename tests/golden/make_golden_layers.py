@@ -26,8 +26,7 @@ sys.path.insert(0, HERE)
 import layer_recipes as R  # noqa: E402
 import tf_shim  # noqa: E402
 
-DET_DEBUG_KEYS = ("class_ids", "indices", "mesh", "ixs", "class_scores", "bbox_delta", "refined_proposals",
-                  "clipped_proposals_list", "pre_nms_class_ids_list", "pre_nms_scores_list", "pre_nms_proposals_list")
+from make_golden_layers_keys import DET_DEBUG_KEYS  # noqa: E402
 
 
 def digest(a):

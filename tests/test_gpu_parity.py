@@ -404,7 +404,7 @@ def _check_targets(conf, props, cls, gt, pp, pn):
     B = props.shape[0]
     t = BuildDetectionTargets(conf, cu(props), cu(cls), cu(gt), DEBUG=True, perm_pos=cu(pp), perm_neg=cu(pn))
     rois, rcls, deltas = (host(x) for x in t.get_target_rois())
-    d = {k: host(v) for k, v in t.debug_outputs().items()}
+    d = {k: host(v) for k, v in t.debug_raw.items()}
     R = conf.MRCNN_TRAIN_ROIS_PER_IMAGE
     assert rois.shape == (B, R, 4) and rcls.shape == (B, R) and deltas.shape == (B, R, 4)
     for b in range(B):
@@ -492,7 +492,8 @@ def test_detection_targets_per_image_signature():
     assert np.array_equal(host(rcls), w_cls)
     # unseeded path: counts only
     t2 = BuildDetectionTargets(conf, props[0], cls[0], gt[0], DEBUG=True)
-    assert int(t2.debug_outputs()["counts"][0, 4]) == int((w_cls > 0).sum())
+    assert int(t2.debug_raw["counts"][0, 4]) == int((w_cls > 0).sum())
+    assert int(t2.debug_outputs()["pos_count"]) == int((w_cls > 0).sum()) and len(t2.debug_outputs()) == 21
 
 
 # ------------------------------------------------------------------ DetectionLayer
@@ -599,8 +600,9 @@ def test_frcnn_proposals_and_roi_pool(golden):
 
 # ------------------------------------------------------------------ device unmold
 def test_unmold_detections_on_device(golden):
-    """od_unmold_detections vs the reference-shaped host function (itself pinned by the reference's numpy code in
-    test_oracle_golden) on DetectionLayer outputs, plus zero-area / empty / full edge rows."""
+    """od_unmold_detections (batched) and the reference-shaped single-image wrapper over it vs the oracle's numpy
+    restatement (pinned by the reference's own numpy code in test_abi.test_oracle_unmold_golden) on synthetic
+    detections, plus zero-area / empty / full edge rows."""
     from objectdetection_b200.detection import unmold_detection, unmold_detections_batch
     rs = np.random.RandomState(31)
     B, M = 5, 100
@@ -618,7 +620,9 @@ def test_unmold_detections_on_device(golden):
     shapes = np.array([[480, 640, 3], [1024, 1024, 3], [375, 500, 3], [600, 600, 3], [720, 1280, 3]])
     boxes, cls, scores, counts = (host(x) for x in unmold_detections_batch(shapes, [1024, 1024, 3], cu(det), windows))
     for b in range(B):
-        wb, wc, ws = unmold_detection(shapes[b], [1024, 1024, 3], det[b], windows[b])
+        wb, wc, ws = oracle.unmold_detection(shapes[b], [1024, 1024, 3], det[b], windows[b])
+        sb, sc, ss = unmold_detection(shapes[b], [1024, 1024, 3], det[b], windows[b])     # single-image wrapper
+        assert np.array_equal(sb, wb) and np.array_equal(sc, wc) and np.array_equal(ss, ws)
         n = counts[b]
         assert n == wb.shape[0]
         assert np.array_equal(boxes[b, :n], wb) and np.array_equal(cls[b, :n], wc) and np.array_equal(scores[b, :n], ws)
