@@ -88,6 +88,7 @@ typedef enum {
 #endif
 
 int od_version(void);                       /* 10000*major + 100*minor + patch */
+const char* od_source_hash(void);           /* sha1 of the sources this library was compiled from (build.py) */
 const char* od_strerror(int status);
 const char* od_last_error_detail(void);     /* thread-local, never NULL */
 /* Kernels launched by this library in this process so far (statistics only; a relaxed atomic counter). */

@@ -81,6 +81,7 @@ class FrcnnParams(ctypes.Structure):
 _P = c_void_p
 SIGNATURES = {
     "od_version": (c_int, []),
+    "od_source_hash": (c_char_p, []),
     "od_strerror": (c_char_p, [c_int]),
     "od_last_error_detail": (c_char_p, []),
     "od_launch_count": (c_int64, []),
@@ -133,6 +134,13 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
+        # a library older than the sources next to it is refused (it would be tested / benchmarked in their place)
+        if os.path.isdir(os.path.join(_HERE, "csrc")) and not os.environ.get("ODHEAD_LIB"):
+            from .build import source_hash
+            have, want = L.od_source_hash().decode(), source_hash()
+            if have != want:
+                raise OdHeadError(-100, f"{LIB_PATH} is stale (built from sources {have[:12]}, tree has {want[:12]}): "
+                                        "run `python -m objectdetection_b200.build`")
         _lib = L
     return _lib
 

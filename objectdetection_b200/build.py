@@ -42,6 +42,28 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def source_hash() -> str:
+    """sha1 over the CUDA sources, their headers and the C ABI header (sorted by name). Compiled into the library
+    (``od_source_hash``) and compared by ``_lib.lib()``, so a stale .so is refused instead of silently tested."""
+    import hashlib
+    h = hashlib.sha1()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(INCLUDE, "odhead.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def needs_build() -> bool:
+    """True when libodhead.so is missing or was built from other sources than the tree holds (hash, not mtimes:
+    file times do not survive a snapshot copy to another box)."""
+    stamp = os.path.join(OBJ, "source_hash.txt")
+    if not os.path.exists(LIB) or not os.path.exists(stamp):
+        return True
+    return open(stamp).read().strip() != source_hash()
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -58,8 +80,8 @@ def build_variant(name: str, defines) -> str:
     objs = []
     for src in sources():
         obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
-        subprocess.run([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-c", src, "-o", obj], check=True,
-                       capture_output=True, text=True)
+        subprocess.run([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], f'-DOD_SOURCE_HASH="{source_hash()}"', "-I", INCLUDE,
+                        "-c", src, "-o", obj], check=True, capture_output=True, text=True)
         objs.append(obj)
     subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs, "-Xcompiler", "-fPIC",
                     "-Xlinker", "--no-undefined", "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True,
@@ -74,10 +96,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(INCLUDE, "odhead.h"))
     headers.append(os.path.abspath(__file__))
     jobs = []
+    digest = source_hash()
+    stamp = os.path.join(OBJ, "source_hash.txt")
+    old = open(stamp).read().strip() if os.path.exists(stamp) else ""
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        if force or _stale(obj, [src] + headers):
+        is_core = os.path.basename(src) == "core.cu"
+        if force or _stale(obj, [src] + headers) or (is_core and old != digest):
             cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+            if is_core:
+                cmd.insert(1, f'-DOD_SOURCE_HASH="{digest}"')
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append((src, cmd))
@@ -106,6 +134,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             print(r.stdout + r.stderr, file=sys.stderr)
             raise RuntimeError("link failed")
+    with open(stamp, "w") as f:
+        f.write(digest)
     return LIB
 
 

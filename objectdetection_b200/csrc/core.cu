@@ -67,6 +67,11 @@ int check_tensor(const DLTensor* t, const char* name, DType dt, int ndim, bool n
 
 extern "C" {
 
+#ifndef OD_SOURCE_HASH
+#define OD_SOURCE_HASH "unknown"
+#endif
+const char* od_source_hash(void) { return OD_SOURCE_HASH; }
+
 int od_version(void) { return 10000 * 0 + 100 * 1 + 0; }
 
 const char* od_strerror(int status) {

@@ -17,6 +17,9 @@
 //      16-byte store. No meta kernel, no per-call allocation.
 //   crop_pool_bins_kernel : FasterRCNN roi_pool = crop 14x14 fused with 2x2 max-pool, same scheme over pooled bins.
 #include "common.cuh"
+#include "tma.cuh"
+
+#include <stdlib.h>
 
 namespace od {
 
@@ -259,6 +262,310 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
   }
 }
 
+// ----------------------------------------------------------------------------- crop_rows_kernel
+// The TMA-staged, separable form of the same gather (D = 256, pool <= 16x16). One CTA per ROI:
+//
+//   plan      crop_and_resize samples a ROI on a separable grid: bin (y, x) blends feature rows top(y)/bot(y) and
+//             columns left(x)/right(x). With a non-negative step the rows are non-decreasing in y, so the DISTINCT rows
+//             the ROI needs, in first-use order, are ranked 0..nr-1 by a short serial scan (same for the columns, whose
+//             consecutive ranks are merged into runs of adjacent pixels). A 14x14 crop of an 8-pixel ROI needs 9 rows of
+//             9 pixels instead of 784 taps.
+//   producer  (last warp) streams rank k = 0..nr-1 into a shared-memory ring: one cp.async.bulk per (row, column run) -
+//             NHWC makes a run of pixels one contiguous block of len KiB - completion counted in bytes on the slot's
+//             `full` mbarrier; a slot is refilled once all consumer warps have arrived on its `empty` mbarrier. Bytes in
+//             flight are set by the ring size, not by registers or occupancy.
+//   consumers thread = (x group, channel quad). On first use of a row it blends left/right for each of its x bins straight
+//             from the ring (2 LDS.128 per bin) into registers and releases the slot; each output row is then one lerp
+//             between the two cached rows and one streaming 16-byte store. Every feature pixel is read once from L2 per
+//             ROI and each x-blend is computed once per (row, x) instead of once per bin.
+//   ROIs the plan cannot serve (flipped / NaN boxes) take a per-bin path with direct loads inside the same kernel.
+// Arithmetic per output value is the reference's (crop_and_resize_op.cc): top = tl + (tr - tl) * xl, bot likewise,
+// out = top + (bot - top) * yl, so the results are bit-identical to crop_bins_kernel and to the oracle.
+constexpr int kRowsMaxPool = 16;
+constexpr int kRowsMaxSlots = 16;
+constexpr int kRowsD4 = 64;                     // D = 256 floats = 64 quads = 1 KiB per pixel
+constexpr uint32_t kRowsPixelBytes = 1024;
+
+struct RowsPlan {
+  int32_t y_top[kRowsMaxPool], y_bot[kRowsMaxPool], y_rt[kRowsMaxPool], y_rb[kRowsMaxPool], y_ok[kRowsMaxPool];
+  float y_lerp[kRowsMaxPool];
+  int32_t x_left[kRowsMaxPool], x_right[kRowsMaxPool], x_cl[kRowsMaxPool], x_cr[kRowsMaxPool], x_ok[kRowsMaxPool];
+  float x_lerp[kRowsMaxPool];
+  int32_t rows[2 * kRowsMaxPool];               // feature row of row-rank k
+  int32_t run_col[kRowsMaxPool], run_rank[kRowsMaxPool], run_len[kRowsMaxPool];
+  int32_t nr, ncols, nruns, nslots, mode;       // mode: 0 ring, 1 per-bin path, 2 skip (box_ind out of range)
+  int32_t mono, W;
+  uint32_t slot_bytes;
+  const float* base;
+};
+constexpr int kRowsRing = 0, kRowsFlat = 1, kRowsSkip = 2;
+
+// geometry of one ROI (level assignment, image base, sampling grid); returns the kBin* flag
+__device__ __forceinline__ uintptr_t roi_geometry(const RoiSource& src, int64_t roi, int32_t ph, int32_t pw,
+                                                  RoiMeta& m, int32_t* level) {
+  float4 box;
+  uintptr_t flag = kBinSample;
+  constexpr int64_t D = 4 * kRowsD4;
+  if (src.mode == 0) {
+    box = __ldg(&src.boxes[roi]);
+    *level = roi_level_of(box, src.image_h, src.image_w, src.min_level, src.min_level + src.num_levels - 1);
+    const int32_t l = *level - src.min_level;
+    m.H = src.lt.H[l];
+    m.W = src.lt.W[l];
+    m.base = src.lt.ptr[l] + (roi / src.rois_per_image) * ((int64_t)m.H * m.W * D);
+  } else {
+    box = __ldg(&src.boxes[roi]);
+    const int32_t b = __ldg(&src.box_ind[roi]);
+    m.H = src.lt.H[0];
+    m.W = src.lt.W[0];
+    m.base = src.lt.ptr[0];
+    if (b >= 0 && b < src.batch) m.base += (int64_t)b * ((int64_t)m.H * m.W * D);
+    else flag = kBinSkip;
+  }
+  fill_grid(m, box, ph, pw);
+  return flag;
+}
+
+// ranks of the distinct values of a non-decreasing (lo[i] <= hi[i] <= lo[i+1]-ish) tap sequence, in first-use order
+__device__ __forceinline__ int32_t rank_scan(int32_t n, const int32_t* ok, const int32_t* lo, const int32_t* hi,
+                                             int32_t* r_lo, int32_t* r_hi, int32_t* vals) {
+  int32_t k = -1, a = -1, b = -1;               // a, b: values of ranks k-1, k
+  for (int32_t i = 0; i < n; ++i) {
+    if (!ok[i]) continue;
+    const int32_t t = lo[i], u = hi[i];
+    if (t == b) r_lo[i] = k;
+    else if (t == a) r_lo[i] = k - 1;
+    else { ++k; vals[k] = t; a = b; b = t; r_lo[i] = k; }
+    if (u == b) r_hi[i] = k;
+    else if (u == a) r_hi[i] = k - 1;
+    else { ++k; vals[k] = u; a = b; b = u; r_hi[i] = k; }
+  }
+  return k + 1;
+}
+
+template <int XPT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+crop_rows_kernel(RoiSource src, int32_t ph, int32_t pw, int32_t XG, uint32_t ring_bytes, float extrap,
+                 float4* __restrict__ out, int32_t* __restrict__ level_out) {
+  pdl_prologue();
+  extern __shared__ __align__(128) unsigned char s_ring[];
+  __shared__ RowsPlan P;
+  __shared__ int32_t s_cols[2 * kRowsMaxPool];
+  __shared__ __align__(8) unsigned long long s_full[kRowsMaxSlots], s_empty[kRowsMaxSlots];
+  const int32_t t = threadIdx.x;
+  const int32_t lane = t & 31;
+  const int32_t n_cons = kRowsD4 * XG;
+  const int64_t roi = blockIdx.x;
+
+  // ---- plan 1/3: per-y and per-x sampling entries (threads 0..ph-1 and 32..32+pw-1)
+  if (t < ph || (t >= 32 && t < 32 + pw)) {
+    RoiMeta m;
+    int32_t level = 0;
+    const uintptr_t flag = roi_geometry(src, roi, ph, pw, m, &level);
+    if (t == 0) {
+      P.base = m.base;
+      P.W = m.W;
+      P.mode = (flag == kBinSkip) ? kRowsSkip : kRowsRing;
+      P.mono = (m.hs >= 0.0f) && (m.ws >= 0.0f);
+      if (level_out && src.mode == 0) level_out[roi] = level;
+    }
+    if (t < ph) {
+      const float in_y = m.in_y0 + (float)t * m.hs;
+      const bool ok = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1));
+      const float fy = floorf(in_y);
+      P.y_ok[t] = ok;
+      P.y_top[t] = ok ? (int32_t)fy : 0;
+      P.y_bot[t] = ok ? (int32_t)ceilf(in_y) : 0;
+      P.y_lerp[t] = ok ? in_y - fy : 0.0f;
+    } else {
+      const int32_t x = t - 32;
+      const float in_x = m.in_x0 + (float)x * m.ws;
+      const bool ok = (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
+      const float fx = floorf(in_x);
+      P.x_ok[x] = ok;
+      P.x_left[x] = ok ? (int32_t)fx : 0;
+      P.x_right[x] = ok ? (int32_t)ceilf(in_x) : 0;
+      P.x_lerp[x] = ok ? in_x - fx : 0.0f;
+    }
+  }
+  __syncthreads();
+  // ---- plan 2/3: rank the distinct rows (thread 0) and columns (thread 32), merge adjacent columns into runs
+  if (t == 0) {
+    P.nr = rank_scan(ph, P.y_ok, P.y_top, P.y_bot, P.y_rt, P.y_rb, P.rows);
+  } else if (t == 32) {
+    const int32_t nc = rank_scan(pw, P.x_ok, P.x_left, P.x_right, P.x_cl, P.x_cr, s_cols);
+    int32_t nruns = 0;
+    for (int32_t k = 0; k < nc; ++k) {
+      if (k == 0 || s_cols[k] != s_cols[k - 1] + 1) {
+        P.run_col[nruns] = s_cols[k];
+        P.run_rank[nruns] = k;
+        P.run_len[nruns] = 1;
+        ++nruns;
+      } else {
+        ++P.run_len[nruns - 1];
+      }
+    }
+    P.ncols = nc;
+    P.nruns = nruns;
+  }
+  __syncthreads();
+  // ---- plan 3/3: ring geometry + barriers
+  if (t == 0) {
+    if (P.mode == kRowsRing) {
+      if (!P.mono) {
+        P.mode = kRowsFlat;
+      } else if (P.ncols == 0 || P.nr == 0) {   // no bin has a valid tap: everything is the extrapolation value
+        for (int32_t y = 0; y < ph; ++y) P.y_ok[y] = 0;
+        P.nr = 0;
+        P.nslots = 1;
+        P.slot_bytes = 0;
+      } else {
+        P.slot_bytes = (uint32_t)P.ncols * kRowsPixelBytes;
+        if (P.slot_bytes > ring_bytes) {
+          P.mode = kRowsFlat;
+        } else {
+          const uint32_t ns = ring_bytes / P.slot_bytes;
+          P.nslots = (int32_t)(ns < (uint32_t)kRowsMaxSlots ? ns : (uint32_t)kRowsMaxSlots);
+        }
+      }
+    }
+    if (P.mode == kRowsRing) {
+      for (int32_t s_ = 0; s_ < P.nslots; ++s_) {
+        mbar_init(&s_full[s_], 1);
+        mbar_init(&s_empty[s_], (uint32_t)(n_cons >> 5));
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  const int32_t mode = P.mode;
+  if (mode == kRowsSkip) return;
+  const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
+  float4* __restrict__ o = out + roi * ((int64_t)ph * pw * kRowsD4);
+
+  if (mode == kRowsFlat) {   // per-bin path: 4 direct loads per output quad (flipped / NaN / oversized ROIs)
+    const float4* __restrict__ base = reinterpret_cast<const float4*>(P.base);
+    const uint32_t W = (uint32_t)P.W;
+    const int32_t total = ph * pw * kRowsD4;
+    for (int32_t e = t; e < total; e += (int32_t)blockDim.x) {
+      const int32_t bin = e >> 6;
+      const uint32_t c = (uint32_t)(e & 63);
+      const int32_t y = bin / pw, x = bin - y * pw;
+      float4 v = ext4;
+      if (P.y_ok[y] && P.x_ok[x]) {
+        const uint32_t top = (uint32_t)P.y_top[y], bot = (uint32_t)P.y_bot[y];
+        const uint32_t left = (uint32_t)P.x_left[x], right = (uint32_t)P.x_right[x];
+        const float4 tl = ldg_f4(base + ((top * W + left) * kRowsD4 + c));
+        const float4 tr = ldg_f4(base + ((top * W + right) * kRowsD4 + c));
+        const float4 bl = ldg_f4(base + ((bot * W + left) * kRowsD4 + c));
+        const float4 br = ldg_f4(base + ((bot * W + right) * kRowsD4 + c));
+        const float xl = P.x_lerp[x];
+        v = lerp4p(lerp4p(tl, tr, xl), lerp4p(bl, br, xl), P.y_lerp[y]);
+      }
+      stg_cs_f4(o + e, v);
+    }
+    return;
+  }
+
+  const int32_t nslots = P.nslots;
+  const uint32_t slot_bytes = P.slot_bytes;
+  if (t >= n_cons) {
+    // ---- producer warp: stream the needed rows, in rank order, through the ring
+    const int32_t nr = P.nr, nruns = P.nruns;
+    const char* __restrict__ gbase = reinterpret_cast<const char*>(P.base);
+    const size_t row_pitch = (size_t)P.W * kRowsPixelBytes;
+    int32_t slot = 0;
+    uint32_t phase = 0;
+    for (int32_t k = 0; k < nr; ++k) {
+      mbar_wait(&s_empty[slot], phase ^ 1u);           // all consumer warps are done with the previous tenant
+      if (lane == 0) mbar_expect_tx(&s_full[slot], slot_bytes);
+      __syncwarp();
+      const char* srow = gbase + (size_t)P.rows[k] * row_pitch;
+      unsigned char* dst = s_ring + (size_t)slot * slot_bytes;
+      for (int32_t j = lane; j < nruns; j += 32)
+        bulk_g2s(dst + (size_t)P.run_rank[j] * kRowsPixelBytes, srow + (size_t)P.run_col[j] * kRowsPixelBytes,
+                 (uint32_t)P.run_len[j] * kRowsPixelBytes, &s_full[slot]);
+      if (++slot == nslots) {
+        slot = 0;
+        phase ^= 1u;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int32_t q = t & 63, xg = t >> 6;
+  int32_t xcl[XPT], xcr[XPT];
+  float xl[XPT];
+  bool xok[XPT], xin[XPT];
+#pragma unroll
+  for (int i = 0; i < XPT; ++i) {
+    const int32_t x = xg + XG * i;
+    xin[i] = x < pw;
+    xok[i] = xin[i] && P.x_ok[x];
+    xcl[i] = xok[i] ? P.x_cl[x] * kRowsD4 + q : q;
+    xcr[i] = xok[i] ? P.x_cr[x] * kRowsD4 + q : q;
+    xl[i] = xok[i] ? P.x_lerp[x] : 0.0f;
+  }
+  float4 va[XPT], vb[XPT];
+#pragma unroll
+  for (int i = 0; i < XPT; ++i) va[i] = vb[i] = ext4;
+  int32_t ra = -1, rb = -1;
+  int32_t slot = 0;
+  uint32_t phase = 0;
+  // blend the next row of the ring (ranks arrive in order) for this thread's x bins, then release its slot
+#define OD_ROWS_LOAD(V)                                                                              \
+  do {                                                                                               \
+    mbar_wait(&s_full[slot], phase);                                                                 \
+    const float4* rowp = reinterpret_cast<const float4*>(s_ring + (size_t)slot * slot_bytes);        \
+    _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                \
+      if (xok[i]) V[i] = lerp4p(rowp[xcl[i]], rowp[xcr[i]], xl[i]);                                  \
+    }                                                                                                \
+    __syncwarp();                                                                                    \
+    if (lane == 0) mbar_arrive(&s_empty[slot]);                                                      \
+    if (++slot == nslots) {                                                                          \
+      slot = 0;                                                                                      \
+      phase ^= 1u;                                                                                   \
+    }                                                                                                \
+  } while (0)
+
+  for (int32_t y = 0; y < ph; ++y) {
+    const bool yok = P.y_ok[y] != 0;
+    bool same = true;
+    float yl = 0.0f;
+    if (yok) {
+      const int32_t kt = P.y_rt[y], kb = P.y_rb[y];
+      yl = P.y_lerp[y];
+      if (kt != ra) {
+        if (kt == rb) {
+#pragma unroll
+          for (int i = 0; i < XPT; ++i) va[i] = vb[i];
+          rb = -1;
+        } else {
+          OD_ROWS_LOAD(va);
+        }
+        ra = kt;
+      }
+      same = (kb == kt);
+      if (!same && kb != rb) {
+        OD_ROWS_LOAD(vb);
+        rb = kb;
+      }
+    }
+    float4* __restrict__ orow = o + (int64_t)y * pw * kRowsD4 + q;
+#pragma unroll
+    for (int i = 0; i < XPT; ++i) {
+      if (xin[i]) {
+        float4 v = ext4;
+        if (yok && xok[i]) v = lerp4p(va[i], same ? va[i] : vb[i], yl);
+        stg_cs_f4(orow + (xg + XG * i) * kRowsD4, v);
+      }
+    }
+  }
+#undef OD_ROWS_LOAD
+}
+
 // FasterRCNN roi_pool (fastrcnn.py:22-70): crop_and_resize to (2*oh) x (2*ow) fused with max_pool 2x2 / stride 2.
 // Same flat-bin scheme as crop_bins_kernel over the POOLED bins: a CTA owns kPoolBins pooled bins, its table has 4
 // entries (the 2x2 sub-bins) per pooled bin; per output quad a thread issues the 16 unconditional 16-byte loads of the
@@ -316,6 +623,64 @@ crop_pool_bins_kernel(RoiSource src, int64_t total_bins, int32_t oh, int32_t ow,
 }
 
 // ----------------------------------------------------------------------------- host side
+// Tunables of the TMA-staged kernel, read once from the environment (A/B runs on one box without rebuilding):
+//   OD_ROI_KERNEL=flat  forces crop_bins_kernel;  OD_ROI_RING_KB  shared-memory ring per CTA (default 64);
+//   OD_ROI_XPT = 1 | 2 | 4  x bins per consumer thread (default 2).
+struct RowsTuning {
+  bool use_rows;
+  uint32_t ring_bytes;
+  int xpt;
+};
+static const RowsTuning& rows_tuning() {
+  static const RowsTuning t = [] {
+    RowsTuning r;
+    const char* k = getenv("OD_ROI_KERNEL");
+    r.use_rows = !(k && strcmp(k, "flat") == 0);
+    const char* kb = getenv("OD_ROI_RING_KB");
+    int kbv = kb ? atoi(kb) : 64;
+    if (kbv < 32) kbv = 32;
+    if (kbv > 200) kbv = 200;
+    r.ring_bytes = (uint32_t)kbv * 1024u;
+    const char* x = getenv("OD_ROI_XPT");
+    const int xv = x ? atoi(x) : 2;
+    r.xpt = (xv == 1 || xv == 4) ? xv : 2;
+    return r;
+  }();
+  return t;
+}
+
+template <int XPT, int MAXT, int MINB>
+static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t XG, uint32_t ring,
+                              float extrap, float* out, int32_t* level_out, cudaStream_t st) {
+  auto kern = crop_rows_kernel<XPT, MAXT, MINB>;
+  static uint32_t configured[64] = {0};    // dynamic shared memory opted in, per device
+  int dev = 0;
+  OD_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && configured[dev] < ring) {
+    OD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+    configured[dev] = ring;
+  }
+  OD_CUDA(launch_pdl(kern, dim3((unsigned)n_rois), dim3((unsigned)(kRowsD4 * XG + 32)), (size_t)ring, st, src, ph, pw, XG,
+                     ring, extrap, reinterpret_cast<float4*>(out), level_out));
+  OD_LAUNCH_CHECK("crop_rows_kernel");
+  return OD_OK;
+}
+
+// returns OD_OK after launching, or 1 when the shape is not served by this kernel (caller falls back to crop_bins)
+static int launch_crop_rows(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap, float* out,
+                            int32_t* level_out, cudaStream_t st) {
+  const RowsTuning& tn = rows_tuning();
+  if (!tn.use_rows || D != 4 * kRowsD4 || ph > kRowsMaxPool || pw > kRowsMaxPool || src.mode > 1 || n_rois > 0x7FFFFFFFll)
+    return 1;
+  int xpt = tn.xpt;
+  if (xpt == 1 && pw > 7) xpt = 2;
+  if (xpt == 2 && pw > 14) xpt = 4;
+  const int32_t XG = (pw + xpt - 1) / xpt;      // consumer threads = 64 * XG (+ one producer warp)
+  if (xpt == 1) return launch_crop_rows_t<1, 480, 2>(src, n_rois, ph, pw, XG, tn.ring_bytes, extrap, out, level_out, st);
+  if (xpt == 2) return launch_crop_rows_t<2, 480, 2>(src, n_rois, ph, pw, XG, tn.ring_bytes, extrap, out, level_out, st);
+  return launch_crop_rows_t<4, 288, 2>(src, n_rois, ph, pw, XG, tn.ring_bytes, extrap, out, level_out, st);
+}
+
 static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
                             float* out, int32_t* level_out, cudaStream_t st) {
   if (n_rois == 0) return OD_OK;
@@ -326,6 +691,10 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
   for (int l = 0; l < (src.mode == 0 ? src.num_levels : 1); ++l)
     if ((int64_t)src.lt.H[l] * src.lt.W[l] * D4 > 0xFFFFFFFFll)
       OD_FAIL(OD_ERR_PARAM, "one image of level %d exceeds 2^32 16-byte units", l);
+  {
+    const int rc = launch_crop_rows(src, n_rois, ph, pw, D, extrap, out, level_out, st);
+    if (rc != 1) return rc;
+  }
   int32_t lg = -1;
   if ((D4 & (D4 - 1)) == 0) {
     lg = 0;

@@ -13,11 +13,12 @@ def pytest_configure(config):
 
 
 def pytest_sessionstart(session):
-    """Safety net: if the in-tree CUDA library is missing (fresh checkout) and nvcc is around, build it once. The
-    package itself never builds or falls back: a missing library raises at the first call."""
+    """Bring the in-tree CUDA library up to date with the sources when nvcc is around (decided by the source hash the
+    library was built from, so a stale .so is rebuilt and an up-to-date one is left alone). The package itself never builds or falls back: a missing or stale library (source
+    hash mismatch, _lib.lib()) raises at the first call."""
     try:
-        from objectdetection_b200 import _lib, build
-        if not os.path.exists(_lib.LIB_PATH):
+        from objectdetection_b200 import build
+        if build.needs_build():
             build.build()
     except Exception as e:   # the tests that need the library will report the real error
         print(f"[conftest] libodhead.so not built: {e}")

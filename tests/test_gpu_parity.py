@@ -369,6 +369,48 @@ def test_roi_pooling_realistic_rois_and_degenerates():
     assert set(np.unique(lv)) == {2, 3, 4, 5}
 
 
+@pytest.mark.parametrize("pool", [[7, 7], [14, 14], [1, 1], [3, 5], [16, 16], [5, 14], [14, 2]])
+def test_roi_pooling_d256_rows_kernel_edge_cases(pool):
+    """D = 256 goes through the TMA-staged separable kernel (crop_rows_kernel): up-sampled, down-sampled, thin, flipped,
+    NaN, zero-area, out-of-image and whole-image ROIs on a small pyramid, every pooled value bit-identical."""
+    rs = np.random.RandomState(4321 + pool[0])
+    fmaps = [rs.random_sample((2, s, s, 256)).astype(f32) for s in (64, 32, 16, 8)]
+    props = _synth.rois_log_uniform(rs, 2, 160, lo=4, hi=900)
+    props[1, 150:] = 0                                                        # zero padded proposals -> level 2
+    props[0, 0] = [0, 0, 1, 1]                                                # last tap exactly on the far edge
+    props[0, 1] = [0.3, 0.3, 0.3, 0.3]                                        # zero area: every bin on one pixel
+    props[0, 2] = [0.25, 0.5, 1.0, 1.0]
+    props[0, 3] = [-0.1, -0.2, 0.4, 0.5]                                      # partly outside -> extrapolated bins
+    props[0, 4] = [0.5, 0.5, 1.2, 1.3]
+    props[0, 5] = [0.9, 0.1, 0.2, 0.8]                                        # flipped in y -> per-bin path
+    props[0, 6] = [0.1, 0.9, 0.8, 0.2]                                        # flipped in x
+    props[0, 7] = [np.nan, 0.1, 0.5, 0.6]
+    props[0, 8] = [0.0, 0.40, 1.0, 0.41]                                      # tall and thin: sparse rows, one column pair
+    props[0, 9] = [0.40, 0.0, 0.41, 1.0]                                      # wide and flat: many column runs
+    props[0, 10] = [1.5, 1.5, 2.0, 2.0]                                       # entirely outside
+    props[0, 11] = [0.5, 0.5, 0.5 + 1e-4, 0.5 + 1e-4]                         # sub-pixel ROI
+    props[0, 12] = [0.2, 0.2, 0.2 + 3 / 63.0, 0.2 + 3 / 63.0]                 # integer-aligned taps on P2 (lerp 0)
+    _roi_align_check(fmaps, props, 1024, pool)
+
+
+def test_crop_and_resize_d256_rows_kernel():
+    """tf.image.crop_and_resize entry (explicit box_ind, extrapolation value, skipped crops) on the D = 256 path."""
+    from objectdetection_b200.maskrcnn import crop_and_resize
+    rs = np.random.RandomState(12)
+    img = rs.random_sample((3, 19, 23, 256)).astype(f32)
+    boxes = np.concatenate([np.array([[0, 0, 1, 1], [0.1, 0.2, 0.7, 0.9], [0.3, 0.3, 0.3, 0.3], [-0.2, -0.1, 0.5, 0.5],
+                                      [0.5, 0.5, 1.3, 1.2], [0.9, 0.8, 0.1, 0.2], [0, 0, 0, 0], [0.25, 0.5, 0.75, 1.0]], f32),
+                            _synth.random_boxes(rs, 24, flip=True)])
+    bi = rs.randint(0, 3, boxes.shape[0]).astype(np.int32)
+    bi[7], bi[9] = 5, -1                                                      # out of range: crop left untouched
+    for crop in ((7, 7), (14, 14), (1, 1), (1, 3), (16, 9)):
+        out0 = np.full((boxes.shape[0], crop[0], crop[1], 256), -7.0, f32)
+        got = host(crop_and_resize(cu(img), cu(boxes), cu(bi), crop, extrapolation_value=0.5, out=cu(out0)))
+        want = oracle.crop_and_resize(img, boxes, bi, crop[0], crop[1], extrapolation=0.5, out=out0.copy())
+        assert_bits(got, want, f"crop {crop}")
+        assert (got[7] == -7.0).all() and (got[9] == -7.0).all()
+
+
 def test_roi_align_properties_full_size():
     """Size-independent properties at the BASELINE size (2 x 1000 ROIs x 7x7 x 256): linearity in the feature maps
     and exactness on a constant pyramid."""

@@ -1,0 +1,15 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_goldens.py -m gpu -x -q -k "roi or crop" 2>&1 | tail -15
+for cfg in "flat 64 2" "rows 64 2" "rows 64 4" "rows 96 2" "rows 48 4" "rows 64 1"; do
+  set -- $cfg
+  echo "=== kernel=$1 ring=$2 xpt=$3"
+  OD_ROI_KERNEL=$1 OD_ROI_RING_KB=$2 OD_ROI_XPT=$3 timeout 300 python bench.py --steps 200 --warmup 5 --no-cpu-baseline 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); r=d['roofline']; s=d['roialign_standalone']
+        print('step_ms', round(d['ms_per_step'],4), 'p14_pipeline_ms', round(r['ms_per_launch'],4), 'frac', round(r['frac'],3), 'sa7', round(s['p7']['ms'],4), round(s['p7']['frac'],3), 'sa14', round(s['p14']['ms'],4), round(s['p14']['frac'],3))
+    else: print(l[:300])
+"
+done
