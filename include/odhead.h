@@ -202,6 +202,15 @@ int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_level
                                  const DLTensor* rois, int32_t image_h, int32_t image_w,
                                  int32_t pool_h, int32_t pool_w,
                                  DLTensor* pooled, DLTensor* roi_level, void* stream);
+/* The same call with a small PERSISTENT workspace (od_pyramid_roi_align_workspace_bytes() bytes, 8-byte aligned, device
+ * memory of the tensors' GPU) that lets the persistent CTAs of the D = 256 kernel draw ROIs dynamically instead of in a
+ * fixed round robin. The caller zero-initialises it ONCE (e.g. cudaMemset after allocating it); every launch leaves it
+ * zeroed again. One workspace must not be used by two launches that can run concurrently (one per stream is safe). */
+size_t od_pyramid_roi_align_workspace_bytes(void);
+int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
+                                    const DLTensor* rois, int32_t image_h, int32_t image_w,
+                                    int32_t pool_h, int32_t pool_w,
+                                    DLTensor* pooled, DLTensor* roi_level, void* ws, size_t ws_bytes, void* stream);
 
 /* tf.image.crop_and_resize(method="bilinear"): image [B,H,W,D] f32 NHWC,
  * boxes [n,4] f32, box_ind [n] i32 (out-of-range -> that crop is left untouched),

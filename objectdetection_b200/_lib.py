@@ -105,6 +105,9 @@ SIGNATURES = {
     "od_mrcnn_loss_forward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "od_pyramid_roi_align_forward": (c_int, [POINTER(_P), c_int32, c_int32, _P, c_int32, c_int32, c_int32, c_int32,
                                              _P, _P, _P]),
+    "od_pyramid_roi_align_workspace_bytes": (c_size_t, []),
+    "od_pyramid_roi_align_forward_ws": (c_int, [POINTER(_P), c_int32, c_int32, _P, c_int32, c_int32, c_int32, c_int32,
+                                                _P, _P, _P, c_size_t, _P]),
     "od_crop_and_resize": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, _P, _P]),
     "od_detection_target_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "od_detection_target_forward": (c_int, [_P, _P, _P, _P, _P, POINTER(TargetParams), _P, _P, _P, _P, _P,
@@ -213,6 +216,23 @@ def workspace(nbytes: int, device) -> torch.Tensor:
             _retired.append(buf)
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
+    return buf
+
+
+_zero_ws = {}
+
+
+def zeroed_workspace(nbytes: int, device) -> torch.Tensor:
+    """A small per-(device, stream) buffer that is zero-initialised once and that the kernels using it leave zeroed
+    (od_pyramid_roi_align_forward_ws: the ROI ticket counter). Never freed; allocated outside graph capture."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _zero_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise OdHeadError(-6, "the ROIAlign ticket workspace would have to be allocated during CUDA graph capture: "
+                                  "run the call once eagerly on the capture stream first")
+        buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _zero_ws[key] = buf
     return buf
 
 

@@ -263,42 +263,60 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
 }
 
 // ----------------------------------------------------------------------------- crop_rows_kernel
-// The TMA-staged, separable form of the same gather (D = 256, pool <= 16x16). One CTA per ROI:
+// The TMA-staged, separable form of the same gather (D = 256, pool <= 16x16). Persistent CTAs (a few per SM), each
+// walking ROIs blockIdx.x, blockIdx.x + gridDim.x, ... with three kinds of warps that only meet through mbarriers:
 //
-//   plan      crop_and_resize samples a ROI on a separable grid: bin (y, x) blends feature rows top(y)/bot(y) and
-//             columns left(x)/right(x). With a non-negative step the rows are non-decreasing in y, so the DISTINCT rows
-//             the ROI needs, in first-use order, are ranked 0..nr-1 by a short serial scan (same for the columns, whose
+//   planner   (1 warp) turns ROI geometry into a PLAN, a few ROIs ahead of everybody else (ring of kRowsPlans plans):
+//             crop_and_resize samples a ROI on a separable grid - bin (y, x) blends feature rows top(y)/bot(y) and columns
+//             left(x)/right(x). With a non-negative step the rows are non-decreasing in y, so the DISTINCT rows the ROI
+//             needs, in first-use order, are ranked 0..nr-1 by a short serial scan (same for the columns, whose
 //             consecutive ranks are merged into runs of adjacent pixels). A 14x14 crop of an 8-pixel ROI needs 9 rows of
 //             9 pixels instead of 784 taps.
-//   producer  (last warp) streams rank k = 0..nr-1 into a shared-memory ring: one cp.async.bulk per (row, column run) -
-//             NHWC makes a run of pixels one contiguous block of len KiB - completion counted in bytes on the slot's
-//             `full` mbarrier; a slot is refilled once all consumer warps have arrived on its `empty` mbarrier. Bytes in
-//             flight are set by the ring size, not by registers or occupancy.
+//   issuer    (1 warp) streams the ranked rows of ROI after ROI into one shared-memory BYTE ring: one cp.async.bulk per
+//             (row, column run) - NHWC makes a run of pixels one contiguous block of len KiB - completion counted in bytes
+//             on the entry's `full` mbarrier; space is reclaimed in FIFO order as all consumer warps arrive on an entry's
+//             `empty` mbarrier. The ring never drains between ROIs; bytes in flight are set by the ring size, not by
+//             registers or occupancy.
 //   consumers thread = (x group, channel quad). On first use of a row it blends left/right for each of its x bins straight
-//             from the ring (2 LDS.128 per bin) into registers and releases the slot; each output row is then one lerp
+//             from the ring (2 LDS.128 per bin) into registers and releases the entry; each output row is then one lerp
 //             between the two cached rows and one streaming 16-byte store. Every feature pixel is read once from L2 per
 //             ROI and each x-blend is computed once per (row, x) instead of once per bin.
-//   ROIs the plan cannot serve (flipped / NaN boxes) take a per-bin path with direct loads inside the same kernel.
+//   ROIs the plan cannot serve (flipped / NaN boxes) take a per-bin path with direct loads on the consumer warps.
 // Arithmetic per output value is the reference's (crop_and_resize_op.cc): top = tl + (tr - tl) * xl, bot likewise,
 // out = top + (bot - top) * yl, so the results are bit-identical to crop_bins_kernel and to the oracle.
 constexpr int kRowsMaxPool = 16;
-constexpr int kRowsMaxSlots = 16;
+constexpr int kRowsEntries = 16;                // outstanding ring entries (one feature row each)
+constexpr int kRowsPlans = 3;                   // plans in flight
 constexpr int kRowsD4 = 64;                     // D = 256 floats = 64 quads = 1 KiB per pixel
 constexpr uint32_t kRowsPixelBytes = 1024;
 
 struct RowsPlan {
-  int32_t y_top[kRowsMaxPool], y_bot[kRowsMaxPool], y_rt[kRowsMaxPool], y_rb[kRowsMaxPool], y_ok[kRowsMaxPool];
+  int4 ytab[kRowsMaxPool];                      // ring mode: {rank of top row, rank of bottom row, y_lerp bits, 0}
+  int32_t y_top[kRowsMaxPool], y_bot[kRowsMaxPool], y_ok[kRowsMaxPool];
   float y_lerp[kRowsMaxPool];
   int32_t x_left[kRowsMaxPool], x_right[kRowsMaxPool], x_cl[kRowsMaxPool], x_cr[kRowsMaxPool], x_ok[kRowsMaxPool];
   float x_lerp[kRowsMaxPool];
   int32_t rows[2 * kRowsMaxPool];               // feature row of row-rank k
   int32_t run_col[kRowsMaxPool], run_rank[kRowsMaxPool], run_len[kRowsMaxPool];
-  int32_t nr, ncols, nruns, nslots, mode;       // mode: 0 ring, 1 per-bin path, 2 skip (box_ind out of range)
+  int32_t nr, ncols, nruns, mode;
   int32_t mono, W;
-  uint32_t slot_bytes;
+  uint32_t row_bytes;                           // ncols KiB: one ring entry
+  int64_t roi;
   const float* base;
 };
-constexpr int kRowsRing = 0, kRowsFlat = 1, kRowsSkip = 2;
+// ring: every bin of the ROI has four valid taps and the grid steps are non-negative (the streaming fast path);
+// flat: anything else (extrapolated bins, flipped / NaN boxes, rows wider than the ring) - per-bin direct loads;
+// skip: box_ind out of range, the crop is left untouched; done: no ROI left for this CTA.
+constexpr int kRowsRing = 0, kRowsFlat = 1, kRowsSkip = 2, kRowsDone = 3;
+
+struct RowsShared {
+  RowsPlan plan[kRowsPlans];
+  int32_t cols[2 * kRowsMaxPool];               // planner scratch
+  int32_t yrt[kRowsMaxPool], yrb[kRowsMaxPool]; // planner scratch
+  uint32_t entry_off[kRowsEntries];             // byte offset of an entry's row in the ring (issuer -> consumers)
+  uint32_t entry_fp[kRowsEntries];              // ring bytes an entry occupies incl. wrap padding (issuer only)
+  unsigned long long full[kRowsEntries], empty[kRowsEntries], plan_full[kRowsPlans], plan_empty[kRowsPlans];
+};
 
 // geometry of one ROI (level assignment, image base, sampling grid); returns the kBin* flag
 __device__ __forceinline__ uintptr_t roi_geometry(const RoiSource& src, int64_t roi, int32_t ph, int32_t pw,
@@ -326,12 +344,11 @@ __device__ __forceinline__ uintptr_t roi_geometry(const RoiSource& src, int64_t 
   return flag;
 }
 
-// ranks of the distinct values of a non-decreasing (lo[i] <= hi[i] <= lo[i+1]-ish) tap sequence, in first-use order
-__device__ __forceinline__ int32_t rank_scan(int32_t n, const int32_t* ok, const int32_t* lo, const int32_t* hi,
-                                             int32_t* r_lo, int32_t* r_hi, int32_t* vals) {
+// ranks of the distinct values of a non-decreasing tap sequence (lo[i] <= hi[i], lo[i] <= lo[i+1]), in first-use order
+__device__ __forceinline__ int32_t rank_scan(int32_t n, const int32_t* lo, const int32_t* hi, int32_t* r_lo, int32_t* r_hi,
+                                             int32_t* vals) {
   int32_t k = -1, a = -1, b = -1;               // a, b: values of ranks k-1, k
   for (int32_t i = 0; i < n; ++i) {
-    if (!ok[i]) continue;
     const int32_t t = lo[i], u = hi[i];
     if (t == b) r_lo[i] = k;
     else if (t == a) r_lo[i] = k - 1;
@@ -343,61 +360,58 @@ __device__ __forceinline__ int32_t rank_scan(int32_t n, const int32_t* ok, const
   return k + 1;
 }
 
-template <int XPT, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-crop_rows_kernel(RoiSource src, int32_t ph, int32_t pw, int32_t XG, uint32_t ring_bytes, float extrap,
-                 float4* __restrict__ out, int32_t* __restrict__ level_out) {
-  pdl_prologue();
-  extern __shared__ __align__(128) unsigned char s_ring[];
-  __shared__ RowsPlan P;
-  __shared__ int32_t s_cols[2 * kRowsMaxPool];
-  __shared__ __align__(8) unsigned long long s_full[kRowsMaxSlots], s_empty[kRowsMaxSlots];
-  const int32_t t = threadIdx.x;
-  const int32_t lane = t & 31;
-  const int32_t n_cons = kRowsD4 * XG;
-  const int64_t roi = blockIdx.x;
-
-  // ---- plan 1/3: per-y and per-x sampling entries (threads 0..ph-1 and 32..32+pw-1)
-  if (t < ph || (t >= 32 && t < 32 + pw)) {
+// one warp builds the plan of one ROI
+__device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi, int32_t ph, int32_t pw, uint32_t ring_bytes,
+                                               int32_t lane, RowsPlan& P, RowsShared& S, int32_t* level_out) {
+  bool ok = true;
+  {
     RoiMeta m;
     int32_t level = 0;
     const uintptr_t flag = roi_geometry(src, roi, ph, pw, m, &level);
-    if (t == 0) {
+    if (lane == 0) {
+      P.roi = roi;
       P.base = m.base;
       P.W = m.W;
       P.mode = (flag == kBinSkip) ? kRowsSkip : kRowsRing;
       P.mono = (m.hs >= 0.0f) && (m.ws >= 0.0f);
       if (level_out && src.mode == 0) level_out[roi] = level;
     }
-    if (t < ph) {
-      const float in_y = m.in_y0 + (float)t * m.hs;
-      const bool ok = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1));
-      const float fy = floorf(in_y);
-      P.y_ok[t] = ok;
-      P.y_top[t] = ok ? (int32_t)fy : 0;
-      P.y_bot[t] = ok ? (int32_t)ceilf(in_y) : 0;
-      P.y_lerp[t] = ok ? in_y - fy : 0.0f;
+    if (lane < 16) {
+      if (lane < ph) {
+        const float in_y = m.in_y0 + (float)lane * m.hs;
+        ok = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1));
+        const float fy = floorf(in_y);
+        P.y_ok[lane] = ok;
+        P.y_top[lane] = ok ? (int32_t)fy : 0;
+        P.y_bot[lane] = ok ? (int32_t)ceilf(in_y) : 0;
+        P.y_lerp[lane] = ok ? in_y - fy : 0.0f;
+      }
     } else {
-      const int32_t x = t - 32;
-      const float in_x = m.in_x0 + (float)x * m.ws;
-      const bool ok = (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
-      const float fx = floorf(in_x);
-      P.x_ok[x] = ok;
-      P.x_left[x] = ok ? (int32_t)fx : 0;
-      P.x_right[x] = ok ? (int32_t)ceilf(in_x) : 0;
-      P.x_lerp[x] = ok ? in_x - fx : 0.0f;
+      const int32_t x = lane - 16;
+      if (x < pw) {
+        const float in_x = m.in_x0 + (float)x * m.ws;
+        ok = (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
+        const float fx = floorf(in_x);
+        P.x_ok[x] = ok;
+        P.x_left[x] = ok ? (int32_t)fx : 0;
+        P.x_right[x] = ok ? (int32_t)ceilf(in_x) : 0;
+        P.x_lerp[x] = ok ? in_x - fx : 0.0f;
+      }
     }
   }
-  __syncthreads();
-  // ---- plan 2/3: rank the distinct rows (thread 0) and columns (thread 32), merge adjacent columns into runs
-  if (t == 0) {
-    P.nr = rank_scan(ph, P.y_ok, P.y_top, P.y_bot, P.y_rt, P.y_rb, P.rows);
-  } else if (t == 32) {
-    const int32_t nc = rank_scan(pw, P.x_ok, P.x_left, P.x_right, P.x_cl, P.x_cr, s_cols);
+  const bool all_ok = __all_sync(0xffffffffu, ok);    // every bin has four valid taps (also orders the writes above)
+  if (lane == 0 && P.mode == kRowsRing && !(all_ok && P.mono)) P.mode = kRowsFlat;
+  __syncwarp();
+  if (P.mode != kRowsRing) return;
+  if (lane == 0) {
+    P.nr = rank_scan(ph, P.y_top, P.y_bot, S.yrt, S.yrb, P.rows);
+    for (int32_t y = 0; y < ph; ++y) P.ytab[y] = make_int4(S.yrt[y], S.yrb[y], __float_as_int(P.y_lerp[y]), 0);
+  } else if (lane == 16) {
+    const int32_t nc = rank_scan(pw, P.x_left, P.x_right, P.x_cl, P.x_cr, S.cols);
     int32_t nruns = 0;
     for (int32_t k = 0; k < nc; ++k) {
-      if (k == 0 || s_cols[k] != s_cols[k - 1] + 1) {
-        P.run_col[nruns] = s_cols[k];
+      if (k == 0 || S.cols[k] != S.cols[k - 1] + 1) {
+        P.run_col[nruns] = S.cols[k];
         P.run_rank[nruns] = k;
         P.run_len[nruns] = 1;
         ++nruns;
@@ -407,163 +421,264 @@ crop_rows_kernel(RoiSource src, int32_t ph, int32_t pw, int32_t XG, uint32_t rin
     }
     P.ncols = nc;
     P.nruns = nruns;
+    P.row_bytes = (uint32_t)nc * kRowsPixelBytes;
+    if (P.row_bytes > ring_bytes) P.mode = kRowsFlat;
+  }
+  __syncwarp();
+}
+
+// counter[0]: next ROI ticket, counter[1]: CTAs that have drawn their last ticket. Both are zero between launches: the
+// last CTA to finish resets them (the workspace is zero-initialised once by its owner).
+template <int XPT, bool FULL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t XG, uint32_t ring_bytes, float extrap,
+                 float4* __restrict__ out, int32_t* __restrict__ level_out, unsigned int* __restrict__ counter,
+                 int32_t l2_prefetch, int32_t dbg) {
+  pdl_prologue();
+  extern __shared__ __align__(128) unsigned char s_ring[];
+  __shared__ RowsShared S;
+  const int32_t t = threadIdx.x;
+  const int32_t lane = t & 31, warp = t >> 5;
+  const int32_t n_cwarps = 2 * XG, n_cons = kRowsD4 * XG;
+  if (t == 0) {
+    for (int32_t e = 0; e < kRowsEntries; ++e) {
+      mbar_init(&S.full[e], 1);
+      mbar_init(&S.empty[e], (uint32_t)n_cwarps);
+    }
+    for (int32_t p = 0; p < kRowsPlans; ++p) {
+      mbar_init(&S.plan_full[p], 1);
+      mbar_init(&S.plan_empty[p], (uint32_t)n_cwarps + 1u);    // consumer warps + the issuer
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  // ---- plan 3/3: ring geometry + barriers
-  if (t == 0) {
-    if (P.mode == kRowsRing) {
-      if (!P.mono) {
-        P.mode = kRowsFlat;
-      } else if (P.ncols == 0 || P.nr == 0) {   // no bin has a valid tap: everything is the extrapolation value
-        for (int32_t y = 0; y < ph; ++y) P.y_ok[y] = 0;
-        P.nr = 0;
-        P.nslots = 1;
-        P.slot_bytes = 0;
-      } else {
-        P.slot_bytes = (uint32_t)P.ncols * kRowsPixelBytes;
-        if (P.slot_bytes > ring_bytes) {
-          P.mode = kRowsFlat;
-        } else {
-          const uint32_t ns = ring_bytes / P.slot_bytes;
-          P.nslots = (int32_t)(ns < (uint32_t)kRowsMaxSlots ? ns : (uint32_t)kRowsMaxSlots);
+  int32_t ps = 0;                                // plan slot + phase, advanced identically by every role
+  uint32_t pphase = 0;
+
+  if (warp == n_cwarps + 1) {
+    // ------------------------------------------------------------------ planner: draws ROIs, plans a few ahead
+    int64_t next_static = blockIdx.x;
+    for (;;) {
+      mbar_wait(&S.plan_empty[ps], pphase ^ 1u);
+      int64_t roi;
+      if (counter) {                              // dynamic: one ticket per plan
+        unsigned int tk = 0;
+        if (lane == 0) tk = atomicAdd(&counter[0], 1u);
+        roi = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+      } else {                                    // static round robin
+        roi = next_static;
+        next_static += gridDim.x;
+      }
+      RowsPlan& P = S.plan[ps];
+      if (roi >= n_rois) {
+        if (lane == 0) {
+          P.mode = kRowsDone;
+          mbar_arrive(&S.plan_full[ps]);
+          if (counter) {
+            __threadfence();                                               // ticket draw before the done count
+            if (atomicAdd(&counter[1], 1u) == gridDim.x - 1) {             // every CTA has drawn its last ticket
+              counter[0] = 0;
+              counter[1] = 0;
+            }
+          }
+        }
+        return;
+      }
+      rows_make_plan(src, roi, ph, pw, ring_bytes, lane, P, S, level_out);
+      if (lane == 0) mbar_arrive(&S.plan_full[ps]);
+      if (l2_prefetch && P.mode == kRowsRing) {
+        // The planner runs a few ROIs ahead of the ring: pull this ROI's rows into L2 now, so that the ring copies issued
+        // later pay an L2 hit instead of a DRAM access queued behind the output stream.
+        const char* __restrict__ gbase = reinterpret_cast<const char*>(P.base);
+        const size_t row_pitch = (size_t)P.W * kRowsPixelBytes;
+        const int32_t nruns = P.nruns, total = P.nr * nruns;
+        for (int32_t i = lane; i < total; i += 32) {
+          const int32_t k = i / nruns, j = i - k * nruns;
+          const char* a = gbase + (size_t)P.rows[k] * row_pitch + (size_t)P.run_col[j] * kRowsPixelBytes;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)P.run_len[j] * kRowsPixelBytes)
+                       : "memory");
         }
       }
-    }
-    if (P.mode == kRowsRing) {
-      for (int32_t s_ = 0; s_ < P.nslots; ++s_) {
-        mbar_init(&s_full[s_], 1);
-        mbar_init(&s_empty[s_], (uint32_t)(n_cons >> 5));
+      if (++ps == kRowsPlans) {
+        ps = 0;
+        pphase ^= 1u;
       }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
-  __syncthreads();
-  const int32_t mode = P.mode;
-  if (mode == kRowsSkip) return;
-  const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
-  float4* __restrict__ o = out + roi * ((int64_t)ph * pw * kRowsD4);
 
-  if (mode == kRowsFlat) {   // per-bin path: 4 direct loads per output quad (flipped / NaN / oversized ROIs)
-    const float4* __restrict__ base = reinterpret_cast<const float4*>(P.base);
-    const uint32_t W = (uint32_t)P.W;
-    const int32_t total = ph * pw * kRowsD4;
-    for (int32_t e = t; e < total; e += (int32_t)blockDim.x) {
-      const int32_t bin = e >> 6;
-      const uint32_t c = (uint32_t)(e & 63);
-      const int32_t y = bin / pw, x = bin - y * pw;
-      float4 v = ext4;
-      if (P.y_ok[y] && P.x_ok[x]) {
-        const uint32_t top = (uint32_t)P.y_top[y], bot = (uint32_t)P.y_bot[y];
-        const uint32_t left = (uint32_t)P.x_left[x], right = (uint32_t)P.x_right[x];
-        const float4 tl = ldg_f4(base + ((top * W + left) * kRowsD4 + c));
-        const float4 tr = ldg_f4(base + ((top * W + right) * kRowsD4 + c));
-        const float4 bl = ldg_f4(base + ((bot * W + left) * kRowsD4 + c));
-        const float4 br = ldg_f4(base + ((bot * W + right) * kRowsD4 + c));
-        const float xl = P.x_lerp[x];
-        v = lerp4p(lerp4p(tl, tr, xl), lerp4p(bl, br, xl), P.y_lerp[y]);
+  if (warp == n_cwarps) {
+    // ------------------------------------------------------------------ issuer: FIFO byte ring
+    uint32_t head = 0, used = 0;
+    int32_t e_idx = 0, old_idx = 0, outstanding = 0;
+    uint32_t old_phase = 0;
+    for (;;) {
+      mbar_wait(&S.plan_full[ps], pphase);
+      const RowsPlan& P = S.plan[ps];
+      const int32_t mode = P.mode;
+      if (mode == kRowsDone) return;
+      if (mode == kRowsRing && !(dbg & 2)) {
+        const int32_t nr = P.nr, nruns = P.nruns;
+        const uint32_t bytes = P.row_bytes;
+        const char* __restrict__ gbase = reinterpret_cast<const char*>(P.base);
+        const size_t row_pitch = (size_t)P.W * kRowsPixelBytes;
+        for (int32_t k = 0; k < nr; ++k) {
+          uint32_t need;
+          bool wrap;
+          for (;;) {
+            if (outstanding == 0) head = 0, used = 0;                  // empty ring: start over at offset 0
+            wrap = head + bytes > ring_bytes;                           // a row never straddles the end of the ring:
+            need = bytes + (wrap ? ring_bytes - head : 0u);             // the tail it skips counts as part of the entry
+            if (used + need <= ring_bytes && outstanding < kRowsEntries) break;
+            mbar_wait(&S.empty[old_idx], old_phase);                    // reclaim the oldest entry (FIFO)
+            used -= S.entry_fp[old_idx];
+            --outstanding;
+            if (++old_idx == kRowsEntries) {
+              old_idx = 0;
+              old_phase ^= 1u;
+            }
+          }
+          if (wrap) head = 0;
+          const uint32_t off = head;
+          head += bytes;
+          used += need;
+          ++outstanding;
+          if (lane == 0) {
+            S.entry_off[e_idx] = off;
+            S.entry_fp[e_idx] = need;
+            mbar_expect_tx(&S.full[e_idx], bytes);
+          }
+          __syncwarp();
+          const char* srow = gbase + (size_t)P.rows[k] * row_pitch;
+          unsigned char* dst = s_ring + off;
+          for (int32_t j = lane; j < nruns; j += 32)
+            bulk_g2s(dst + (size_t)P.run_rank[j] * kRowsPixelBytes, srow + (size_t)P.run_col[j] * kRowsPixelBytes,
+                     (uint32_t)P.run_len[j] * kRowsPixelBytes, &S.full[e_idx]);
+          if (++e_idx == kRowsEntries) e_idx = 0;
+        }
       }
-      stg_cs_f4(o + e, v);
-    }
-    return;
-  }
-
-  const int32_t nslots = P.nslots;
-  const uint32_t slot_bytes = P.slot_bytes;
-  if (t >= n_cons) {
-    // ---- producer warp: stream the needed rows, in rank order, through the ring
-    const int32_t nr = P.nr, nruns = P.nruns;
-    const char* __restrict__ gbase = reinterpret_cast<const char*>(P.base);
-    const size_t row_pitch = (size_t)P.W * kRowsPixelBytes;
-    int32_t slot = 0;
-    uint32_t phase = 0;
-    for (int32_t k = 0; k < nr; ++k) {
-      mbar_wait(&s_empty[slot], phase ^ 1u);           // all consumer warps are done with the previous tenant
-      if (lane == 0) mbar_expect_tx(&s_full[slot], slot_bytes);
       __syncwarp();
-      const char* srow = gbase + (size_t)P.rows[k] * row_pitch;
-      unsigned char* dst = s_ring + (size_t)slot * slot_bytes;
-      for (int32_t j = lane; j < nruns; j += 32)
-        bulk_g2s(dst + (size_t)P.run_rank[j] * kRowsPixelBytes, srow + (size_t)P.run_col[j] * kRowsPixelBytes,
-                 (uint32_t)P.run_len[j] * kRowsPixelBytes, &s_full[slot]);
-      if (++slot == nslots) {
-        slot = 0;
-        phase ^= 1u;
+      if (lane == 0) mbar_arrive(&S.plan_empty[ps]);
+      if (++ps == kRowsPlans) {
+        ps = 0;
+        pphase ^= 1u;
       }
     }
-    return;
   }
 
-  // ---- consumers
+  // -------------------------------------------------------------------- consumers
   const int32_t q = t & 63, xg = t >> 6;
-  int32_t xcl[XPT], xcr[XPT];
-  float xl[XPT];
-  bool xok[XPT], xin[XPT];
+  const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
+  int32_t e_idx = 0;
+  uint32_t e_phase = 0;
+  for (;;) {
+    mbar_wait(&S.plan_full[ps], pphase);
+    const RowsPlan& P = S.plan[ps];
+    const int32_t mode = P.mode;
+    if (mode == kRowsDone) return;
+    float4* __restrict__ o = out + P.roi * ((int64_t)ph * pw * kRowsD4);
+    if (mode == kRowsRing) {
+      // this thread's x bins: x = xg + XG * i. Column ranks -> float4 index inside a ring row (+ the channel quad).
+      int32_t xcl[XPT], xcr[XPT];
+      float xl[XPT];
+      bool xin[XPT];
 #pragma unroll
-  for (int i = 0; i < XPT; ++i) {
-    const int32_t x = xg + XG * i;
-    xin[i] = x < pw;
-    xok[i] = xin[i] && P.x_ok[x];
-    xcl[i] = xok[i] ? P.x_cl[x] * kRowsD4 + q : q;
-    xcr[i] = xok[i] ? P.x_cr[x] * kRowsD4 + q : q;
-    xl[i] = xok[i] ? P.x_lerp[x] : 0.0f;
-  }
-  float4 va[XPT], vb[XPT];
+      for (int i = 0; i < XPT; ++i) {
+        const int32_t x = xg + XG * i;
+        xin[i] = FULL || x < pw;
+        const int32_t xs = xin[i] ? x : 0;
+        xcl[i] = P.x_cl[xs] * kRowsD4 + q;
+        xcr[i] = P.x_cr[xs] * kRowsD4 + q;
+        xl[i] = P.x_lerp[xs];
+      }
+      // Row of rank k lives in r0 (k even) or r1 (k odd): the two rows a bin blends have consecutive ranks, so loading
+      // rank k only ever replaces rank k-2. dv = bottom - top of the current row pair, reused by every y that shares it.
+      float4 r0[XPT], r1[XPT], dv[XPT];
 #pragma unroll
-  for (int i = 0; i < XPT; ++i) va[i] = vb[i] = ext4;
-  int32_t ra = -1, rb = -1;
-  int32_t slot = 0;
-  uint32_t phase = 0;
-  // blend the next row of the ring (ranks arrive in order) for this thread's x bins, then release its slot
+      for (int i = 0; i < XPT; ++i) r0[i] = r1[i] = dv[i] = ext4;
+      int32_t loaded = -1, dkt = -1, dkb = -1;
 #define OD_ROWS_LOAD(V)                                                                              \
   do {                                                                                               \
-    mbar_wait(&s_full[slot], phase);                                                                 \
-    const float4* rowp = reinterpret_cast<const float4*>(s_ring + (size_t)slot * slot_bytes);        \
-    _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                \
-      if (xok[i]) V[i] = lerp4p(rowp[xcl[i]], rowp[xcr[i]], xl[i]);                                  \
-    }                                                                                                \
+    if (dbg & 2) break;               /* timing experiment: no input stream at all */                \
+    mbar_wait(&S.full[e_idx], e_phase);                                                              \
+    const float4* rowp = reinterpret_cast<const float4*>(s_ring + S.entry_off[e_idx]);               \
+    _Pragma("unroll") for (int i = 0; i < XPT; ++i) V[i] = lerp4p(rowp[xcl[i]], rowp[xcr[i]], xl[i]); \
     __syncwarp();                                                                                    \
-    if (lane == 0) mbar_arrive(&s_empty[slot]);                                                      \
-    if (++slot == nslots) {                                                                          \
-      slot = 0;                                                                                      \
-      phase ^= 1u;                                                                                   \
+    if (lane == 0) mbar_arrive(&S.empty[e_idx]);                                                     \
+    if (++e_idx == kRowsEntries) {                                                                   \
+      e_idx = 0;                                                                                     \
+      e_phase ^= 1u;                                                                                 \
     }                                                                                                \
   } while (0)
-
-  for (int32_t y = 0; y < ph; ++y) {
-    const bool yok = P.y_ok[y] != 0;
-    bool same = true;
-    float yl = 0.0f;
-    if (yok) {
-      const int32_t kt = P.y_rt[y], kb = P.y_rb[y];
-      yl = P.y_lerp[y];
-      if (kt != ra) {
-        if (kt == rb) {
-#pragma unroll
-          for (int i = 0; i < XPT; ++i) va[i] = vb[i];
-          rb = -1;
-        } else {
-          OD_ROWS_LOAD(va);
+#define OD_ROWS_DIFF(B, T)                                                                           \
+  _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                  \
+    sub2(dv[i].x, dv[i].y, B[i].x, B[i].y, T[i].x, T[i].y);                                          \
+    sub2(dv[i].z, dv[i].w, B[i].z, B[i].w, T[i].z, T[i].w);                                          \
+  }
+#define OD_ROWS_EMIT(T)                                                                              \
+  _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                  \
+    float4 m_, v_;                                                                                   \
+    m_.x = __fmul_rn(dv[i].x, yl);                                                                   \
+    m_.y = __fmul_rn(dv[i].y, yl);                                                                   \
+    m_.z = __fmul_rn(dv[i].z, yl);                                                                   \
+    m_.w = __fmul_rn(dv[i].w, yl);                                                                   \
+    add2(v_.x, v_.y, T[i].x, T[i].y, m_.x, m_.y);                                                    \
+    add2(v_.z, v_.w, T[i].z, T[i].w, m_.z, m_.w);                                                    \
+    if ((FULL || xin[i]) && !(dbg & 1)) stg_cs_f4(orow + i * (XG * kRowsD4), v_);                    \
+  }
+      float4* __restrict__ orow = o + xg * kRowsD4 + q;
+      for (int32_t y = 0; y < ph; ++y, orow += pw * kRowsD4) {
+        const int4 e = P.ytab[y];
+        const int32_t kt = e.x, kb = e.y;
+        const float yl = __int_as_float(e.z);
+        while (loaded < kb) {
+          ++loaded;
+          if (loaded & 1) OD_ROWS_LOAD(r1);
+          else OD_ROWS_LOAD(r0);
         }
-        ra = kt;
+        if (kt != dkt || kb != dkb) {              // new row pair
+          dkt = kt;
+          dkb = kb;
+          if (kt & 1) {
+            if (kb & 1) { OD_ROWS_DIFF(r1, r1) } else { OD_ROWS_DIFF(r0, r1) }
+          } else {
+            if (kb & 1) { OD_ROWS_DIFF(r1, r0) } else { OD_ROWS_DIFF(r0, r0) }
+          }
+        }
+        if (kt & 1) { OD_ROWS_EMIT(r1) } else { OD_ROWS_EMIT(r0) }
       }
-      same = (kb == kt);
-      if (!same && kb != rb) {
-        OD_ROWS_LOAD(vb);
-        rb = kb;
+#undef OD_ROWS_LOAD
+#undef OD_ROWS_DIFF
+#undef OD_ROWS_EMIT
+    } else if (mode == kRowsFlat) {   // per-bin path: 4 direct loads per output quad
+      const float4* __restrict__ base = reinterpret_cast<const float4*>(P.base);
+      const uint32_t W = (uint32_t)P.W;
+      const int32_t total = ph * pw * kRowsD4;
+      for (int32_t e = t; e < total; e += n_cons) {
+        const int32_t bin = e >> 6;
+        const uint32_t c = (uint32_t)(e & 63);
+        const int32_t y = bin / pw, x = bin - y * pw;
+        float4 v = ext4;
+        if (P.y_ok[y] && P.x_ok[x]) {
+          const uint32_t top = (uint32_t)P.y_top[y], bot = (uint32_t)P.y_bot[y];
+          const uint32_t left = (uint32_t)P.x_left[x], right = (uint32_t)P.x_right[x];
+          const float4 tl = ldg_f4(base + ((top * W + left) * kRowsD4 + c));
+          const float4 tr = ldg_f4(base + ((top * W + right) * kRowsD4 + c));
+          const float4 bl = ldg_f4(base + ((bot * W + left) * kRowsD4 + c));
+          const float4 br = ldg_f4(base + ((bot * W + right) * kRowsD4 + c));
+          const float xl = P.x_lerp[x];
+          v = lerp4p(lerp4p(tl, tr, xl), lerp4p(bl, br, xl), P.y_lerp[y]);
+        }
+        stg_cs_f4(o + e, v);
       }
     }
-    float4* __restrict__ orow = o + (int64_t)y * pw * kRowsD4 + q;
-#pragma unroll
-    for (int i = 0; i < XPT; ++i) {
-      if (xin[i]) {
-        float4 v = ext4;
-        if (yok && xok[i]) v = lerp4p(va[i], same ? va[i] : vb[i], yl);
-        stg_cs_f4(orow + (xg + XG * i) * kRowsD4, v);
-      }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.plan_empty[ps]);   // this warp no longer reads the plan
+    if (++ps == kRowsPlans) {
+      ps = 0;
+      pphase ^= 1u;
     }
   }
-#undef OD_ROWS_LOAD
 }
 
 // FasterRCNN roi_pool (fastrcnn.py:22-70): crop_and_resize to (2*oh) x (2*ow) fused with max_pool 2x2 / stride 2.
@@ -624,65 +739,84 @@ crop_pool_bins_kernel(RoiSource src, int64_t total_bins, int32_t oh, int32_t ow,
 
 // ----------------------------------------------------------------------------- host side
 // Tunables of the TMA-staged kernel, read once from the environment (A/B runs on one box without rebuilding):
-//   OD_ROI_KERNEL=flat  forces crop_bins_kernel;  OD_ROI_RING_KB  shared-memory ring per CTA (default 64);
-//   OD_ROI_XPT = 1 | 2 | 4  x bins per consumer thread (default 2).
+//   OD_ROI_KERNEL=flat   forces crop_bins_kernel;       OD_ROI_MIN_POOL  smallest max(pool_h, pool_w) served (default 10);
+//   OD_ROI_RING_KB       shared-memory ring per CTA (default 64);   OD_ROI_CPS  persistent CTAs per SM (default 2);
+//   OD_ROI_XPT = 1|2|4   x bins per consumer thread (default 2);    OD_ROI_DYNAMIC=0  static round robin even with a workspace.
 struct RowsTuning {
-  bool use_rows;
+  bool use_rows, dynamic;
   uint32_t ring_bytes;
-  int xpt;
+  int xpt, cps, min_pool, l2_prefetch, dbg;
 };
+static int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  int x = v ? atoi(v) : dflt;
+  return x < lo ? lo : (x > hi ? hi : x);
+}
 static const RowsTuning& rows_tuning() {
   static const RowsTuning t = [] {
     RowsTuning r;
     const char* k = getenv("OD_ROI_KERNEL");
     r.use_rows = !(k && strcmp(k, "flat") == 0);
-    const char* kb = getenv("OD_ROI_RING_KB");
-    int kbv = kb ? atoi(kb) : 64;
-    if (kbv < 32) kbv = 32;
-    if (kbv > 200) kbv = 200;
-    r.ring_bytes = (uint32_t)kbv * 1024u;
-    const char* x = getenv("OD_ROI_XPT");
-    const int xv = x ? atoi(x) : 2;
+    r.ring_bytes = (uint32_t)env_int("OD_ROI_RING_KB", 64, 32, 200) * 1024u;
+    const int xv = env_int("OD_ROI_XPT", 2, 1, 4);
     r.xpt = (xv == 1 || xv == 4) ? xv : 2;
+    r.cps = env_int("OD_ROI_CPS", 2, 1, 8);
+    r.min_pool = env_int("OD_ROI_MIN_POOL", 10, 1, 17);
+    r.dynamic = env_int("OD_ROI_DYNAMIC", 1, 0, 1) != 0;
+    r.l2_prefetch = env_int("OD_ROI_L2_PREFETCH", 0, 0, 1);
+    r.dbg = env_int("OD_ROI_TIMING_EXPERIMENT", 0, 0, 3);   // 1: no output stores, 2: no input stream (WRONG RESULTS; timing only)
     return r;
   }();
   return t;
 }
 
-template <int XPT, int MAXT, int MINB>
-static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t XG, uint32_t ring,
-                              float extrap, float* out, int32_t* level_out, cudaStream_t st) {
-  auto kern = crop_rows_kernel<XPT, MAXT, MINB>;
+template <int XPT, bool FULL, int MAXT, int MINB>
+static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t XG, const RowsTuning& tn,
+                              float extrap, float* out, int32_t* level_out, unsigned int* counter, cudaStream_t st) {
+  auto kern = crop_rows_kernel<XPT, FULL, MAXT, MINB>;
   static uint32_t configured[64] = {0};    // dynamic shared memory opted in, per device
+  static int sms[64] = {0};
   int dev = 0;
   OD_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && configured[dev] < ring) {
-    OD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
-    configured[dev] = ring;
+  if (dev < 0 || dev >= 64) OD_FAIL(OD_ERR_DEVICE, "device index %d not supported", dev);
+  if (configured[dev] < tn.ring_bytes) {
+    OD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn.ring_bytes));
+    configured[dev] = tn.ring_bytes;
   }
-  OD_CUDA(launch_pdl(kern, dim3((unsigned)n_rois), dim3((unsigned)(kRowsD4 * XG + 32)), (size_t)ring, st, src, ph, pw, XG,
-                     ring, extrap, reinterpret_cast<float4*>(out), level_out));
+  if (!sms[dev]) OD_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int64_t grid = n_rois < (int64_t)sms[dev] * tn.cps ? n_rois : (int64_t)sms[dev] * tn.cps;
+  OD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)(kRowsD4 * XG + 64)), (size_t)tn.ring_bytes, st, src, n_rois,
+                     ph, pw, XG, tn.ring_bytes, extrap, reinterpret_cast<float4*>(out), level_out, counter, tn.l2_prefetch, tn.dbg));
   OD_LAUNCH_CHECK("crop_rows_kernel");
   return OD_OK;
 }
 
-// returns OD_OK after launching, or 1 when the shape is not served by this kernel (caller falls back to crop_bins)
+// returns OD_OK after launching, or 1 when the shape is not served by this kernel (caller falls back to crop_bins).
+// `counter`: two zeroed uint32 in the caller's workspace (dynamic ROI scheduling) or NULL (static round robin).
 static int launch_crop_rows(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap, float* out,
-                            int32_t* level_out, cudaStream_t st) {
+                            int32_t* level_out, unsigned int* counter, cudaStream_t st) {
   const RowsTuning& tn = rows_tuning();
-  if (!tn.use_rows || D != 4 * kRowsD4 || ph > kRowsMaxPool || pw > kRowsMaxPool || src.mode > 1 || n_rois > 0x7FFFFFFFll)
-    return 1;
+  const int32_t pmax = ph > pw ? ph : pw;
+  if (!tn.use_rows || D != 4 * kRowsD4 || pmax > kRowsMaxPool || pmax < tn.min_pool || src.mode > 1) return 1;
+  if (n_rois + 4096 > 0x7FFFFFFFll) return 1;
+  if (!tn.dynamic) counter = nullptr;
   int xpt = tn.xpt;
-  if (xpt == 1 && pw > 7) xpt = 2;
+  if (xpt == 1 && pw > 15) xpt = 2;
   if (xpt == 2 && pw > 14) xpt = 4;
-  const int32_t XG = (pw + xpt - 1) / xpt;      // consumer threads = 64 * XG (+ one producer warp)
-  if (xpt == 1) return launch_crop_rows_t<1, 480, 2>(src, n_rois, ph, pw, XG, tn.ring_bytes, extrap, out, level_out, st);
-  if (xpt == 2) return launch_crop_rows_t<2, 480, 2>(src, n_rois, ph, pw, XG, tn.ring_bytes, extrap, out, level_out, st);
-  return launch_crop_rows_t<4, 288, 2>(src, n_rois, ph, pw, XG, tn.ring_bytes, extrap, out, level_out, st);
+  const int32_t XG = (pw + xpt - 1) / xpt;      // consumer threads = 64 * XG (+ issuer warp + planner warp)
+  const bool full = XG * xpt == pw;
+#define OD_ROWS_DISPATCH(X, T, M)                                                                                       \
+  return full ? launch_crop_rows_t<X, true, T, M>(src, n_rois, ph, pw, XG, tn, extrap, out, level_out, counter, st)  \
+              : launch_crop_rows_t<X, false, T, M>(src, n_rois, ph, pw, XG, tn, extrap, out, level_out, counter, st)
+  if (xpt == 1 && pw > 7) OD_ROWS_DISPATCH(1, 1024, 1);
+  if (xpt == 1) OD_ROWS_DISPATCH(1, 512, 2);
+  if (xpt == 2) OD_ROWS_DISPATCH(2, 512, 2);
+  OD_ROWS_DISPATCH(4, 320, 2);
+#undef OD_ROWS_DISPATCH
 }
 
 static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
-                            float* out, int32_t* level_out, cudaStream_t st) {
+                            float* out, int32_t* level_out, cudaStream_t st, unsigned int* counter = nullptr) {
   if (n_rois == 0) return OD_OK;
   const int32_t D4 = D / 4;
   const int64_t bins_per_roi = (int64_t)ph * pw;
@@ -692,7 +826,7 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
     if ((int64_t)src.lt.H[l] * src.lt.W[l] * D4 > 0xFFFFFFFFll)
       OD_FAIL(OD_ERR_PARAM, "one image of level %d exceeds 2^32 16-byte units", l);
   {
-    const int rc = launch_crop_rows(src, n_rois, ph, pw, D, extrap, out, level_out, st);
+    const int rc = launch_crop_rows(src, n_rois, ph, pw, D, extrap, out, level_out, counter, st);
     if (rc != 1) return rc;
   }
   int32_t lg = -1;
@@ -731,9 +865,12 @@ using namespace od;
 
 extern "C" {
 
-int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
-                                 const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t pool_h,
-                                 int32_t pool_w, DLTensor* pooled, DLTensor* roi_level, void* stream) {
+size_t od_pyramid_roi_align_workspace_bytes(void) { return 256; }
+
+int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
+                                    const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t pool_h,
+                                    int32_t pool_w, DLTensor* pooled, DLTensor* roi_level, void* ws, size_t ws_bytes,
+                                    void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!fmaps) OD_FAIL(OD_ERR_NULL, "fmaps is NULL");
   if (num_levels < 1 || num_levels > OD_MAX_LEVELS) OD_FAIL(OD_ERR_PARAM, "num_levels %d not in [1,%d]", num_levels, OD_MAX_LEVELS);
@@ -782,8 +919,19 @@ int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_level
   src.batch = (int32_t)B;
   src.lt = lt;
   src.boxes = dptr<float4>(rois);
-  return launch_crop_bins(src, total, pool_h, pool_w, (int32_t)D, 0.0f, dptr<float>(pooled), dptr<int32_t>(roi_level), st);
+  if (ws && (ws_bytes < od_pyramid_roi_align_workspace_bytes() || reinterpret_cast<uintptr_t>(ws) % 8))
+    OD_FAIL(OD_ERR_WORKSPACE, "workspace must be 8-byte aligned and at least %zu bytes", od_pyramid_roi_align_workspace_bytes());
+  return launch_crop_bins(src, total, pool_h, pool_w, (int32_t)D, 0.0f, dptr<float>(pooled), dptr<int32_t>(roi_level), st,
+                          static_cast<unsigned int*>(ws));
 }
+
+int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
+                                 const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t pool_h,
+                                 int32_t pool_w, DLTensor* pooled, DLTensor* roi_level, void* stream) {
+  return od_pyramid_roi_align_forward_ws(fmaps, num_levels, min_level, rois, image_h, image_w, pool_h, pool_w, pooled,
+                                         roi_level, nullptr, 0, stream);
+}
+
 
 int od_crop_and_resize(const DLTensor* image, const DLTensor* boxes, const DLTensor* box_ind, int32_t crop_h,
                        int32_t crop_w, float extrapolation_value, DLTensor* out, void* stream) {

@@ -35,9 +35,11 @@ def pyramid_roi_align(feature_maps, proposals, image_shape, pool_shape, levels=(
     lv = torch.empty((B, N), dtype=torch.int32, device=dev) if return_levels else None
     dl = _lib.DL()
     ptrs = (ctypes.c_void_p * len(fmaps))(*[dl(f) for f in fmaps])
-    _lib.check(_lib.lib().od_pyramid_roi_align_forward(ptrs, len(fmaps), min(levels), dl(rois), int(image_shape[0]),
-                                                       int(image_shape[1]), ph, pw, dl(out), dl(lv),
-                                                       _lib.stream_ptr(dev)), "od_pyramid_roi_align_forward")
+    L = _lib.lib()
+    ws = _lib.zeroed_workspace(L.od_pyramid_roi_align_workspace_bytes(), dev)     # ROI ticket counter (stays zeroed)
+    _lib.check(L.od_pyramid_roi_align_forward_ws(ptrs, len(fmaps), min(levels), dl(rois), int(image_shape[0]),
+                                                 int(image_shape[1]), ph, pw, dl(out), dl(lv), ws.data_ptr(),
+                                                 ws.numel(), _lib.stream_ptr(dev)), "od_pyramid_roi_align_forward_ws")
     return (out, lv) if return_levels else out
 
 

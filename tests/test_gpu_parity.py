@@ -391,6 +391,10 @@ def test_roi_pooling_d256_rows_kernel_edge_cases(pool):
     props[0, 11] = [0.5, 0.5, 0.5 + 1e-4, 0.5 + 1e-4]                         # sub-pixel ROI
     props[0, 12] = [0.2, 0.2, 0.2 + 3 / 63.0, 0.2 + 3 / 63.0]                 # integer-aligned taps on P2 (lerp 0)
     _roi_align_check(fmaps, props, 1024, pool)
+    _roi_align_check(fmaps, props, 1024, pool)                                # again: the ticket counter was left zeroed
+    from objectdetection_b200 import _lib
+    torch.cuda.synchronize()
+    assert all(int(w.count_nonzero()) == 0 for w in _lib._zero_ws.values())
 
 
 def test_crop_and_resize_d256_rows_kernel():

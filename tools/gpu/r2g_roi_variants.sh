@@ -1,0 +1,22 @@
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_goldens.py -m gpu -x -q -k "roi or crop" 2>&1 | tail -4
+run() {
+  echo "=== $*"
+  env "$@" timeout 300 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-extras 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); r=d['roofline']; s=d['roialign_standalone']
+        print('step_ms', round(d['ms_per_step'],4), 'eager', round(d['extra']['eager_ms_per_step'],4), 'p14_pipeline_ms', round(r['ms_per_launch'],4), 'frac', round(r['frac'],3), 'sa7', round(s['p7']['ms'],4), round(s['p7']['frac'],3), 'sa14', round(s['p14']['ms'],4), round(s['p14']['frac'],3), 'e2e', round(d['e2e']['value'],1), 'ceil', round(d['e2e']['h2d_ceiling_gbs'],1), round(d['e2e']['frac_of_ceiling'],3))
+    else: print(l[:300])
+"
+}
+run OD_ROI_KERNEL=flat
+run OD_ROI_RING_KB=96 OD_ROI_L2_PREFETCH=0
+run OD_ROI_RING_KB=96 OD_ROI_L2_PREFETCH=1
+run OD_ROI_RING_KB=64 OD_ROI_L2_PREFETCH=1
+run OD_ROI_RING_KB=108 OD_ROI_L2_PREFETCH=1
+run OD_ROI_RING_KB=108 OD_ROI_L2_PREFETCH=0
+run OD_ROI_CPS=1 OD_ROI_RING_KB=200 OD_ROI_XPT=1 OD_ROI_L2_PREFETCH=1
+run OD_ROI_CPS=1 OD_ROI_RING_KB=200 OD_ROI_XPT=1 OD_ROI_L2_PREFETCH=0
+run OD_ROI_CPS=3 OD_ROI_RING_KB=64 OD_ROI_XPT=4 OD_ROI_L2_PREFETCH=1
