@@ -130,6 +130,24 @@ __device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, f
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
   asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
 }
+__device__ __forceinline__ float4 sub4p(float4 b, float4 a) {
+  float4 d;
+  sub2(d.x, d.y, b.x, b.y, a.x, a.y);
+  sub2(d.z, d.w, b.z, b.w, a.z, a.w);
+  return d;
+}
+// a + d * t per component, d = b - a computed by the caller. The multiply stays scalar: ptxas contracts a packed
+// mul.rn.f32x2 + add.rn.f32x2 pair into FFMA2 even with -fmad=false (checked in SASS), which would change the rounding.
+__device__ __forceinline__ float4 axpy4p(float4 a, float4 d, float t) {
+  float4 m, r;
+  m.x = __fmul_rn(d.x, t);
+  m.y = __fmul_rn(d.y, t);
+  m.z = __fmul_rn(d.z, t);
+  m.w = __fmul_rn(d.w, t);
+  add2(r.x, r.y, a.x, a.y, m.x, m.y);
+  add2(r.z, r.w, a.z, a.w, m.z, m.w);
+  return r;
+}
 // a + (b - a) * t per component, every operation individually rounded (the multiply stays scalar: ptxas would
 // contract mul.f32x2 + add.f32x2 into FFMA2)
 __device__ __forceinline__ float4 lerp4p(float4 a, float4 b, float t) {
@@ -291,7 +309,8 @@ constexpr int kRowsD4 = 64;                     // D = 256 floats = 64 quads = 1
 constexpr uint32_t kRowsPixelBytes = 1024;
 
 struct RowsPlan {
-  int4 ytab[kRowsMaxPool];                      // ring mode: {rank of top row, rank of bottom row, y_lerp bits, 0}
+  int2 ytab[kRowsMaxPool + 1];                  // ring mode, per y: {y_lerp bits, top row == bottom row}; one pad entry
+  int32_t yfirst[2 * kRowsMaxPool + 1];         // ring mode: first y whose TOP row has rank >= k (y's of rank k are contiguous)
   int32_t y_top[kRowsMaxPool], y_bot[kRowsMaxPool], y_ok[kRowsMaxPool];
   float y_lerp[kRowsMaxPool];
   int32_t x_left[kRowsMaxPool], x_right[kRowsMaxPool], x_cl[kRowsMaxPool], x_cr[kRowsMaxPool], x_ok[kRowsMaxPool];
@@ -300,6 +319,7 @@ struct RowsPlan {
   int32_t run_col[kRowsMaxPool], run_rank[kRowsMaxPool], run_len[kRowsMaxPool];
   int32_t nr, ncols, nruns, mode;
   int32_t mono, W;
+  int32_t keep;                                 // issuer: copy this ROI's rows with the L2 evict_last policy
   uint32_t row_bytes;                           // ncols KiB: one ring entry
   int64_t roi;
   const float* base;
@@ -312,28 +332,23 @@ constexpr int kRowsRing = 0, kRowsFlat = 1, kRowsSkip = 2, kRowsDone = 3;
 struct RowsShared {
   RowsPlan plan[kRowsPlans];
   int32_t cols[2 * kRowsMaxPool];               // planner scratch
-  int32_t yrt[kRowsMaxPool], yrb[kRowsMaxPool]; // planner scratch
-  uint32_t entry_off[kRowsEntries];             // byte offset of an entry's row in the ring (issuer -> consumers)
   uint32_t entry_fp[kRowsEntries];              // ring bytes an entry occupies incl. wrap padding (issuer only)
   unsigned long long full[kRowsEntries], empty[kRowsEntries], plan_full[kRowsPlans], plan_empty[kRowsPlans];
 };
 
-// geometry of one ROI (level assignment, image base, sampling grid); returns the kBin* flag
-__device__ __forceinline__ uintptr_t roi_geometry(const RoiSource& src, int64_t roi, int32_t ph, int32_t pw,
-                                                  RoiMeta& m, int32_t* level) {
-  float4 box;
+// geometry of one ROI (level assignment, image base, sampling grid) from its preloaded box (and batch index in
+// crop_and_resize mode); returns the kBin* flag
+__device__ __forceinline__ uintptr_t roi_geometry(const RoiSource& src, int64_t roi, float4 box, int32_t b, int32_t ph,
+                                                  int32_t pw, RoiMeta& m, int32_t* level) {
   uintptr_t flag = kBinSample;
   constexpr int64_t D = 4 * kRowsD4;
   if (src.mode == 0) {
-    box = __ldg(&src.boxes[roi]);
     *level = roi_level_of(box, src.image_h, src.image_w, src.min_level, src.min_level + src.num_levels - 1);
     const int32_t l = *level - src.min_level;
     m.H = src.lt.H[l];
     m.W = src.lt.W[l];
-    m.base = src.lt.ptr[l] + (roi / src.rois_per_image) * ((int64_t)m.H * m.W * D);
+    m.base = src.lt.ptr[l] + (int64_t)((uint32_t)roi / (uint32_t)src.rois_per_image) * ((int64_t)m.H * m.W * D);
   } else {
-    box = __ldg(&src.boxes[roi]);
-    const int32_t b = __ldg(&src.box_ind[roi]);
     m.H = src.lt.H[0];
     m.W = src.lt.W[0];
     m.base = src.lt.ptr[0];
@@ -344,85 +359,103 @@ __device__ __forceinline__ uintptr_t roi_geometry(const RoiSource& src, int64_t 
   return flag;
 }
 
-// ranks of the distinct values of a non-decreasing tap sequence (lo[i] <= hi[i], lo[i] <= lo[i+1]), in first-use order
-__device__ __forceinline__ int32_t rank_scan(int32_t n, const int32_t* lo, const int32_t* hi, int32_t* r_lo, int32_t* r_hi,
-                                             int32_t* vals) {
-  int32_t k = -1, a = -1, b = -1;               // a, b: values of ranks k-1, k
-  for (int32_t i = 0; i < n; ++i) {
-    const int32_t t = lo[i], u = hi[i];
-    if (t == b) r_lo[i] = k;
-    else if (t == a) r_lo[i] = k - 1;
-    else { ++k; vals[k] = t; a = b; b = t; r_lo[i] = k; }
-    if (u == b) r_hi[i] = k;
-    else if (u == a) r_hi[i] = k - 1;
-    else { ++k; vals[k] = u; a = b; b = u; r_hi[i] = k; }
-  }
-  return k + 1;
-}
-
-// one warp builds the plan of one ROI
-__device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi, int32_t ph, int32_t pw, uint32_t ring_bytes,
-                                               int32_t lane, RowsPlan& P, RowsShared& S, int32_t* level_out) {
-  bool ok = true;
-  {
-    RoiMeta m;
-    int32_t level = 0;
-    const uintptr_t flag = roi_geometry(src, roi, ph, pw, m, &level);
-    if (lane == 0) {
-      P.roi = roi;
-      P.base = m.base;
-      P.W = m.W;
-      P.mode = (flag == kBinSkip) ? kRowsSkip : kRowsRing;
-      P.mono = (m.hs >= 0.0f) && (m.ws >= 0.0f);
-      if (level_out && src.mode == 0) level_out[roi] = level;
-    }
-    if (lane < 16) {
-      if (lane < ph) {
-        const float in_y = m.in_y0 + (float)lane * m.hs;
-        ok = (in_y >= 0.0f) && (in_y <= (float)(m.H - 1));
-        const float fy = floorf(in_y);
-        P.y_ok[lane] = ok;
-        P.y_top[lane] = ok ? (int32_t)fy : 0;
-        P.y_bot[lane] = ok ? (int32_t)ceilf(in_y) : 0;
-        P.y_lerp[lane] = ok ? in_y - fy : 0.0f;
-      }
+// One warp builds the plan of one ROI, all lanes busy: lanes 0-15 own the y samples, lanes 16-31 the x samples.
+// With a non-negative grid step the tap sequence lo(0) <= hi(0), lo(1) <= hi(1), ... is non-decreasing and
+// hi - lo is 0 or 1, so a tap is NEW (not seen before) exactly when it differs from both taps of the previous
+// sample; first-use order is ascending order, the rank of a new tap is the number of new taps before it (two
+// ballots and a popcount) and a repeated tap is the largest or second largest value seen so far.
+__device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi, float4 box, int32_t bidx, int32_t ph,
+                                               int32_t pw, uint32_t ring_bytes, int32_t l2_keep, int32_t lane, RowsPlan& P,
+                                               RowsShared& S, int32_t* level_out) {
+  RoiMeta m;
+  int32_t level = 0;
+  const uintptr_t flag = roi_geometry(src, roi, box, bidx, ph, pw, m, &level);
+  const bool mono = (m.hs >= 0.0f) && (m.ws >= 0.0f);
+  const int32_t half = lane >> 4, i = lane & 15;
+  const int32_t n = half ? pw : ph;
+  const bool valid = i < n;
+  const float in = half ? (m.in_x0 + (float)i * m.ws) : (m.in_y0 + (float)i * m.hs);
+  const float lim = (float)((half ? m.W : m.H) - 1);
+  const bool ok = !valid || ((in >= 0.0f) && (in <= lim));
+  const float fl = floorf(in);
+  const int32_t lo = (valid && ok) ? (int32_t)fl : 0;
+  const int32_t hi = (valid && ok) ? (int32_t)ceilf(in) : 0;
+  const float lerp = (valid && ok) ? in - fl : 0.0f;
+  if (valid) {                                      // the per-bin tables (the flat path reads them)
+    if (half) {
+      P.x_ok[i] = ok;
+      P.x_left[i] = lo;
+      P.x_right[i] = hi;
+      P.x_lerp[i] = lerp;
     } else {
-      const int32_t x = lane - 16;
-      if (x < pw) {
-        const float in_x = m.in_x0 + (float)x * m.ws;
-        ok = (in_x >= 0.0f) && (in_x <= (float)(m.W - 1));
-        const float fx = floorf(in_x);
-        P.x_ok[x] = ok;
-        P.x_left[x] = ok ? (int32_t)fx : 0;
-        P.x_right[x] = ok ? (int32_t)ceilf(in_x) : 0;
-        P.x_lerp[x] = ok ? in_x - fx : 0.0f;
-      }
+      P.y_ok[i] = ok;
+      P.y_top[i] = lo;
+      P.y_bot[i] = hi;
+      P.y_lerp[i] = lerp;
     }
   }
-  const bool all_ok = __all_sync(0xffffffffu, ok);    // every bin has four valid taps (also orders the writes above)
-  if (lane == 0 && P.mode == kRowsRing && !(all_ok && P.mono)) P.mode = kRowsFlat;
-  __syncwarp();
-  if (P.mode != kRowsRing) return;
-  if (lane == 0) {
-    P.nr = rank_scan(ph, P.y_top, P.y_bot, S.yrt, S.yrb, P.rows);
-    for (int32_t y = 0; y < ph; ++y) P.ytab[y] = make_int4(S.yrt[y], S.yrb[y], __float_as_int(P.y_lerp[y]), 0);
-  } else if (lane == 16) {
-    const int32_t nc = rank_scan(pw, P.x_left, P.x_right, P.x_cl, P.x_cr, S.cols);
-    int32_t nruns = 0;
-    for (int32_t k = 0; k < nc; ++k) {
-      if (k == 0 || S.cols[k] != S.cols[k - 1] + 1) {
-        P.run_col[nruns] = S.cols[k];
-        P.run_rank[nruns] = k;
-        P.run_len[nruns] = 1;
-        ++nruns;
+  const bool all_ok = __all_sync(0xffffffffu, ok);  // every bin has four valid taps
+  int32_t mode = (flag == kBinSkip) ? kRowsSkip : ((all_ok && mono) ? kRowsRing : kRowsFlat);
+  if (mode == kRowsRing) {
+    const int32_t plo = __shfl_up_sync(0xffffffffu, lo, 1), phi = __shfl_up_sync(0xffffffffu, hi, 1);
+    const bool new_lo = valid && (i == 0 || (lo != plo && lo != phi));
+    const bool new_hi = valid && hi != lo && (i == 0 || hi != phi);
+    const uint32_t hm = half ? 0xFFFF0000u : 0x0000FFFFu;
+    const uint32_t ml = __ballot_sync(0xffffffffu, new_lo) & hm, mh = __ballot_sync(0xffffffffu, new_hi) & hm;
+    const uint32_t below = hm & ((1u << lane) - 1u);
+    const int32_t c = __popc(ml & below) + __popc(mh & below);      // distinct taps before this sample
+    const int32_t r_lo = new_lo ? c : (lo == phi ? c - 1 : c - 2);
+    const int32_t c2 = c + (new_lo ? 1 : 0);
+    const int32_t r_hi = (hi == lo) ? r_lo : (new_hi ? c2 : c2 - 1);
+    const int32_t cnt = __popc(ml) + __popc(mh);                    // distinct taps of this half
+    int32_t* vals = half ? S.cols : P.rows;
+    if (new_lo) vals[r_lo] = lo;
+    if (new_hi) vals[r_hi] = hi;
+    if (valid) {
+      if (half) {
+        P.x_cl[i] = r_lo;
+        P.x_cr[i] = r_hi;
       } else {
-        ++P.run_len[nruns - 1];
+        P.ytab[i] = make_int2(__float_as_int(lerp), r_hi == r_lo ? 1 : 0);
       }
     }
-    P.ncols = nc;
-    P.nruns = nruns;
-    P.row_bytes = (uint32_t)nc * kRowsPixelBytes;
-    if (P.row_bytes > ring_bytes) P.mode = kRowsFlat;
+    {   // lane k: how many y's blend a top row of rank < k (ranks are <= 31, entry 32 is the pool height)
+      int32_t before = 0;
+      for (int32_t y = 0; y < ph; ++y) before += (__shfl_sync(0xffffffffu, r_lo, y) < lane) ? 1 : 0;
+      P.yfirst[lane] = before;
+      if (lane == 0) P.yfirst[32] = ph;
+    }
+    const int32_t nc = __shfl_sync(0xffffffffu, cnt, 16), nr = __shfl_sync(0xffffffffu, cnt, 0);
+    __syncwarp();
+    // distinct columns -> runs of adjacent pixels (one bulk copy each): lane k looks at column rank k
+    const int32_t ck = lane < nc ? S.cols[lane] : 0;
+    const int32_t cp = __shfl_up_sync(0xffffffffu, ck, 1);
+    const bool start = lane < nc && (lane == 0 || ck != cp + 1);
+    const uint32_t sm = __ballot_sync(0xffffffffu, start);
+    if (start) {
+      const uint32_t le = (2u << lane) - 1u;        // lanes <= this one (wraps to all ones for lane 31)
+      const int32_t j = __popc(sm & le) - 1;
+      const uint32_t rest = sm & ~le;
+      P.run_col[j] = ck;
+      P.run_rank[j] = lane;
+      P.run_len[j] = (rest ? __ffs(rest) - 1 : nc) - lane;
+    }
+    if ((uint32_t)nc * kRowsPixelBytes > ring_bytes) mode = kRowsFlat;
+    if (lane == 0) {
+      P.nr = nr;
+      P.ncols = nc;
+      P.nruns = __popc(sm);
+      P.row_bytes = (uint32_t)nc * kRowsPixelBytes;
+    }
+  }
+  if (lane == 0) {
+    P.roi = roi;
+    P.base = m.base;
+    P.W = m.W;
+    P.mono = mono;
+    P.mode = mode;
+    P.keep = l2_keep == 1 || (l2_keep == 2 && src.mode == 0 && level > src.min_level);
+    if (level_out && src.mode == 0) level_out[roi] = level;
   }
   __syncwarp();
 }
@@ -433,7 +466,7 @@ template <int XPT, bool FULL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t XG, uint32_t ring_bytes, float extrap,
                  float4* __restrict__ out, int32_t* __restrict__ level_out, unsigned int* __restrict__ counter,
-                 int32_t l2_prefetch, int32_t dbg) {
+                 int32_t l2_prefetch, int32_t l2_keep, int32_t dbg) {
   pdl_prologue();
   extern __shared__ __align__(128) unsigned char s_ring[];
   __shared__ RowsShared S;
@@ -458,26 +491,41 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
 
   if (warp == n_cwarps + 1) {
     // ------------------------------------------------------------------ planner: draws ROIs, plans a few ahead
-    int64_t next_static = blockIdx.x;
-    for (;;) {
-      mbar_wait(&S.plan_empty[ps], pphase ^ 1u);
-      int64_t roi;
-      if (counter) {                              // dynamic: one ticket per plan
-        unsigned int tk = 0;
-        if (lane == 0) tk = atomicAdd(&counter[0], 1u);
-        roi = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
-      } else {                                    // static round robin
-        roi = next_static;
-        next_static += gridDim.x;
+    // The ticket is drawn two plans ahead and the box fetched one plan ahead, so that neither the atomic's nor the
+    // load's round trip sits between two plans. A CTA therefore draws up to two tickets past the end; the reset of the
+    // counters below waits for all of them.
+    const int64_t stride = gridDim.x;
+    auto draw = [&](int64_t k) -> int64_t {         // k-th ROI of this CTA; dynamic: valid on lane 0 only (see bcast)
+      if (!counter) return (int64_t)blockIdx.x + k * stride;
+      return lane == 0 ? (int64_t)atomicAdd(&counter[0], 1u) : 0;
+    };
+    auto bcast = [&](int64_t r) -> int64_t {        // the shuffle is what waits for the atomic: done one plan later
+      return counter ? (int64_t)__shfl_sync(0xffffffffu, (unsigned int)r, 0) : r;
+    };
+    auto fetch = [&](int64_t r, float4& bx, int32_t& bi) {
+      bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      bi = 0;
+      if (r < n_rois) {
+        bx = __ldg(&src.boxes[r]);
+        if (src.mode == 1) bi = __ldg(&src.box_ind[r]);
       }
+    };
+    int64_t roi = bcast(draw(0)), roi1 = bcast(draw(1));
+    float4 box, box1;
+    int32_t bi, bi1;
+    fetch(roi, box, bi);
+    for (int64_t k = 2;; ++k) {
+      fetch(roi1, box1, bi1);
+      const int64_t roi2_l0 = draw(k);
+      mbar_wait(&S.plan_empty[ps], pphase ^ 1u);
       RowsPlan& P = S.plan[ps];
       if (roi >= n_rois) {
         if (lane == 0) {
           P.mode = kRowsDone;
           mbar_arrive(&S.plan_full[ps]);
           if (counter) {
-            __threadfence();                                               // ticket draw before the done count
-            if (atomicAdd(&counter[1], 1u) == gridDim.x - 1) {             // every CTA has drawn its last ticket
+            __threadfence();                                               // ticket draws before the done count
+            if (roi2_l0 >= 0 && atomicAdd(&counter[1], 1u) == gridDim.x - 1) { // every CTA has drawn its last ticket
               counter[0] = 0;
               counter[1] = 0;
             }
@@ -485,7 +533,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
         }
         return;
       }
-      rows_make_plan(src, roi, ph, pw, ring_bytes, lane, P, S, level_out);
+      rows_make_plan(src, roi, box, bi, ph, pw, ring_bytes, l2_keep, lane, P, S, level_out);
       if (lane == 0) mbar_arrive(&S.plan_full[ps]);
       if (l2_prefetch && P.mode == kRowsRing) {
         // The planner runs a few ROIs ahead of the ring: pull this ROI's rows into L2 now, so that the ring copies issued
@@ -494,8 +542,8 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
         const size_t row_pitch = (size_t)P.W * kRowsPixelBytes;
         const int32_t nruns = P.nruns, total = P.nr * nruns;
         for (int32_t i = lane; i < total; i += 32) {
-          const int32_t k = i / nruns, j = i - k * nruns;
-          const char* a = gbase + (size_t)P.rows[k] * row_pitch + (size_t)P.run_col[j] * kRowsPixelBytes;
+          const int32_t kk = i / nruns, j = i - kk * nruns;
+          const char* a = gbase + (size_t)P.rows[kk] * row_pitch + (size_t)P.run_col[j] * kRowsPixelBytes;
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)P.run_len[j] * kRowsPixelBytes)
                        : "memory");
         }
@@ -504,14 +552,21 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
         ps = 0;
         pphase ^= 1u;
       }
+      roi = roi1;
+      box = box1;
+      bi = bi1;
+      roi1 = bcast(roi2_l0);
     }
   }
 
   if (warp == n_cwarps) {
     // ------------------------------------------------------------------ issuer: FIFO byte ring
+    // Placement is a pure function of the sequence of row sizes (a row that would straddle the end of the ring starts
+    // over at offset 0), so the consumers derive every entry's offset themselves instead of reading it back.
     uint32_t head = 0, used = 0;
     int32_t e_idx = 0, old_idx = 0, outstanding = 0;
     uint32_t old_phase = 0;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_normal = l2_policy_evict_normal();
     for (;;) {
       mbar_wait(&S.plan_full[ps], pphase);
       const RowsPlan& P = S.plan[ps];
@@ -522,15 +577,18 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
         const uint32_t bytes = P.row_bytes;
         const char* __restrict__ gbase = reinterpret_cast<const char*>(P.base);
         const size_t row_pitch = (size_t)P.W * kRowsPixelBytes;
+        const uint64_t pol = P.keep ? pol_keep : pol_normal;
+        // this lane's column run (nruns <= 16): smem offset inside the row, global offset inside the feature row, bytes
+        const int32_t jr = lane < nruns ? lane : 0;
+        const uint32_t run_dst = (uint32_t)P.run_rank[jr] * kRowsPixelBytes;
+        const size_t run_src = (size_t)P.run_col[jr] * kRowsPixelBytes;
+        const uint32_t run_bytes = (uint32_t)P.run_len[jr] * kRowsPixelBytes;
+        int32_t my_row = lane < nr ? P.rows[lane] : 0;           // rank k's feature row lives on lane k (nr <= 32)
         for (int32_t k = 0; k < nr; ++k) {
-          uint32_t need;
-          bool wrap;
-          for (;;) {
-            if (outstanding == 0) head = 0, used = 0;                  // empty ring: start over at offset 0
-            wrap = head + bytes > ring_bytes;                           // a row never straddles the end of the ring:
-            need = bytes + (wrap ? ring_bytes - head : 0u);             // the tail it skips counts as part of the entry
-            if (used + need <= ring_bytes && outstanding < kRowsEntries) break;
-            mbar_wait(&S.empty[old_idx], old_phase);                    // reclaim the oldest entry (FIFO)
+          const bool wrap = head + bytes > ring_bytes;            // the tail a wrapped row skips counts as part of it
+          const uint32_t need = bytes + (wrap ? ring_bytes - head : 0u);
+          while (used + need > ring_bytes || outstanding == kRowsEntries) {
+            mbar_wait(&S.empty[old_idx], old_phase);              // reclaim the oldest entry (FIFO)
             used -= S.entry_fp[old_idx];
             --outstanding;
             if (++old_idx == kRowsEntries) {
@@ -538,22 +596,17 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
               old_phase ^= 1u;
             }
           }
-          if (wrap) head = 0;
-          const uint32_t off = head;
-          head += bytes;
+          const uint32_t off = wrap ? 0u : head;
+          head = off + bytes;
           used += need;
           ++outstanding;
           if (lane == 0) {
-            S.entry_off[e_idx] = off;
             S.entry_fp[e_idx] = need;
             mbar_expect_tx(&S.full[e_idx], bytes);
           }
           __syncwarp();
-          const char* srow = gbase + (size_t)P.rows[k] * row_pitch;
-          unsigned char* dst = s_ring + off;
-          for (int32_t j = lane; j < nruns; j += 32)
-            bulk_g2s(dst + (size_t)P.run_rank[j] * kRowsPixelBytes, srow + (size_t)P.run_col[j] * kRowsPixelBytes,
-                     (uint32_t)P.run_len[j] * kRowsPixelBytes, &S.full[e_idx]);
+          const char* srow = gbase + (size_t)__shfl_sync(0xffffffffu, my_row, k) * row_pitch;
+          if (lane < nruns) bulk_g2s_hint(s_ring + off + run_dst, srow + run_src, run_bytes, &S.full[e_idx], pol);
           if (++e_idx == kRowsEntries) e_idx = 0;
         }
       }
@@ -567,10 +620,11 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
   }
 
   // -------------------------------------------------------------------- consumers
+  // thread = (x group xg, channel quad q): x bins xg*XPT .. xg*XPT+XPT-1 of every output row, 4 channels.
   const int32_t q = t & 63, xg = t >> 6;
   const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
   int32_t e_idx = 0;
-  uint32_t e_phase = 0;
+  uint32_t e_phase = 0, c_head = 0;              // ring entry, its phase, and the issuer's head replayed locally
   for (;;) {
     mbar_wait(&S.plan_full[ps], pphase);
     const RowsPlan& P = S.plan[ps];
@@ -578,31 +632,38 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
     if (mode == kRowsDone) return;
     float4* __restrict__ o = out + P.roi * ((int64_t)ph * pw * kRowsD4);
     if (mode == kRowsRing) {
-      // this thread's x bins: x = xg + XG * i. Column ranks -> float4 index inside a ring row (+ the channel quad).
+      // Column ranks -> float4 index inside a ring row (+ the channel quad).
       int32_t xcl[XPT], xcr[XPT];
-      float xl[XPT];
+      float xl2[XPT];
       bool xin[XPT];
 #pragma unroll
       for (int i = 0; i < XPT; ++i) {
-        const int32_t x = xg + XG * i;
+        const int32_t x = xg * XPT + i;
         xin[i] = FULL || x < pw;
         const int32_t xs = xin[i] ? x : 0;
         xcl[i] = P.x_cl[xs] * kRowsD4 + q;
         xcr[i] = P.x_cr[xs] * kRowsD4 + q;
-        xl[i] = P.x_lerp[xs];
+        xl2[i] = P.x_lerp[xs];
       }
-      // Row of rank k lives in r0 (k even) or r1 (k odd): the two rows a bin blends have consecutive ranks, so loading
-      // rank k only ever replaces rank k-2. dv = bottom - top of the current row pair, reused by every y that shares it.
-      float4 r0[XPT], r1[XPT], dv[XPT];
+      const int32_t nr = P.nr;
+      const uint32_t row_bytes = P.row_bytes;
+      // Rank-major walk: the y's whose top row has rank k are contiguous (P.yfirst), their bottom row is rank k or k+1.
+      // Rows alternate between RA (even ranks) and RB (odd ranks). bottom - top is recomputed per y: a group holds 1.2 y's
+      // on average, caching the difference would only cost registers.
+      float4 RA[XPT], RB[XPT];
 #pragma unroll
-      for (int i = 0; i < XPT; ++i) r0[i] = r1[i] = dv[i] = ext4;
-      int32_t loaded = -1, dkt = -1, dkb = -1;
+      for (int i = 0; i < XPT; ++i) RA[i] = RB[i] = ext4;
 #define OD_ROWS_LOAD(V)                                                                              \
   do {                                                                                               \
     if (dbg & 2) break;               /* timing experiment: no input stream at all */                \
+    const uint32_t off_ = (c_head + row_bytes > ring_bytes) ? 0u : c_head;                           \
+    c_head = off_ + row_bytes;                                                                       \
     mbar_wait(&S.full[e_idx], e_phase);                                                              \
-    const float4* rowp = reinterpret_cast<const float4*>(s_ring + S.entry_off[e_idx]);               \
-    _Pragma("unroll") for (int i = 0; i < XPT; ++i) V[i] = lerp4p(rowp[xcl[i]], rowp[xcr[i]], xl[i]); \
+    const float4* rowp = reinterpret_cast<const float4*>(s_ring + off_);                             \
+    _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                \
+      const float4 l_ = rowp[xcl[i]], r_ = rowp[xcr[i]];                                             \
+      V[i] = axpy4p(l_, sub4p(r_, l_), xl2[i]);                                                      \
+    }                                                                                                \
     __syncwarp();                                                                                    \
     if (lane == 0) mbar_arrive(&S.empty[e_idx]);                                                     \
     if (++e_idx == kRowsEntries) {                                                                   \
@@ -610,46 +671,42 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
       e_phase ^= 1u;                                                                                 \
     }                                                                                                \
   } while (0)
-#define OD_ROWS_DIFF(B, T)                                                                           \
-  _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                  \
-    sub2(dv[i].x, dv[i].y, B[i].x, B[i].y, T[i].x, T[i].y);                                          \
-    sub2(dv[i].z, dv[i].w, B[i].z, B[i].w, T[i].z, T[i].w);                                          \
+#define OD_ROWS_GROUP(CUR, NXT)                                                                      \
+  {                                                                                                  \
+    const int32_t yend = P.yfirst[k + 1];                                                            \
+    const bool more = k + 1 < nr;                                                                    \
+    if (more) OD_ROWS_LOAD(NXT);                                                                     \
+    _Pragma("unroll 1") while (y < yend) {                                                           \
+      const int2 nxt_ = P.ytab[y + 1];                                                               \
+      const float yl2 = __int_as_float(ent.x);                                                       \
+      if (ent.y) {                    /* top row == bottom row: (top - top) * yl, as the reference */ \
+        _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                            \
+          const float4 v_ = axpy4p(CUR[i], sub4p(CUR[i], CUR[i]), yl2);                              \
+          if ((FULL || xin[i]) && !(dbg & 1)) stg_cs_f4(orow + i * kRowsD4, v_);                     \
+        }                                                                                            \
+      } else {                                                                                       \
+        _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                            \
+          const float4 v_ = axpy4p(CUR[i], sub4p(NXT[i], CUR[i]), yl2);                              \
+          if ((FULL || xin[i]) && !(dbg & 1)) stg_cs_f4(orow + i * kRowsD4, v_);                     \
+        }                                                                                            \
+      }                                                                                              \
+      ent = nxt_;                                                                                    \
+      ++y;                                                                                           \
+      orow += pw * kRowsD4;                                                                          \
+    }                                                                                                \
+    if (!more) break;                                                                                \
+    ++k;                                                                                             \
   }
-#define OD_ROWS_EMIT(T)                                                                              \
-  _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                  \
-    float4 m_, v_;                                                                                   \
-    m_.x = __fmul_rn(dv[i].x, yl);                                                                   \
-    m_.y = __fmul_rn(dv[i].y, yl);                                                                   \
-    m_.z = __fmul_rn(dv[i].z, yl);                                                                   \
-    m_.w = __fmul_rn(dv[i].w, yl);                                                                   \
-    add2(v_.x, v_.y, T[i].x, T[i].y, m_.x, m_.y);                                                    \
-    add2(v_.z, v_.w, T[i].z, T[i].w, m_.z, m_.w);                                                    \
-    if ((FULL || xin[i]) && !(dbg & 1)) stg_cs_f4(orow + i * (XG * kRowsD4), v_);                    \
-  }
-      float4* __restrict__ orow = o + xg * kRowsD4 + q;
-      for (int32_t y = 0; y < ph; ++y, orow += pw * kRowsD4) {
-        const int4 e = P.ytab[y];
-        const int32_t kt = e.x, kb = e.y;
-        const float yl = __int_as_float(e.z);
-        while (loaded < kb) {
-          ++loaded;
-          if (loaded & 1) OD_ROWS_LOAD(r1);
-          else OD_ROWS_LOAD(r0);
-        }
-        if (kt != dkt || kb != dkb) {              // new row pair
-          dkt = kt;
-          dkb = kb;
-          if (kt & 1) {
-            if (kb & 1) { OD_ROWS_DIFF(r1, r1) } else { OD_ROWS_DIFF(r0, r1) }
-          } else {
-            if (kb & 1) { OD_ROWS_DIFF(r1, r0) } else { OD_ROWS_DIFF(r0, r0) }
-          }
-        }
-        if (kt & 1) { OD_ROWS_EMIT(r1) } else { OD_ROWS_EMIT(r0) }
+      float4* __restrict__ orow = o + (xg * XPT) * kRowsD4 + q;
+      int2 ent = P.ytab[0];
+      int32_t y = 0, k = 0;
+      OD_ROWS_LOAD(RA);
+      for (;;) {
+        OD_ROWS_GROUP(RA, RB)
+        OD_ROWS_GROUP(RB, RA)
       }
 #undef OD_ROWS_LOAD
-#undef OD_ROWS_DIFF
-#undef OD_ROWS_EMIT
+#undef OD_ROWS_GROUP
     } else if (mode == kRowsFlat) {   // per-bin path: 4 direct loads per output quad
       const float4* __restrict__ base = reinterpret_cast<const float4*>(P.base);
       const uint32_t W = (uint32_t)P.W;
@@ -745,7 +802,7 @@ crop_pool_bins_kernel(RoiSource src, int64_t total_bins, int32_t oh, int32_t ow,
 struct RowsTuning {
   bool use_rows, dynamic;
   uint32_t ring_bytes;
-  int xpt, cps, min_pool, l2_prefetch, dbg;
+  int xpt, cps, min_pool, l2_prefetch, l2_keep, dbg;
 };
 static int env_int(const char* name, int dflt, int lo, int hi) {
   const char* v = getenv(name);
@@ -764,6 +821,7 @@ static const RowsTuning& rows_tuning() {
     r.min_pool = env_int("OD_ROI_MIN_POOL", 10, 1, 17);
     r.dynamic = env_int("OD_ROI_DYNAMIC", 1, 0, 1) != 0;
     r.l2_prefetch = env_int("OD_ROI_L2_PREFETCH", 0, 0, 1);
+    r.l2_keep = env_int("OD_ROI_L2_KEEP", 0, 0, 2);         // 1: every level evict_last, 2: all but the finest level
     r.dbg = env_int("OD_ROI_TIMING_EXPERIMENT", 0, 0, 3);   // 1: no output stores, 2: no input stream (WRONG RESULTS; timing only)
     return r;
   }();
@@ -786,7 +844,7 @@ static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, 
   if (!sms[dev]) OD_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
   const int64_t grid = n_rois < (int64_t)sms[dev] * tn.cps ? n_rois : (int64_t)sms[dev] * tn.cps;
   OD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)(kRowsD4 * XG + 64)), (size_t)tn.ring_bytes, st, src, n_rois,
-                     ph, pw, XG, tn.ring_bytes, extrap, reinterpret_cast<float4*>(out), level_out, counter, tn.l2_prefetch, tn.dbg));
+                     ph, pw, XG, tn.ring_bytes, extrap, reinterpret_cast<float4*>(out), level_out, counter, tn.l2_prefetch, tn.l2_keep, tn.dbg));
   OD_LAUNCH_CHECK("crop_rows_kernel");
   return OD_OK;
 }
