@@ -413,15 +413,17 @@ def run_ours(args):
         host_sets.append(h)
         dev_sets.append(d)
     h2d_bytes = sum(t.numel() * 4 for k, v in host_sets[0].items() for t in (v if isinstance(v, list) else [v]))
-    pooled7 = torch.empty((1, B * N_ROIS, 7, 7, DEPTH), dtype=torch.float32, device=dev)
-    pooled14 = torch.empty((1, B * N_ROIS, 14, 14, DEPTH), dtype=torch.float32, device=dev)
+    # one set of outputs per input set: with two lanes, two consecutive steps are in flight at the same time
+    pooled7s = [torch.empty((1, B * N_ROIS, 7, 7, DEPTH), dtype=torch.float32, device=dev) for _ in range(NSETS)]
+    pooled14s = [torch.empty((1, B * N_ROIS, 14, 14, DEPTH), dtype=torch.float32, device=dev) for _ in range(NSETS)]
+    pooled7, pooled14 = pooled7s[0], pooled14s[0]
     roi_ev = []
 
     def propose(inp):
         return Proposals(conf, B, inp["probs"], inp["bbox"], anchors).get_proposals()
 
-    def roi7(inp, proposals):
-        pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [7, 7], out=pooled7)
+    def roi7(inp, proposals, s_=0):
+        pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [7, 7], out=pooled7s[s_])
 
     def detect(inp, proposals):
         return DetectionLayer(conf, conf.IMAGE_SHAPE, B, window, proposals, inp["hprobs"], inp["hbbox"]).get_detections()
@@ -429,69 +431,91 @@ def run_ours(args):
     # The layer classes are called unchanged inside torch.cuda.graph: per resident input set, graph A = Proposals,
     # graph B = DetectionLayer, graph C = ROIAlign 7x7. B (a chain of small latency-bound kernels on a few SMs) and C
     # (HBM-bound, all SMs) only depend on the proposals: B replays on a second, high-priority stream next to C. The
-    # 14x14 ROIAlign launch - the roofline kernel, persistent CTAs that fill every SM - stays an eager call after C so
-    # that CUDA events bracket it inside the timed region; the step joins both streams at its end.
+    # 14x14 ROIAlign launch - the roofline kernel - stays an eager call after C so that CUDA events bracket it inside the
+    # timed region; the step joins both streams at its end.
+    # LANES: consecutive steps work on different images and do not depend on each other. With two lanes, step i runs on
+    # lane i % 2 (own streams, own input set, own outputs), so that the latency-bound proposal front of step i+1 (top-k,
+    # NMS mask + scan: ~70 us on a few SMs) runs while the HBM-bound ROIAlign launches of step i stream. Every kernel of
+    # every step still runs inside the timed region; ms_per_step is the total divided by the number of steps.
+    LANES = max(1, min(args.lanes, NSETS))
     graphs_a, graphs_b, graphs_c = [None] * NSETS, [None] * NSETS, [None] * NSETS
     static_prop, static_det = [None] * NSETS, [None] * NSETS
     graph_launches = [0] * NSETS      # kernels captured per step (od_launch_count delta during the captures)
     main_stream = torch.cuda.current_stream()
-    det_stream = torch.cuda.Stream(priority=-1)     # high priority: its small CTAs slip in between ROIAlign CTAs
+    lane_main = [main_stream] + [torch.cuda.Stream() for _ in range(LANES - 1)]
+    lane_det = [torch.cuda.Stream(priority=-1) for _ in range(LANES)]   # high priority: small CTAs slip in between ROIAlign CTAs
+    lane_cap = [torch.cuda.Stream() for _ in range(LANES)]              # capture streams (their workspaces belong to the graphs)
+    det_stream = lane_det[0]
     ev_prop = [torch.cuda.Event() for _ in range(NSETS)]
     ev_det = [torch.cuda.Event() for _ in range(NSETS)]
 
+    def lane_of(s_):
+        return s_ % LANES
+
     def capture_graphs():
-        side = torch.cuda.Stream()
-        for cap_stream in (side, det_stream):        # eager runs on the capture streams: workspaces + constant caches exist
-            cap_stream.wait_stream(main_stream)
-            with torch.cuda.stream(cap_stream):
-                for s_ in range(NSETS):
+        for s_ in range(NSETS):                      # eager runs on the capture streams: workspaces + constant caches exist
+            l_ = lane_of(s_)
+            for cap_stream in (lane_cap[l_], lane_det[l_]):
+                cap_stream.wait_stream(main_stream)
+                with torch.cuda.stream(cap_stream):
                     p_ = propose(dev_sets[s_])
-                    roi7(dev_sets[s_], p_)
+                    roi7(dev_sets[s_], p_, s_)
                     detect(dev_sets[s_], p_)
-            main_stream.wait_stream(cap_stream)
+                main_stream.wait_stream(cap_stream)
         torch.cuda.synchronize()
         for s_ in range(NSETS):
+            l_ = lane_of(s_)
             n0 = L.od_launch_count()
             ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga, stream=side):
+            with torch.cuda.graph(ga, stream=lane_cap[l_]):
                 static_prop[s_] = propose(dev_sets[s_])
-            with torch.cuda.graph(gb, stream=det_stream):
+            with torch.cuda.graph(gb, stream=lane_det[l_]):
                 static_det[s_] = detect(dev_sets[s_], static_prop[s_])
-            with torch.cuda.graph(gc, stream=side):
-                roi7(dev_sets[s_], static_prop[s_])
+            with torch.cuda.graph(gc, stream=lane_cap[l_]):
+                roi7(dev_sets[s_], static_prop[s_], s_)
             graph_launches[s_] = L.od_launch_count() - n0
             graphs_a[s_], graphs_b[s_], graphs_c[s_] = ga, gb, gc
 
     def step(s_, time_roi=False, use_graphs=True):
         inp = dev_sets[s_]
-        if use_graphs and graphs_a[s_] is not None:
-            graphs_a[s_].replay()
-            proposals = static_prop[s_]
-            ev_prop[s_].record(main_stream)
-            with torch.cuda.stream(det_stream):
-                det_stream.wait_event(ev_prop[s_])
-                graphs_b[s_].replay()
-                det = static_det[s_]
-                if world > 1:      # the path's only collective, hidden under the ROIAlign launches
+        lm, ld = lane_main[lane_of(s_)], lane_det[lane_of(s_)]
+        with torch.cuda.stream(lm):
+            if use_graphs and graphs_a[s_] is not None:
+                graphs_a[s_].replay()
+                proposals = static_prop[s_]
+                ev_prop[s_].record(lm)
+                with torch.cuda.stream(ld):
+                    ld.wait_event(ev_prop[s_])
+                    graphs_b[s_].replay()
+                    det = static_det[s_]
+                    if world > 1:      # the path's only collective, hidden under the ROIAlign launches
+                        det = gather_detections(det, batch=world * B)
+                    ev_det[s_].record(ld)
+                graphs_c[s_].replay()
+            else:
+                proposals = propose(inp)
+                roi7(inp, proposals, s_)
+                det = detect(inp, proposals)
+                if world > 1:
                     det = gather_detections(det, batch=world * B)
-                ev_det[s_].record(det_stream)
-            graphs_c[s_].replay()
-        else:
-            proposals = propose(inp)
-            roi7(inp, proposals)
-            det = detect(inp, proposals)
-            if world > 1:
-                det = gather_detections(det, batch=world * B)
-        if time_roi:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [14, 14], out=pooled14)
-        if time_roi:
-            e1.record()
-            roi_ev.append((e0, e1))
-        if use_graphs and graphs_a[s_] is not None:
-            main_stream.wait_event(ev_det[s_])       # join: the step ends when both branches are done
+            if time_roi:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(lm)
+            pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [14, 14], out=pooled14s[s_])
+            if time_roi:
+                e1.record(lm)
+                roi_ev.append((e0, e1))
+            if use_graphs and graphs_a[s_] is not None:
+                lm.wait_event(ev_det[s_])       # join: the step ends when both branches are done
         return det, proposals
+
+    def fork_lanes():      # the lanes start after everything already queued on the main stream
+        for l_ in range(1, LANES):
+            lane_main[l_].wait_stream(main_stream)
+
+    def join_lanes():      # ... and the main stream continues when every lane is done
+        for l_ in range(1, LANES):
+            main_stream.wait_stream(lane_main[l_])
 
     if not args.no_graph:
         capture_graphs()
@@ -511,8 +535,10 @@ def run_ours(args):
     launches0 = L.od_launch_count()
     wall0 = time.time()
     ev0.record()
+    fork_lanes()
     for i in range(args.steps):
         det, proposals = step(i % NSETS, time_roi=True)
+    join_lanes()
     ev1.record()
     torch.cuda.synchronize(); barrier()
     wall1 = time.time()
@@ -522,7 +548,25 @@ def run_ours(args):
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
-    roi14_ms = float(np.mean([a.elapsed_time(b) for a, b in roi_ev]))
+    roi14_ms_lanes = float(np.mean([a.elapsed_time(b) for a, b in roi_ev]))
+
+    # ---- one step at a time (lane i+1 waits for lane i): the step's latency, and the 14x14 ROIAlign launch timed with
+    # nothing of another step running next to it - this is the duration the kernel's roofline is computed from
+    roi14_ms, serial_ms = roi14_ms_lanes, ms_per_step
+    if LANES > 1:
+        del roi_ev[:]
+        n_s = max(5, min(args.steps, 200))
+        sa_, sb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        sa_.record()
+        for i in range(n_s):
+            fork_lanes()
+            step(i % NSETS, time_roi=True)
+            join_lanes()
+        sb_.record()
+        torch.cuda.synchronize(); barrier()
+        serial_ms = max_over_ranks(sa_.elapsed_time(sb_) / n_s)
+        roi14_ms = float(np.mean([a.elapsed_time(b) for a, b in roi_ev]))
 
     # ---- the same step launched eagerly (no CUDA graph), for the record
     eager_ms = None
@@ -533,8 +577,10 @@ def run_ours(args):
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ea.record()
+        fork_lanes()
         for i in range(n_e):
             step(i % NSETS, use_graphs=False)
+        join_lanes()
         eb.record()
         torch.cuda.synchronize()
         eager_ms = max_over_ranks(ea.elapsed_time(eb) / n_e)
@@ -563,6 +609,7 @@ def run_ours(args):
     roof_bytes = []
     for s in range(NSETS):
         _, props = step(s)
+        torch.cuda.synchronize()
         _, lv = pyramid_roi_align(dev_sets[s]["fmaps"], props, conf.IMAGE_SHAPE, [14, 14], out=pooled14, return_levels=True)
         roof_bytes.append(roialign_algorithmic_bytes(props.cpu().numpy(), lv.cpu().numpy(), 14, DEPTH))
     alg = float(np.mean([r["total"] for r in roof_bytes]))
@@ -573,7 +620,12 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": f"{roi_kernel} (PyramidROIAlign 14x14, 2x1000 ROIs)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                "ms_per_launch": roi14_ms}
+                "ms_per_launch": roi14_ms,
+                "measured": "CUDA events around the launch, in this run, steps issued one at a time" if LANES > 1 else
+                            "CUDA events around the launch inside the timed region",
+                "with_two_steps_in_flight": {"ms_per_launch": roi14_ms_lanes, "frac": alg / (roi14_ms_lanes * 1e-3) / 1e9 / peak,
+                                             "note": "the same events inside the headline timed region; the launch shares "
+                                                     "HBM and SMs with the other lane's kernels"} if LANES > 1 else None}
 
     # ---- timed region 2: end to end, inputs in pinned HOST memory. Every step copies all of its inputs H2D (into the
     # buffers the layer classes read), runs the step and reads the detections back D2H. The copy of step i+1 runs on
@@ -597,20 +649,24 @@ def run_ours(args):
             ready[s_].record(copy_stream)
 
     def e2e_loop(n):
+        join_lanes()
         for s_ in range(NSETS):
             consumed[s_].record(main_stream)
         h2d(0)
         out = None
         for i in range(n):
             s_ = i % NSETS
+            lm = lane_main[lane_of(s_)]
             if i + 1 < n:
                 h2d((i + 1) % NSETS)                 # overlaps with this step's kernels
-            main_stream.wait_event(ready[s_])
+            lm.wait_event(ready[s_])
             d, _ = step(s_)
-            det_host[s_].copy_(d[rank * B:(rank + 1) * B], non_blocking=True)   # D2H of this rank's detections
-            consumed[s_].record(main_stream)
-            main_stream.synchronize()                # the caller reads the result of every step
+            with torch.cuda.stream(lm):
+                det_host[s_].copy_(d[rank * B:(rank + 1) * B], non_blocking=True)   # D2H of this rank's detections
+                consumed[s_].record(lm)
+            lm.synchronize()                         # the caller reads the result of every step
             out = det_host[s_]
+        join_lanes()
         return out
 
     e2e_loop(3)
@@ -652,7 +708,7 @@ def run_ours(args):
     # ---- stand-alone ROIAlign on the SURVEY §8d ROI recipe (seed 1234), L2 flushed between launches
     standalone = {}
     if rank == 0:
-        standalone = run_standalone_roialign(torch, dev, conf, dev_sets, pooled7, pooled14, det, peak, ms_per_step,
+        standalone = run_standalone_roialign(torch, dev, conf, dev_sets, pooled7, pooled14, det, peak, serial_ms,
                                              roofline["ms_per_launch"], world, B, NSETS)
 
     extra = None
@@ -665,6 +721,7 @@ def run_ours(args):
     if extra is None:
         extra = {}
     extra["eager_ms_per_step"] = eager_ms
+    extra["ms_per_step_one_at_a_time"] = serial_ms
 
     if rank == 0:
         line = {
@@ -674,7 +731,9 @@ def run_ours(args):
             "config": shared_config(world),
             "launch": "eager, one stream" if args.no_graph else
                       "CUDA graph A (Proposals), then graph B (DetectionLayer, 2nd stream) || graph C (ROIAlign 7x7), "
-                      "then eager ROIAlign 14x14",
+                      "then eager ROIAlign 14x14" + (f"; {LANES} steps in flight (step i on lane i % {LANES}: own streams, "
+                      "inputs and outputs), every kernel of every step inside the timed region" if LANES > 1 else ""),
+            "lanes": LANES,
             "l2": f"{NSETS} rotating input sets; each step reads 2x89 MB of pyramid and writes 0.5 GB of pooled ROIs "
                   f"(> 126 MB L2)",
             "collective": "all_gather(detections) per step" if world > 1 else "none",
@@ -954,6 +1013,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip scaling_b64 and the configs[2]/[3]/stress extras")
     ap.add_argument("--check", action="store_true", help="compare every shard's detections with the CPU oracle")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph)")
+    ap.add_argument("--lanes", type=int, default=2, help="steps in flight (1: strictly one step after the other)")
     ap.add_argument("--kernel-times", action="store_true", help="print per-kernel device times (CUPTI) to stderr")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -207,6 +207,11 @@ int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_level
  * fixed round robin. The caller zero-initialises it ONCE (e.g. cudaMemset after allocating it); every launch leaves it
  * zeroed again. One workspace must not be used by two launches that can run concurrently (one per stream is safe). */
 size_t od_pyramid_roi_align_workspace_bytes(void);
+/* A workspace of ..._bytes_n(B*N) bytes additionally holds a processing order of the ROIs (level by level, top to bottom),
+ * computed by a short pre-pass of every launch, so that ROIs reading the same feature pixels run close in time and every
+ * pixel is fetched from HBM once. Only the first od_pyramid_roi_align_workspace_bytes() bytes must be (and stay) zeroed.
+ * The results do not depend on the order. */
+size_t od_pyramid_roi_align_workspace_bytes_n(int64_t n_rois);
 int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
                                     const DLTensor* rois, int32_t image_h, int32_t image_w,
                                     int32_t pool_h, int32_t pool_w,

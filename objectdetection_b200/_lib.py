@@ -106,6 +106,7 @@ SIGNATURES = {
     "od_pyramid_roi_align_forward": (c_int, [POINTER(_P), c_int32, c_int32, _P, c_int32, c_int32, c_int32, c_int32,
                                              _P, _P, _P]),
     "od_pyramid_roi_align_workspace_bytes": (c_size_t, []),
+    "od_pyramid_roi_align_workspace_bytes_n": (c_size_t, [c_int64]),
     "od_pyramid_roi_align_forward_ws": (c_int, [POINTER(_P), c_int32, c_int32, _P, c_int32, c_int32, c_int32, c_int32,
                                                 _P, _P, _P, c_size_t, _P]),
     "od_crop_and_resize": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, _P, _P]),
@@ -231,6 +232,8 @@ def zeroed_workspace(nbytes: int, device) -> torch.Tensor:
         if torch.cuda.is_current_stream_capturing():
             raise OdHeadError(-6, "the ROIAlign ticket workspace would have to be allocated during CUDA graph capture: "
                                   "run the call once eagerly on the capture stream first")
+        if buf is not None:
+            _retired.append(buf)       # a captured graph may still hold its address
         buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _zero_ws[key] = buf
     return buf

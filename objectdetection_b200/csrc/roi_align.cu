@@ -89,6 +89,7 @@ struct RoiSource {
   const int32_t* box_ind;
   const float* boxes5;
   float fimage_h, fimage_w;
+  const int32_t* order;   // optional (mode 0): processing order of the ROIs, order[j] = ROI handled j-th (roi_order_kernel)
 };
 
 struct __align__(16) BinTaps {  // tap offsets from the image base, in 16-byte units
@@ -225,21 +226,26 @@ __device__ __forceinline__ void bin_table_entry(const RoiSource& src, int64_t ro
   *bi_out = bi;
 }
 
-template <int BINS, int UNROLL, bool POW2>
+template <int BINS, int UNROLL, bool POW2, bool ORDERED>
 __global__ void __launch_bounds__(kBinThreads, OD_BIN_MINB)
 crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_t ph, int32_t pw, int32_t D4,
                  int32_t lgD4, float extrap, float4* __restrict__ out, int32_t* __restrict__ level_out) {
   pdl_prologue();
   __shared__ BinTaps s_taps[BINS];
   __shared__ BinInfo s_info[BINS];
+  __shared__ uint32_t s_obin[ORDERED ? BINS : 1];    // ORDERED: output bin of table entry i (ROIs are walked in src.order)
   const int32_t t = threadIdx.x;
   const int64_t bin0 = (int64_t)blockIdx.x * BINS;
   const int32_t nb = (int32_t)min((int64_t)BINS, total_bins - bin0);
 
   for (int32_t i = t; i < nb; i += kBinThreads) {
     const int64_t fb = bin0 + i;
-    const int64_t roi = fb / bins_per_roi;
+    int64_t roi = fb / bins_per_roi;
     const int32_t bin = (int32_t)(fb - roi * bins_per_roi);
+    if (ORDERED) {
+      roi = __ldg(&src.order[roi]);
+      s_obin[i] = (uint32_t)(roi * bins_per_roi + bin);
+    }
     const int32_t y = bin / pw;
     bin_table_entry(src, roi, y, bin - y * pw, bin == 0, ph, pw, D4, level_out, &s_taps[i], &s_info[i]);
   }
@@ -252,6 +258,7 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
     float4 tl[UNROLL], tr[UNROLL], bl[UNROLL], br[UNROLL];
     float xl[UNROLL], yl[UNROLL];
     uint32_t fl[UNROLL];
+    float4* op[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const int32_t e = min(e0 + u * kBinThreads, total - 1);  // clamped: loads are unconditional
@@ -263,6 +270,7 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
       fl[u] = (uint32_t)(bi.base_flag & 3u);
       xl[u] = bi.xl;
       yl[u] = bi.yl;
+      op[u] = ORDERED ? out + ((int64_t)s_obin[bin] * D4 + c) : o + e;
       tl[u] = ldg_f4(base + (tp.tl + c));
       tr[u] = ldg_f4(base + (tp.tr + c));
       bl[u] = ldg_f4(base + (tp.bl + c));
@@ -275,9 +283,71 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
       const float4 bot = lerp4p(bl[u], br[u], xl[u]);
       float4 v = lerp4p(top, bot, yl[u]);
       if (fl[u] == (uint32_t)kBinExtrapolate) v = ext4;
-      if (e < total && fl[u] != (uint32_t)kBinSkip) stg_cs_f4(o + e, v);
+      if (e < total && fl[u] != (uint32_t)kBinSkip) stg_cs_f4(op[u], v);
     }
   }
+}
+
+// ----------------------------------------------------------------------------- roi_order_kernel
+// Proposals arrive sorted by score, i.e. in random spatial order, while overlapping ROIs read the same feature pixels:
+// walked in index order the ROIs of one image pull ~1.4x the pyramid through DRAM (L2 holds the write stream too),
+// walked level by level and top to bottom every pixel is fetched once (profiles/r2_roialign.md). One CTA per image
+// buckets its ROIs by (pyramid level, 32 bands of the box centre's y) with a shared-memory counting sort and writes the
+// processing order; the order inside a bucket is whatever the atomics produce (any order gives the same output).
+constexpr int kOrderBands = 32;
+constexpr int kOrderThreads = 1024;
+constexpr int kOrderPerThread = 4;               // up to 4096 ROIs per image; beyond that the order is not used
+__global__ void __launch_bounds__(kOrderThreads)
+roi_order_kernel(const float4* __restrict__ boxes, int32_t N, int32_t image_h, int32_t image_w, int32_t min_level,
+                 int32_t num_levels, int32_t* __restrict__ order) {
+  pdl_prologue();
+  __shared__ int32_t s_cnt[OD_MAX_LEVELS * kOrderBands];
+  __shared__ int32_t s_base[OD_MAX_LEVELS * kOrderBands];
+  const int32_t t = threadIdx.x, b = blockIdx.x;
+  const int32_t nb = num_levels * kOrderBands;
+  for (int32_t i = t; i < nb; i += kOrderThreads) s_cnt[i] = 0;
+  __syncthreads();
+  int32_t key[kOrderPerThread], pos[kOrderPerThread];
+#pragma unroll
+  for (int j = 0; j < kOrderPerThread; ++j) {
+    const int32_t n = t + j * kOrderThreads;
+    key[j] = -1;
+    if (n < N) {
+      const float4 bx = __ldg(&boxes[(int64_t)b * N + n]);
+      const int32_t lv = roi_level_of(bx, image_h, image_w, min_level, min_level + num_levels - 1) - min_level;
+      const float yc = 0.5f * (bx.x + bx.z) * (float)kOrderBands;
+      const int32_t band = (yc >= 0.0f) ? (yc < (float)kOrderBands ? (int32_t)yc : kOrderBands - 1) : 0;   // NaN -> 0
+      key[j] = lv * kOrderBands + band;
+      pos[j] = atomicAdd(&s_cnt[key[j]], 1);
+    }
+  }
+  __syncthreads();
+  if (t < 32) {                                   // exclusive scan of <= 256 bucket counts, 8 per lane
+    int32_t c[OD_MAX_LEVELS * kOrderBands / 32], sum = 0;
+#pragma unroll
+    for (int i = 0; i < OD_MAX_LEVELS * kOrderBands / 32; ++i) {
+      const int32_t k = t * (OD_MAX_LEVELS * kOrderBands / 32) + i;
+      c[i] = k < nb ? s_cnt[k] : 0;
+      sum += c[i];
+    }
+    int32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (t >= d) incl += v;
+    }
+    int32_t run = incl - sum;
+#pragma unroll
+    for (int i = 0; i < OD_MAX_LEVELS * kOrderBands / 32; ++i) {
+      const int32_t k = t * (OD_MAX_LEVELS * kOrderBands / 32) + i;
+      if (k < nb) s_base[k] = run;
+      run += c[i];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kOrderPerThread; ++j)
+    if (key[j] >= 0) order[(int64_t)b * N + s_base[key[j]] + pos[j]] = b * N + t + j * kOrderThreads;
 }
 
 // ----------------------------------------------------------------------------- crop_rows_kernel
@@ -305,6 +375,7 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
 constexpr int kRowsMaxPool = 16;
 constexpr int kRowsEntries = 16;                // outstanding ring entries (one feature row each)
 constexpr int kRowsPlans = 3;                   // plans in flight
+constexpr int kRowsStages = 2;                  // output staging slots (1 KiB each) per consumer warp, TMA-store variant
 constexpr int kRowsD4 = 64;                     // D = 256 floats = 64 quads = 1 KiB per pixel
 constexpr uint32_t kRowsPixelBytes = 1024;
 
@@ -462,9 +533,9 @@ __device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi
 
 // counter[0]: next ROI ticket, counter[1]: CTAs that have drawn their last ticket. Both are zero between launches: the
 // last CTA to finish resets them (the workspace is zero-initialised once by its owner).
-template <int XPT, bool FULL, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t XG, uint32_t ring_bytes, float extrap,
+template <bool TMAST>
+__global__ void __launch_bounds__(512, 2)
+crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t ring_bytes, float extrap,
                  float4* __restrict__ out, int32_t* __restrict__ level_out, unsigned int* __restrict__ counter,
                  int32_t l2_prefetch, int32_t l2_keep, int32_t dbg) {
   pdl_prologue();
@@ -472,7 +543,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
   __shared__ RowsShared S;
   const int32_t t = threadIdx.x;
   const int32_t lane = t & 31, warp = t >> 5;
-  const int32_t n_cwarps = 2 * XG, n_cons = kRowsD4 * XG;
+  const int32_t n_cwarps = pw, n_cons = 32 * pw;   // one consumer warp per x bin
   if (t == 0) {
     for (int32_t e = 0; e < kRowsEntries; ++e) {
       mbar_init(&S.full[e], 1);
@@ -500,7 +571,9 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
       return lane == 0 ? (int64_t)atomicAdd(&counter[0], 1u) : 0;
     };
     auto bcast = [&](int64_t r) -> int64_t {        // the shuffle is what waits for the atomic: done one plan later
-      return counter ? (int64_t)__shfl_sync(0xffffffffu, (unsigned int)r, 0) : r;
+      if (counter) r = (int64_t)__shfl_sync(0xffffffffu, (unsigned int)r, 0);
+      if (src.order && r < n_rois) r = (int64_t)__ldg(&src.order[r]);      // ticket -> ROI in processing order
+      return r;
     };
     auto fetch = [&](int64_t r, float4& bx, int32_t& bi) {
       bx = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -620,39 +693,33 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
   }
 
   // -------------------------------------------------------------------- consumers
-  // thread = (x group xg, channel quad q): x bins xg*XPT .. xg*XPT+XPT-1 of every output row, 4 channels.
-  const int32_t q = t & 63, xg = t >> 6;
+  // warp = x bin, lane = channel quads `lane` and `lane + 32`: one output pixel (1 KiB) per warp and output row.
+  // TMAST: the pixel is staged in a per-warp shared-memory slot and leaves through the bulk-copy engine (lane 0 issues
+  // one 1 KiB shared->global copy per output row and only ever waits for the slot it is about to overwrite), so the
+  // number of stores in flight does not depend on registers or on LSU back-pressure.
+  const int32_t x = warp;
   const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
-  int32_t e_idx = 0;
+  float4* const stage = reinterpret_cast<float4*>(s_ring + ring_bytes) + warp * (kRowsStages * kRowsD4);
+  const uint64_t pol_out = l2_policy_evict_first();
+  int32_t e_idx = 0, st = 0;
   uint32_t e_phase = 0, c_head = 0;              // ring entry, its phase, and the issuer's head replayed locally
   for (;;) {
     mbar_wait(&S.plan_full[ps], pphase);
     const RowsPlan& P = S.plan[ps];
     const int32_t mode = P.mode;
-    if (mode == kRowsDone) return;
+    if (mode == kRowsDone) break;
     float4* __restrict__ o = out + P.roi * ((int64_t)ph * pw * kRowsD4);
     if (mode == kRowsRing) {
       // Column ranks -> float4 index inside a ring row (+ the channel quad).
-      int32_t xcl[XPT], xcr[XPT];
-      float xl2[XPT];
-      bool xin[XPT];
-#pragma unroll
-      for (int i = 0; i < XPT; ++i) {
-        const int32_t x = xg * XPT + i;
-        xin[i] = FULL || x < pw;
-        const int32_t xs = xin[i] ? x : 0;
-        xcl[i] = P.x_cl[xs] * kRowsD4 + q;
-        xcr[i] = P.x_cr[xs] * kRowsD4 + q;
-        xl2[i] = P.x_lerp[xs];
-      }
+      const int32_t xcl = P.x_cl[x] * kRowsD4 + lane, xcr = P.x_cr[x] * kRowsD4 + lane;
+      const float xl = P.x_lerp[x];
       const int32_t nr = P.nr;
       const uint32_t row_bytes = P.row_bytes;
       // Rank-major walk: the y's whose top row has rank k are contiguous (P.yfirst), their bottom row is rank k or k+1.
       // Rows alternate between RA (even ranks) and RB (odd ranks). bottom - top is recomputed per y: a group holds 1.2 y's
       // on average, caching the difference would only cost registers.
-      float4 RA[XPT], RB[XPT];
-#pragma unroll
-      for (int i = 0; i < XPT; ++i) RA[i] = RB[i] = ext4;
+      float4 RA[2], RB[2];
+      RA[0] = RA[1] = RB[0] = RB[1] = ext4;
 #define OD_ROWS_LOAD(V)                                                                              \
   do {                                                                                               \
     if (dbg & 2) break;               /* timing experiment: no input stream at all */                \
@@ -660,9 +727,9 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
     c_head = off_ + row_bytes;                                                                       \
     mbar_wait(&S.full[e_idx], e_phase);                                                              \
     const float4* rowp = reinterpret_cast<const float4*>(s_ring + off_);                             \
-    _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                                \
-      const float4 l_ = rowp[xcl[i]], r_ = rowp[xcr[i]];                                             \
-      V[i] = axpy4p(l_, sub4p(r_, l_), xl2[i]);                                                      \
+    _Pragma("unroll") for (int i = 0; i < 2; ++i) {                                                  \
+      const float4 l_ = rowp[xcl + 32 * i], r_ = rowp[xcr + 32 * i];                                 \
+      V[i] = axpy4p(l_, sub4p(r_, l_), xl);                                                          \
     }                                                                                                \
     __syncwarp();                                                                                    \
     if (lane == 0) mbar_arrive(&S.empty[e_idx]);                                                     \
@@ -671,6 +738,24 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
       e_phase ^= 1u;                                                                                 \
     }                                                                                                \
   } while (0)
+#define OD_ROWS_PUT(V0, V1)                                                                          \
+  if (TMAST) {                                                                                       \
+    float4* sp_ = stage + st * kRowsD4;                                                              \
+    if (lane == 0) bulk_wait_read<kRowsStages - 1>();   /* the copy that last read this slot is done */ \
+    __syncwarp();                                                                                    \
+    sp_[lane] = V0;                                                                                  \
+    sp_[lane + 32] = V1;                                                                             \
+    fence_proxy_async_smem();                                                                        \
+    __syncwarp();                                                                                    \
+    if (lane == 0) {                                                                                 \
+      if (!(dbg & 1)) bulk_s2g_hint(orow, sp_, kRowsPixelBytes, pol_out);                            \
+      bulk_commit();                                                                                 \
+    }                                                                                                \
+    if (++st == kRowsStages) st = 0;                                                                 \
+  } else if (!(dbg & 1)) {                                                                           \
+    stg_cs_f4(orow + lane, V0);                                                                      \
+    stg_cs_f4(orow + lane + 32, V1);                                                                 \
+  }
 #define OD_ROWS_GROUP(CUR, NXT)                                                                      \
   {                                                                                                  \
     const int32_t yend = P.yfirst[k + 1];                                                            \
@@ -678,18 +763,16 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
     if (more) OD_ROWS_LOAD(NXT);                                                                     \
     _Pragma("unroll 1") while (y < yend) {                                                           \
       const int2 nxt_ = P.ytab[y + 1];                                                               \
-      const float yl2 = __int_as_float(ent.x);                                                       \
+      const float yl = __int_as_float(ent.x);                                                        \
+      float4 v0_, v1_;                                                                               \
       if (ent.y) {                    /* top row == bottom row: (top - top) * yl, as the reference */ \
-        _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                            \
-          const float4 v_ = axpy4p(CUR[i], sub4p(CUR[i], CUR[i]), yl2);                              \
-          if ((FULL || xin[i]) && !(dbg & 1)) stg_cs_f4(orow + i * kRowsD4, v_);                     \
-        }                                                                                            \
+        v0_ = axpy4p(CUR[0], sub4p(CUR[0], CUR[0]), yl);                                             \
+        v1_ = axpy4p(CUR[1], sub4p(CUR[1], CUR[1]), yl);                                             \
       } else {                                                                                       \
-        _Pragma("unroll") for (int i = 0; i < XPT; ++i) {                                            \
-          const float4 v_ = axpy4p(CUR[i], sub4p(NXT[i], CUR[i]), yl2);                              \
-          if ((FULL || xin[i]) && !(dbg & 1)) stg_cs_f4(orow + i * kRowsD4, v_);                     \
-        }                                                                                            \
+        v0_ = axpy4p(CUR[0], sub4p(NXT[0], CUR[0]), yl);                                             \
+        v1_ = axpy4p(CUR[1], sub4p(NXT[1], CUR[1]), yl);                                             \
       }                                                                                              \
+      OD_ROWS_PUT(v0_, v1_)                                                                          \
       ent = nxt_;                                                                                    \
       ++y;                                                                                           \
       orow += pw * kRowsD4;                                                                          \
@@ -697,7 +780,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
     if (!more) break;                                                                                \
     ++k;                                                                                             \
   }
-      float4* __restrict__ orow = o + (xg * XPT) * kRowsD4 + q;
+      float4* __restrict__ orow = o + x * kRowsD4;    // this warp's pixel of output row 0
       int2 ent = P.ytab[0];
       int32_t y = 0, k = 0;
       OD_ROWS_LOAD(RA);
@@ -706,6 +789,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
         OD_ROWS_GROUP(RB, RA)
       }
 #undef OD_ROWS_LOAD
+#undef OD_ROWS_PUT
 #undef OD_ROWS_GROUP
     } else if (mode == kRowsFlat) {   // per-bin path: 4 direct loads per output quad
       const float4* __restrict__ base = reinterpret_cast<const float4*>(P.base);
@@ -714,16 +798,16 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
       for (int32_t e = t; e < total; e += n_cons) {
         const int32_t bin = e >> 6;
         const uint32_t c = (uint32_t)(e & 63);
-        const int32_t y = bin / pw, x = bin - y * pw;
+        const int32_t y = bin / pw, xb = bin - y * pw;
         float4 v = ext4;
-        if (P.y_ok[y] && P.x_ok[x]) {
+        if (P.y_ok[y] && P.x_ok[xb]) {
           const uint32_t top = (uint32_t)P.y_top[y], bot = (uint32_t)P.y_bot[y];
-          const uint32_t left = (uint32_t)P.x_left[x], right = (uint32_t)P.x_right[x];
+          const uint32_t left = (uint32_t)P.x_left[xb], right = (uint32_t)P.x_right[xb];
           const float4 tl = ldg_f4(base + ((top * W + left) * kRowsD4 + c));
           const float4 tr = ldg_f4(base + ((top * W + right) * kRowsD4 + c));
           const float4 bl = ldg_f4(base + ((bot * W + left) * kRowsD4 + c));
           const float4 br = ldg_f4(base + ((bot * W + right) * kRowsD4 + c));
-          const float xl = P.x_lerp[x];
+          const float xl = P.x_lerp[xb];
           v = lerp4p(lerp4p(tl, tr, xl), lerp4p(bl, br, xl), P.y_lerp[y]);
         }
         stg_cs_f4(o + e, v);
@@ -736,6 +820,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t 
       pphase ^= 1u;
     }
   }
+  if (TMAST && lane == 0) bulk_wait_read<0>();        // the staging slots must outlive the copies that read them
 }
 
 // FasterRCNN roi_pool (fastrcnn.py:22-70): crop_and_resize to (2*oh) x (2*ow) fused with max_pool 2x2 / stride 2.
@@ -797,12 +882,13 @@ crop_pool_bins_kernel(RoiSource src, int64_t total_bins, int32_t oh, int32_t ow,
 // ----------------------------------------------------------------------------- host side
 // Tunables of the TMA-staged kernel, read once from the environment (A/B runs on one box without rebuilding):
 //   OD_ROI_KERNEL=flat   forces crop_bins_kernel;       OD_ROI_MIN_POOL  smallest max(pool_h, pool_w) served (default 10);
-//   OD_ROI_RING_KB       shared-memory ring per CTA (default 64);   OD_ROI_CPS  persistent CTAs per SM (default 2);
-//   OD_ROI_XPT = 1|2|4   x bins per consumer thread (default 2);    OD_ROI_DYNAMIC=0  static round robin even with a workspace.
+//   OD_ROI_RING_KB       shared-memory ring per CTA (default: what is left of the SM's shared memory for OD_ROI_CPS CTAs);
+//   OD_ROI_CPS           persistent CTAs per SM (default 2);    OD_ROI_TMA_STORE=1  staged bulk (TMA) stores instead of plain
+//   streaming stores;    OD_ROI_DYNAMIC=0  static round robin even with a workspace;   OD_ROI_ORDER=1  ROI order pre-pass.
 struct RowsTuning {
-  bool use_rows, dynamic;
-  uint32_t ring_bytes;
-  int xpt, cps, min_pool, l2_prefetch, l2_keep, dbg;
+  bool use_rows, dynamic, tma_store;
+  int ring_kb;
+  int cps, min_pool, l2_prefetch, l2_keep, dbg;
 };
 static int env_int(const char* name, int dflt, int lo, int hi) {
   const char* v = getenv(name);
@@ -814,12 +900,11 @@ static const RowsTuning& rows_tuning() {
     RowsTuning r;
     const char* k = getenv("OD_ROI_KERNEL");
     r.use_rows = !(k && strcmp(k, "flat") == 0);
-    r.ring_bytes = (uint32_t)env_int("OD_ROI_RING_KB", 64, 32, 200) * 1024u;
-    const int xv = env_int("OD_ROI_XPT", 2, 1, 4);
-    r.xpt = (xv == 1 || xv == 4) ? xv : 2;
+    r.ring_kb = env_int("OD_ROI_RING_KB", 0, 0, 200);       // 0: derived from the CTA count per SM
     r.cps = env_int("OD_ROI_CPS", 2, 1, 8);
     r.min_pool = env_int("OD_ROI_MIN_POOL", 10, 1, 17);
     r.dynamic = env_int("OD_ROI_DYNAMIC", 1, 0, 1) != 0;
+    r.tma_store = env_int("OD_ROI_TMA_STORE", 0, 0, 1) != 0;   // measured slower (profiles/r2_roialign.md): opt-in
     r.l2_prefetch = env_int("OD_ROI_L2_PREFETCH", 0, 0, 1);
     r.l2_keep = env_int("OD_ROI_L2_KEEP", 0, 0, 2);         // 1: every level evict_last, 2: all but the finest level
     r.dbg = env_int("OD_ROI_TIMING_EXPERIMENT", 0, 0, 3);   // 1: no output stores, 2: no input stream (WRONG RESULTS; timing only)
@@ -828,23 +913,30 @@ static const RowsTuning& rows_tuning() {
   return t;
 }
 
-template <int XPT, bool FULL, int MAXT, int MINB>
-static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t XG, const RowsTuning& tn,
+template <bool TMAST>
+static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, const RowsTuning& tn,
                               float extrap, float* out, int32_t* level_out, unsigned int* counter, cudaStream_t st) {
-  auto kern = crop_rows_kernel<XPT, FULL, MAXT, MINB>;
+  auto kern = crop_rows_kernel<TMAST>;
   static uint32_t configured[64] = {0};    // dynamic shared memory opted in, per device
   static int sms[64] = {0};
   int dev = 0;
   OD_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) OD_FAIL(OD_ERR_DEVICE, "device index %d not supported", dev);
-  if (configured[dev] < tn.ring_bytes) {
-    OD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tn.ring_bytes));
-    configured[dev] = tn.ring_bytes;
+  // shared memory per CTA: 227 KiB per SM shared by `cps` CTAs, minus the static part (plans, barriers) and 1 KiB that the
+  // hardware reserves per CTA; the staging slots of the TMA-store variant come out of the same budget
+  const uint32_t stage_bytes = TMAST ? (uint32_t)pw * kRowsStages * kRowsPixelBytes : 0u;
+  uint32_t ring_bytes = tn.ring_kb ? (uint32_t)tn.ring_kb * 1024u
+                                   : ((227u * 1024u) / (uint32_t)tn.cps - 6u * 1024u - stage_bytes) & ~1023u;
+  const uint32_t dyn = ring_bytes + stage_bytes;
+  if (dyn > 220u * 1024u) OD_FAIL(OD_ERR_PARAM, "OD_ROI_RING_KB too large: %u bytes of dynamic shared memory", dyn);
+  if (configured[dev] < dyn) {
+    OD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    configured[dev] = dyn;
   }
   if (!sms[dev]) OD_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
   const int64_t grid = n_rois < (int64_t)sms[dev] * tn.cps ? n_rois : (int64_t)sms[dev] * tn.cps;
-  OD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)(kRowsD4 * XG + 64)), (size_t)tn.ring_bytes, st, src, n_rois,
-                     ph, pw, XG, tn.ring_bytes, extrap, reinterpret_cast<float4*>(out), level_out, counter, tn.l2_prefetch, tn.l2_keep, tn.dbg));
+  OD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)(32 * pw + 64)), (size_t)dyn, st, src, n_rois, ph, pw,
+                     ring_bytes, extrap, reinterpret_cast<float4*>(out), level_out, counter, tn.l2_prefetch, tn.l2_keep, tn.dbg));
   OD_LAUNCH_CHECK("crop_rows_kernel");
   return OD_OK;
 }
@@ -855,28 +947,29 @@ static int launch_crop_rows(const RoiSource& src, int64_t n_rois, int32_t ph, in
                             int32_t* level_out, unsigned int* counter, cudaStream_t st) {
   const RowsTuning& tn = rows_tuning();
   const int32_t pmax = ph > pw ? ph : pw;
-  if (!tn.use_rows || D != 4 * kRowsD4 || pmax > kRowsMaxPool || pmax < tn.min_pool || src.mode > 1) return 1;
+  // one consumer warp per x bin + issuer + planner in a 512-thread CTA: pool widths up to 14
+  if (!tn.use_rows || D != 4 * kRowsD4 || ph > kRowsMaxPool || pw > 14 || pmax < tn.min_pool || src.mode > 1) return 1;
   if (n_rois + 4096 > 0x7FFFFFFFll) return 1;
   if (!tn.dynamic) counter = nullptr;
-  int xpt = tn.xpt;
-  if (xpt == 1 && pw > 15) xpt = 2;
-  if (xpt == 2 && pw > 14) xpt = 4;
-  const int32_t XG = (pw + xpt - 1) / xpt;      // consumer threads = 64 * XG (+ issuer warp + planner warp)
-  const bool full = XG * xpt == pw;
-#define OD_ROWS_DISPATCH(X, T, M)                                                                                       \
-  return full ? launch_crop_rows_t<X, true, T, M>(src, n_rois, ph, pw, XG, tn, extrap, out, level_out, counter, st)  \
-              : launch_crop_rows_t<X, false, T, M>(src, n_rois, ph, pw, XG, tn, extrap, out, level_out, counter, st)
-  if (xpt == 1 && pw > 7) OD_ROWS_DISPATCH(1, 1024, 1);
-  if (xpt == 1) OD_ROWS_DISPATCH(1, 512, 2);
-  if (xpt == 2) OD_ROWS_DISPATCH(2, 512, 2);
-  OD_ROWS_DISPATCH(4, 320, 2);
-#undef OD_ROWS_DISPATCH
+  return tn.tma_store ? launch_crop_rows_t<true>(src, n_rois, ph, pw, tn, extrap, out, level_out, counter, st)
+                      : launch_crop_rows_t<false>(src, n_rois, ph, pw, tn, extrap, out, level_out, counter, st);
 }
 
-static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
-                            float* out, int32_t* level_out, cudaStream_t st, unsigned int* counter = nullptr) {
+static int launch_crop_bins(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
+                            float* out, int32_t* level_out, cudaStream_t st, unsigned int* counter = nullptr,
+                            int32_t* order_buf = nullptr) {
   if (n_rois == 0) return OD_OK;
   const int32_t D4 = D / 4;
+  // processing order (PyramidROIAlign with a sized workspace, enough ROIs for the order to matter, D = 256 paths only)
+  static const int use_order = env_int("OD_ROI_ORDER", 0, 0, 1);   // measured neutral (profiles/r2_roialign.md): opt-in
+  src.order = nullptr;
+  if (use_order && order_buf && src.mode == 0 && D == 4 * kRowsD4 && n_rois >= 512 && n_rois <= 0x7FFFFFFFll &&
+      src.rois_per_image <= kOrderThreads * kOrderPerThread) {
+    OD_CUDA(launch_pdl(roi_order_kernel, dim3((unsigned)src.batch), dim3(kOrderThreads), 0, st, src.boxes, src.rois_per_image,
+                       src.image_h, src.image_w, src.min_level, src.num_levels, order_buf));
+    OD_LAUNCH_CHECK("roi_order_kernel");
+    src.order = order_buf;
+  }
   const int64_t bins_per_roi = (int64_t)ph * pw;
   if (bins_per_roi > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "pool shape %dx%d too large", ph, pw);
   const int64_t total_bins = n_rois * bins_per_roi;
@@ -898,8 +991,12 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
     const int64_t grid = (total_bins + BINS - 1) / BINS;
     if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
     // 32 bins per 128-thread CTA, 2 quads in flight per thread: best of the sweeps in profiles/r1_crop_variants.md
-    OD_CUDA(launch_pdl(crop_bins_kernel<BINS, OD_BIN_UNROLL, true>, dim3((unsigned)grid), dim3(kBinThreads), 0, st,
-        src, total_bins, (int32_t)bins_per_roi, ph, pw, D4, lg, extrap, reinterpret_cast<float4*>(out), level_out));
+    if (src.order)
+      OD_CUDA(launch_pdl(crop_bins_kernel<BINS, OD_BIN_UNROLL, true, true>, dim3((unsigned)grid), dim3(kBinThreads), 0, st,
+          src, total_bins, (int32_t)bins_per_roi, ph, pw, D4, lg, extrap, reinterpret_cast<float4*>(out), level_out));
+    else
+      OD_CUDA(launch_pdl(crop_bins_kernel<BINS, OD_BIN_UNROLL, true, false>, dim3((unsigned)grid), dim3(kBinThreads), 0, st,
+          src, total_bins, (int32_t)bins_per_roi, ph, pw, D4, lg, extrap, reinterpret_cast<float4*>(out), level_out));
   } else {
     // thin or non-power-of-two depth: more bins per CTA so that the table build is amortised
     constexpr int BINS = 512;
@@ -907,10 +1004,10 @@ static int launch_crop_bins(const RoiSource& src, int64_t n_rois, int32_t ph, in
     const int64_t grid = (total_bins + BINS - 1) / BINS;
     if (grid > 0x7FFFFFFFll) OD_FAIL(OD_ERR_PARAM, "too many bins: %lld", (long long)total_bins);
     if (lg >= 0)
-      crop_bins_kernel<BINS, 2, true><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw,
+      crop_bins_kernel<BINS, 2, true, false><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw,
                                                                            D4, lg, extrap, reinterpret_cast<float4*>(out), level_out);
     else
-      crop_bins_kernel<BINS, 2, false><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw,
+      crop_bins_kernel<BINS, 2, false, false><<<(unsigned)grid, kBinThreads, 0, st>>>(src, total_bins, (int32_t)bins_per_roi, ph, pw,
                                                                             D4, lg, extrap, reinterpret_cast<float4*>(out), level_out);
   }
   OD_LAUNCH_CHECK("crop_bins_kernel");
@@ -924,6 +1021,9 @@ using namespace od;
 extern "C" {
 
 size_t od_pyramid_roi_align_workspace_bytes(void) { return 256; }
+size_t od_pyramid_roi_align_workspace_bytes_n(int64_t n_rois) {
+  return 256 + align_up((size_t)(n_rois > 0 ? n_rois : 0) * sizeof(int32_t), 256);
+}
 
 int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
                                     const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t pool_h,
@@ -979,8 +1079,11 @@ int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_le
   src.boxes = dptr<float4>(rois);
   if (ws && (ws_bytes < od_pyramid_roi_align_workspace_bytes() || reinterpret_cast<uintptr_t>(ws) % 8))
     OD_FAIL(OD_ERR_WORKSPACE, "workspace must be 8-byte aligned and at least %zu bytes", od_pyramid_roi_align_workspace_bytes());
+  // workspace: [0,256) the ticket counters (stay zeroed), [256, 256 + 4*B*N) the ROI processing order (scratch)
+  int32_t* order_buf = (ws && ws_bytes >= od_pyramid_roi_align_workspace_bytes_n(total))
+                           ? reinterpret_cast<int32_t*>(static_cast<char*>(ws) + 256) : nullptr;
   return launch_crop_bins(src, total, pool_h, pool_w, (int32_t)D, 0.0f, dptr<float>(pooled), dptr<int32_t>(roi_level), st,
-                          static_cast<unsigned int*>(ws));
+                          static_cast<unsigned int*>(ws), order_buf);
 }
 
 int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,

@@ -36,7 +36,7 @@ def pyramid_roi_align(feature_maps, proposals, image_shape, pool_shape, levels=(
     dl = _lib.DL()
     ptrs = (ctypes.c_void_p * len(fmaps))(*[dl(f) for f in fmaps])
     L = _lib.lib()
-    ws = _lib.zeroed_workspace(L.od_pyramid_roi_align_workspace_bytes(), dev)     # ROI ticket counter (stays zeroed)
+    ws = _lib.zeroed_workspace(L.od_pyramid_roi_align_workspace_bytes_n(B * N), dev)   # ticket counter (stays zeroed) + ROI order
     _lib.check(L.od_pyramid_roi_align_forward_ws(ptrs, len(fmaps), min(levels), dl(rois), int(image_shape[0]),
                                                  int(image_shape[1]), ph, pw, dl(out), dl(lv), ws.data_ptr(),
                                                  ws.numel(), _lib.stream_ptr(dev)), "od_pyramid_roi_align_forward_ws")

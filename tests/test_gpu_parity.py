@@ -394,7 +394,7 @@ def test_roi_pooling_d256_rows_kernel_edge_cases(pool):
     _roi_align_check(fmaps, props, 1024, pool)                                # again: the ticket counter was left zeroed
     from objectdetection_b200 import _lib
     torch.cuda.synchronize()
-    assert all(int(w.count_nonzero()) == 0 for w in _lib._zero_ws.values())
+    assert all(int(w[:256].count_nonzero()) == 0 for w in _lib._zero_ws.values())   # the ticket counters; the rest is scratch
 
 
 def test_crop_and_resize_d256_rows_kernel():
