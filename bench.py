@@ -403,7 +403,7 @@ def run_ours(args):
         return float(t.item())
 
     # ---- inputs: NSETS rotating sets, each in pinned host memory and resident in HBM
-    NSETS = 2
+    NSETS = max(2, min(int(args.lanes), 4))
     host_sets, dev_sets = [], []
     for s in range(NSETS):
         raw = synth_inputs(1000 + 17 * rank + s, B, A)
@@ -446,8 +446,12 @@ def run_ours(args):
     lane_det = [torch.cuda.Stream(priority=-1) for _ in range(LANES)]   # high priority: small CTAs slip in between ROIAlign CTAs
     lane_cap = [torch.cuda.Stream() for _ in range(LANES)]              # capture streams (their workspaces belong to the graphs)
     det_stream = lane_det[0]
+    # N > 1: every all_gather of every lane goes through ONE stream, in step order - collectives of one NCCL communicator
+    # must be enqueued in the same order on all ranks and must not run concurrently with each other
+    gather_stream = torch.cuda.Stream(priority=-1) if world > 1 else None
     ev_prop = [torch.cuda.Event() for _ in range(NSETS)]
     ev_det = [torch.cuda.Event() for _ in range(NSETS)]
+    ev_det_local = [torch.cuda.Event() for _ in range(NSETS)]
 
     def lane_of(s_):
         return s_ % LANES
@@ -489,15 +493,25 @@ def run_ours(args):
                     graphs_b[s_].replay()
                     det = static_det[s_]
                     if world > 1:      # the path's only collective, hidden under the ROIAlign launches
+                        ev_det_local[s_].record(ld)
+                    else:
+                        ev_det[s_].record(ld)
+                if world > 1:
+                    with torch.cuda.stream(gather_stream):
+                        gather_stream.wait_event(ev_det_local[s_])
                         det = gather_detections(det, batch=world * B)
-                    ev_det[s_].record(ld)
+                        ev_det[s_].record(gather_stream)
                 graphs_c[s_].replay()
             else:
                 proposals = propose(inp)
                 roi7(inp, proposals, s_)
                 det = detect(inp, proposals)
                 if world > 1:
-                    det = gather_detections(det, batch=world * B)
+                    ev_det_local[s_].record(lm)
+                    with torch.cuda.stream(gather_stream):
+                        gather_stream.wait_event(ev_det_local[s_])
+                        det = gather_detections(det, batch=world * B)
+                        ev_det[s_].record(gather_stream)
             if time_roi:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(lm)
@@ -505,7 +519,7 @@ def run_ours(args):
             if time_roi:
                 e1.record(lm)
                 roi_ev.append((e0, e1))
-            if use_graphs and graphs_a[s_] is not None:
+            if (use_graphs and graphs_a[s_] is not None) or world > 1:
                 lm.wait_event(ev_det[s_])       # join: the step ends when both branches are done
         return det, proposals
 

@@ -107,6 +107,28 @@ struct Workspace {
   bool ok() const { return dry || off <= size; }
 };
 
+// ----------------------------------------------------------------------------- debug bounds build
+// compute-sanitizer is not available on the GPU pool, so the index-heavy kernels carry their own checks: a library
+// built with -DOD_DEBUG_BOUNDS (build.build_variant("dbg", ["OD_DEBUG_BOUNDS"]), selected with ODHEAD_LIB) verifies
+// every data-dependent index into shared-memory tables, rings, bitmaps and workspace arrays and traps (with a printf
+// naming the site) on the first violation; the -m gpu suite is run against it once per round (profiles/). In the
+// product build the macros expand to nothing.
+#ifdef OD_DEBUG_BOUNDS
+#define OD_DBG_ASSERT(cond, what)                                                                              \
+  do {                                                                                                         \
+    if (!(cond)) {                                                                                             \
+      printf("OD_DEBUG_BOUNDS %s:%d: %s  [block (%d,%d,%d) thread %d]\n", __FILE__, __LINE__, what, (int)blockIdx.x, \
+             (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);                                              \
+      __trap();                                                                                                \
+    }                                                                                                          \
+  } while (0)
+#else
+#define OD_DBG_ASSERT(cond, what) \
+  do {                            \
+  } while (0)
+#endif
+#define OD_DBG_IDX(i, n) OD_DBG_ASSERT((long long)(i) >= 0 && (long long)(i) < (long long)(n), #i " in [0, " #n ")")
+
 // ----------------------------------------------------------------------------- programmatic dependent launch
 // The proposal front is a chain of ~12 short kernels. Launched with programmatic stream serialisation, the CTAs of kernel
 // N+1 become resident while kernel N still runs and block in griddepcontrol.wait until N has completed and flushed, so

@@ -123,6 +123,7 @@ det_rank_gather_kernel(const unsigned long long* __restrict__ keys, const float4
     for (int q = 1; q < kParts; ++q) rank += partial[threadIdx.x + q * kDetRankMine];
     const bool valid = (mine >> 48) != 0ull;
     const int n = (int)(0xFFFFu - (uint32_t)(mine & 0xFFFFull));
+    OD_DBG_IDX(rank, N);
     sorted_keys[(int64_t)b * n_pow2 + rank] = valid ? mine : 0ull;
     sorted_boxes[(int64_t)b * N + rank] = valid ? clipped[(int64_t)b * N + n] : make_float4(0.f, 0.f, 0.f, 0.f);
     group[(int64_t)b * N + rank] = valid ? cls[(int64_t)b * N + n] : -1;
@@ -212,6 +213,7 @@ det_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* 
         const uint32_t n = 0xFFFFu - (uint32_t)(k & 0xFFFFull);
         const uint32_t skey = (uint32_t)((k >> 16) & 0xFFFFFFFFull);
         out = ((unsigned long long)skey << 32) | (unsigned long long)(0xFFFFFFFFu - n);
+        OD_DBG_IDX(n, N);
         if (nms_keep_mask) nms_keep_mask[(int64_t)b * N + n] = 1;
       }
     }
@@ -225,7 +227,10 @@ det_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* 
       if (w < warp) off += c;
       total += c;
     }
-    if (out != 0ull) fkeys[off + __popc(bal & ((1u << lane) - 1u))] = out;
+    if (out != 0ull) {
+      OD_DBG_IDX(off + __popc(bal & ((1u << lane) - 1u)), n_pow2);
+      fkeys[off + __popc(bal & ((1u << lane) - 1u))] = out;
+    }
     m += total;
     __syncthreads();
   }
@@ -240,6 +245,7 @@ det_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* 
       const float4 bx = clipped[(int64_t)b * N + n];
       float* row = det + (int64_t)rank * 6;
       row[0] = bx.x; row[1] = bx.y; row[2] = bx.z; row[3] = bx.w;
+      OD_DBG_IDX(n, N);
       row[4] = (float)cls[(int64_t)b * N + n];
       row[5] = score[(int64_t)b * N + n];
     }

@@ -121,9 +121,11 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ nu
     if (cb == rb) bits &= (r == 63) ? 0ull : ~((2ull << r) - 1ull);   // only j > i
     if (!row_ok) bits = 0ull;
     if (cb != rb) {
+      OD_DBG_IDX(cb, Ws);
       if (row_ok) mask[((int64_t)b * K + i) * Ws + cb] = bits;
     } else {
       // diagonal tile, stored transposed: word jj, bit r = "box r of this chunk suppresses box jj"
+      OD_DBG_IDX(cb, W);
       uint32_t* dt = reinterpret_cast<uint32_t*>(diagT + ((int64_t)b * W + cb) * 64);
       const int warp = (t >> 5) & 1, lane = t & 31;
 #pragma unroll 8
@@ -295,6 +297,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
         }
       }
       if (lane == 0) {
+        OD_DBG_ASSERT(!(own_lo | own_hi) || (c >= 0 && c < Wr), "carried bits beyond the removed bitmap");
         if (own_lo | own_hi) smem_or64(&removed[c], ((unsigned long long)own_hi << 32) | own_lo);   // round boundary: the carried bitmap must be complete
         pipe_out[0] = kept_total;
         pipe_out[1] = c_waited;
@@ -340,6 +343,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
             const int r = lane + 32 * h;
             if ((kept >> r) & 1ull) {
               const int pos = base + __popcll(kept & ((1ull << r) - 1ull));
+              OD_DBG_IDX(pos, max_out);
+              OD_DBG_IDX(c * 64 + r, K);
               if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = c * 64 + r;
               if (keep_flag) keep_flag[(int64_t)b * K + c * 64 + r] = 1;
             }
@@ -361,6 +366,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
 #pragma unroll
                 for (int r = 0; r < 16; ++r) acc |= v[r] & (0ull - (unsigned long long)((kbits >> (r0 + r)) & 1u));
               }
+              OD_DBG_IDX(w, Wr);
               smem_or64(&removed[w], acc);
             }
         }
@@ -414,6 +420,8 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
     if (kept != 0ull) {
       if (tid < 64 && ((kept >> tid) & 1ull)) {
         const int pos = kept_total + __popcll(kept & ((1ull << tid) - 1ull));
+        OD_DBG_IDX(pos, max_out);
+        OD_DBG_IDX(c * 64 + tid, K);
         if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = c * 64 + tid;
         if (keep_flag) keep_flag[(int64_t)b * K + c * 64 + tid] = 1;
       }
@@ -445,6 +453,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned long
               acc1 |= ((kb >> r) & 1u) ? v1[r] : 0ull;
             }
           }
+          OD_DBG_IDX(w0, Wr);
           removed[w0] |= acc0;
           if (w1 < Wn) removed[w1] |= acc1;
         }
@@ -578,6 +587,7 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
       while (bits) {
         const int r = __ffsll((long long)bits) - 1;
         bits &= bits - 1ull;
+        OD_DBG_IDX(base, kWideBatch * 64);
         rows_s[base++] = (c + lane) * 64 + r;
       }
       if (lane == 31) ctl[2] = incl;
@@ -612,6 +622,7 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
 #pragma unroll
           for (int u = 0; u < 8; ++u) acc |= v[u];
         }
+        OD_DBG_IDX(j, S);
         smem_or64(&removed[j], acc);
       }
     }
@@ -641,6 +652,7 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
       }
       const int allow = max_out - kept_total;
       while (__popcll(kept) > allow) kept &= ~(1ull << (63 - __clzll((long long)kept)));
+      OD_DBG_IDX(c - lo, kWideMaxS);
       if (lane == 0) kb_s[c - lo] = kept;   // (kb_s has kWideBatch >= S entries when the results are buffered)
     }
     __syncthreads();
@@ -669,6 +681,7 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
           unsigned long long acc = 0ull;
           for (int r = q0; r < 64; r += qstep)
             if ((kept >> r) & 1ull) acc |= __ldg(&mrow[(size_t)(c * 64 + r) * Ws + c + 1 + j]);
+          OD_DBG_IDX(c + 1 - lo + j, S);
           smem_or64(&removed[c + 1 - lo + j], acc);
         }
       }
@@ -694,6 +707,8 @@ nms_scan_wide_kernel(const unsigned long long* __restrict__ mask, const unsigned
       const int r = lane + 32 * h;
       if ((kept >> r) & 1ull) {
         const int pos = base + __popcll(kept & ((1ull << r) - 1ull));
+        OD_DBG_IDX(pos, max_out);
+        OD_DBG_IDX((lo + i) * 64 + r, K);
         if (keep_pos) keep_pos[(int64_t)b * max_out + pos] = (lo + i) * 64 + r;
         if (keep_flag) keep_flag[(int64_t)b * K + (lo + i) * 64 + r] = 1;
       }

@@ -212,6 +212,7 @@ __device__ __forceinline__ void bin_table_entry(const RoiSource& src, int64_t ro
     const uint32_t top = (uint32_t)fy, bot = (uint32_t)ceilf(in_y);
     const uint32_t left = (uint32_t)fx, right = (uint32_t)ceilf(in_x);
     const uint32_t W = (uint32_t)m.W, d4 = (uint32_t)D4;
+    OD_DBG_ASSERT(bot < (uint32_t)m.H && right < W && top <= bot && left <= right, "bilinear tap outside the feature map");
     tp.tl = (top * W + left) * d4;
     tp.tr = (top * W + right) * d4;
     tp.bl = (bot * W + left) * d4;
@@ -264,6 +265,7 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
       const int32_t e = min(e0 + u * kBinThreads, total - 1);  // clamped: loads are unconditional
       const int32_t bin = POW2 ? (e >> lgD4) : (e / D4);
       const uint32_t c = (uint32_t)(POW2 ? (e & (D4 - 1)) : (e - bin * D4));
+      OD_DBG_IDX(bin, BINS);
       const BinTaps tp = s_taps[bin];
       const BinInfo bi = s_info[bin];
       const float4* __restrict__ base = reinterpret_cast<const float4*>(bi.base_flag & ~(uintptr_t)15);
@@ -318,6 +320,7 @@ roi_order_kernel(const float4* __restrict__ boxes, int32_t N, int32_t image_h, i
       const float yc = 0.5f * (bx.x + bx.z) * (float)kOrderBands;
       const int32_t band = (yc >= 0.0f) ? (yc < (float)kOrderBands ? (int32_t)yc : kOrderBands - 1) : 0;   // NaN -> 0
       key[j] = lv * kOrderBands + band;
+      OD_DBG_IDX(key[j], nb);
       pos[j] = atomicAdd(&s_cnt[key[j]], 1);
     }
   }
@@ -347,7 +350,10 @@ roi_order_kernel(const float4* __restrict__ boxes, int32_t N, int32_t image_h, i
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < kOrderPerThread; ++j)
-    if (key[j] >= 0) order[(int64_t)b * N + s_base[key[j]] + pos[j]] = b * N + t + j * kOrderThreads;
+    if (key[j] >= 0) {
+      OD_DBG_IDX(s_base[key[j]] + pos[j], N);
+      order[(int64_t)b * N + s_base[key[j]] + pos[j]] = b * N + t + j * kOrderThreads;
+    }
 }
 
 // ----------------------------------------------------------------------------- crop_rows_kernel
@@ -480,6 +486,7 @@ __device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi
     const int32_t r_hi = (hi == lo) ? r_lo : (new_hi ? c2 : c2 - 1);
     const int32_t cnt = __popc(ml) + __popc(mh);                    // distinct taps of this half
     int32_t* vals = half ? S.cols : P.rows;
+    OD_DBG_ASSERT(!valid || (r_lo >= 0 && r_lo <= r_hi && r_hi < cnt && cnt <= 2 * kRowsMaxPool), "tap rank outside the plan");
     if (new_lo) vals[r_lo] = lo;
     if (new_hi) vals[r_hi] = hi;
     if (valid) {
@@ -506,6 +513,7 @@ __device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi
     if (start) {
       const uint32_t le = (2u << lane) - 1u;        // lanes <= this one (wraps to all ones for lane 31)
       const int32_t j = __popc(sm & le) - 1;
+      OD_DBG_IDX(j, kRowsMaxPool);
       const uint32_t rest = sm & ~le;
       P.run_col[j] = ck;
       P.run_rank[j] = lane;
@@ -670,6 +678,8 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
             }
           }
           const uint32_t off = wrap ? 0u : head;
+          OD_DBG_ASSERT(off + bytes <= ring_bytes && run_dst + run_bytes <= bytes && bytes > 0, "row outside the ring");
+          OD_DBG_IDX(e_idx, kRowsEntries);
           head = off + bytes;
           used += need;
           ++outstanding;
@@ -725,6 +735,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     if (dbg & 2) break;               /* timing experiment: no input stream at all */                \
     const uint32_t off_ = (c_head + row_bytes > ring_bytes) ? 0u : c_head;                           \
     c_head = off_ + row_bytes;                                                                       \
+    OD_DBG_ASSERT(c_head <= ring_bytes && (uint32_t)(xcr + 32) * 16u < row_bytes + 16u && xcl <= xcr, "ring read outside the row"); \
     mbar_wait(&S.full[e_idx], e_phase);                                                              \
     const float4* rowp = reinterpret_cast<const float4*>(s_ring + off_);                             \
     _Pragma("unroll") for (int i = 0; i < 2; ++i) {                                                  \
@@ -758,7 +769,9 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
   }
 #define OD_ROWS_GROUP(CUR, NXT)                                                                      \
   {                                                                                                  \
+    OD_DBG_IDX(k + 1, 2 * kRowsMaxPool + 1);                                                         \
     const int32_t yend = P.yfirst[k + 1];                                                            \
+    OD_DBG_ASSERT(yend <= ph && P.roi >= 0 && P.roi < n_rois, "y group / ROI outside the crop");     \
     const bool more = k + 1 < nr;                                                                    \
     if (more) OD_ROWS_LOAD(NXT);                                                                     \
     _Pragma("unroll 1") while (y < yend) {                                                           \

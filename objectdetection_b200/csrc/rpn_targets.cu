@@ -239,6 +239,7 @@ __global__ void rpn_label_best_kernel(const int32_t* __restrict__ gt_best, int G
   const int j = threadIdx.x + blockIdx.x * blockDim.x, b = blockIdx.y;
   if (j >= G) return;
   const int a = gt_best[(int64_t)b * G + j];
+  OD_DBG_ASSERT(a < A, "best anchor of a GT box beyond the anchor count");
   if (a >= 0) cls[(int64_t)b * A + a] = 1;
 }
 
@@ -397,6 +398,7 @@ rpn_compact_kernel(const int32_t* __restrict__ cls, int A, const int2* __restric
   int rp = before.x + (excl & 0xffff), rn = before.y + (excl >> 16);
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
+    OD_DBG_ASSERT(rp <= A && rn <= A, "rank of a labelled anchor beyond the anchor count");
     if (l[u] == 1) list_pos[(int64_t)b * A + rp++] = i0 + u;
     if (l[u] == -1) list_neg[(int64_t)b * A + rn++] = i0 + u;
   }

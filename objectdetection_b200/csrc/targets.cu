@@ -1,8 +1,10 @@
 // targets.cu — DetectionTargetLayer: BuildDetectionTargets.build_detection_target
 // (data_processor.py:512-652) with get_iou_tf (:473-510) and box_refinement_tf (:443-471), batched.
 //
-// One CTA per image. The N x G IoU matrix is never materialised (unless the debug tensor is requested):
-// GT boxes sit in shared memory and each thread reduces one proposal row to (max, first argmax).
+// Two kernels. detection_iou_kernel (8 CTAs of 256 proposals per image at N = 2000): GT boxes sit in shared memory and
+// each thread reduces one proposal row of the N x G IoU matrix to (max, first argmax); the matrix is never materialised
+// (unless the debug tensor is requested). The zero-padding strip of the proposals is a stable compaction whose base per
+// CTA is a count over the rows in front of it. detection_target_kernel (one CTA per image) does the sequential part:
 // pos/neg index lists are stable block compactions (ascending index == tf.where order). tf.random_shuffle
 // (:587,:597) is replaced by explicit permutation inputs: the shuffled list is list[q] for q in perm (in
 // order) with q < len(list).
@@ -11,6 +13,7 @@
 namespace od {
 
 constexpr int kTgtThreads = 1024;
+constexpr int kIouThreads = 256;
 
 struct TargetDebugPtrs {
   float* iou;              // [B,N,G]
@@ -73,15 +76,74 @@ __device__ int block_stable_compact(int n, Pred pred, Emit emit, int* scratch) {
   return base;
 }
 
+__device__ __forceinline__ bool prop_nonzero(float4 p) {
+  return (((fabsf(p.x) + fabsf(p.y)) + fabsf(p.z)) + fabsf(p.w)) != 0.0f;
+}
+
+// (1) strip zero padding (:564-571) and (2) IoU rows -> max / first argmax (:576-579, :610) for proposals
+// [blockIdx.x * 256, +256) of image blockIdx.y. Outputs are indexed by the COMPACTED proposal index.
+__global__ void __launch_bounds__(kIouThreads)
+detection_iou_kernel(const float4* __restrict__ proposals, const int32_t* __restrict__ gt_class_ids,
+                     const float4* __restrict__ gt_boxes, int N, int G, int32_t* __restrict__ ws_i32,
+                     float* __restrict__ ws_f32, int32_t* __restrict__ n_prop_out, TargetDebugPtrs dbg) {
+  pdl_prologue();
+  extern __shared__ float4 s_gt[];                        // [G] compacted GT boxes
+  __shared__ int scratch[40];
+  __shared__ int s_base;
+  const int b = blockIdx.y, tid = threadIdx.x, r0 = blockIdx.x * kIouThreads;
+  const float4* prop = proposals + (int64_t)b * N;
+  const int32_t* gcls = gt_class_ids + (int64_t)b * G;
+  const float4* gbox = gt_boxes + (int64_t)b * G;
+  int32_t* prop_src = ws_i32 + (int64_t)b * 4 * N;
+  int32_t* iou_arg = prop_src + N;
+  float* iou_max = ws_f32 + (int64_t)b * N;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  const int n_gt = block_stable_compact(
+      G, [&](int j) { return gcls[j] != 0; }, [&](int j, int r) { s_gt[r] = gbox[j]; }, scratch);
+  // non-zero rows in front of this CTA's slice
+  int cnt = 0;
+  for (int i = tid; i < r0; i += kIouThreads) cnt += prop_nonzero(prop[i]) ? 1 : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((tid & 31) == 0 && cnt) atomicAdd(&s_base, cnt);
+  __syncthreads();
+  const int base = s_base;
+  const int n_here = min(kIouThreads, N - r0);
+  const int total = block_stable_compact(
+      n_here, [&](int k) { return prop_nonzero(prop[r0 + k]); },
+      [&](int k, int r) {
+        const int i = base + r;                           // compacted index
+        OD_DBG_IDX(i, N);
+        const float4 p = prop[r0 + k];
+        float best = -INFINITY;
+        int arg = 0;
+        for (int j = 0; j < n_gt; ++j) {
+          const float v = target_iou(p, s_gt[j]);
+          if (dbg.iou) dbg.iou[((int64_t)b * N + i) * G + j] = v;
+          if (v > best) {
+            best = v;
+            arg = j;
+          }
+        }
+        prop_src[i] = r0 + k;
+        iou_max[i] = best;
+        iou_arg[i] = arg;
+        if (dbg.roi_iou_max) dbg.roi_iou_max[(int64_t)b * N + i] = best;
+      },
+      scratch);
+  if (tid == 0 && r0 + kIouThreads >= N) n_prop_out[b] = base + total;
+}
+
 __global__ void __launch_bounds__(kTgtThreads)
 detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __restrict__ gt_class_ids,
                         const float4* __restrict__ gt_boxes, const int32_t* __restrict__ perm_pos,
                         const int32_t* __restrict__ perm_neg, int N, int G, int R, float4 stddev,
                         float4* __restrict__ rois, int32_t* __restrict__ roi_cls, float4* __restrict__ roi_deltas,
-                        int32_t* __restrict__ ws_i32, float* __restrict__ ws_f32, int32_t* __restrict__ mask_src,
-                        TargetDebugPtrs dbg) {
-  extern __shared__ float4 s_gt[];                        // [G] compacted GT boxes
-  int32_t* s_gt_src = reinterpret_cast<int32_t*>(s_gt + G);  // [G] original GT row of compacted j
+                        int32_t* __restrict__ ws_i32, float* __restrict__ ws_f32, const int32_t* __restrict__ n_prop_in,
+                        int32_t* __restrict__ mask_src, TargetDebugPtrs dbg) {
+  pdl_prologue();
+  extern __shared__ int32_t s_gt_src[];                   // [G] original GT row of compacted j
   __shared__ int scratch[40];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float4* prop = proposals + (int64_t)b * N;
@@ -93,41 +155,11 @@ detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __r
   int32_t* pos_list = iou_arg + N;
   int32_t* neg_list = pos_list + N;
   float* iou_max = ws_f32 + (int64_t)b * N;
+  (void)prop_src;
 
-  // (1) strip zero padding (:564-571)
   const int n_gt = block_stable_compact(
-      G, [&](int j) { return gcls[j] != 0; },
-      [&](int j, int r) {
-        s_gt[r] = gbox[j];
-        s_gt_src[r] = j;
-      },
-      scratch);
-  const int n_prop = block_stable_compact(
-      N,
-      [&](int i) {
-        const float4 p = prop[i];
-        return (((fabsf(p.x) + fabsf(p.y)) + fabsf(p.z)) + fabsf(p.w)) != 0.0f;
-      },
-      [&](int i, int r) { prop_src[r] = i; }, scratch);
-  __syncthreads();
-
-  // (2) IoU rows -> max / first argmax (:576-579, :610)
-  for (int i = tid; i < n_prop; i += kTgtThreads) {
-    const float4 p = prop[prop_src[i]];
-    float best = -INFINITY;
-    int arg = 0;
-    for (int j = 0; j < n_gt; ++j) {
-      const float v = target_iou(p, s_gt[j]);
-      if (dbg.iou) dbg.iou[((int64_t)b * N + i) * G + j] = v;
-      if (v > best) {
-        best = v;
-        arg = j;
-      }
-    }
-    iou_max[i] = best;
-    iou_arg[i] = arg;
-    if (dbg.roi_iou_max) dbg.roi_iou_max[(int64_t)b * N + i] = best;
-  }
+      G, [&](int j) { return gcls[j] != 0; }, [&](int j, int r) { s_gt_src[r] = j; }, scratch);
+  const int n_prop = n_prop_in[b];
   __syncthreads();
 
   // (3) where(max >= 0.5) / where(max < 0.5), ascending (:582-583)
@@ -183,9 +215,13 @@ detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __r
       [&](int t, int r) {
         if (r >= pos_count) return;
         const int idx = pos_list[pp[t]];
+        OD_DBG_IDX(idx, N);
         const float4 box = prop[idx];
         const int a = iou_arg[idx];
+        OD_DBG_IDX(a, G);
         const int g = s_gt_src[a];
+        OD_DBG_IDX(g, G);
+        OD_DBG_IDX(r, R);
         o_rois[r] = box;
         o_cls[r] = gcls[g];
         o_del[r] = refine_box(box, gbox[g], stddev);
@@ -203,6 +239,8 @@ detection_target_kernel(const float4* __restrict__ proposals, const int32_t* __r
       [&](int t, int r) {
         if (r >= neg_count) return;
         const int idx = neg_list[pn[t]];
+        OD_DBG_IDX(idx, N);
+        OD_DBG_IDX(pos_count + r, R);
         o_rois[pos_count + r] = prop[idx];
         if (dbg.sampled_neg) dbg.sampled_neg[(int64_t)b * R + r] = idx;
       },
@@ -281,6 +319,7 @@ size_t od_detection_target_workspace_bytes(int64_t batch, int64_t num_proposals,
   w.take<int32_t>((size_t)(batch * 4 * num_proposals));
   w.take<float>((size_t)(batch * num_proposals));
   w.take<int32_t>((size_t)(batch * 4096));   // GT row of every sampled positive (mask targets), R <= 4096
+  w.take<int32_t>((size_t)batch);            // non-zero proposals per image
   return w.off + 256;
 }
 
@@ -357,6 +396,7 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
   int32_t* ws_i32 = w.take<int32_t>((size_t)(B * 4 * N));
   float* ws_f32 = w.take<float>((size_t)(B * N));
   int32_t* mask_src = w.take<int32_t>((size_t)(B * 4096));
+  int32_t* n_prop = w.take<int32_t>((size_t)B);
   if (!w.ok()) OD_FAIL(OD_ERR_WORKSPACE, "workspace %zu < %zu bytes", ws_bytes, w.off);
   TargetDebugPtrs dp;
   dp.iou = dptr<float>(dbg.iou);
@@ -368,13 +408,22 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
   dp.sampled_neg = dptr<int32_t>(dbg.sampled_neg);
   dp.gt_assignment = dptr<int32_t>(dbg.gt_assignment);
   const float4 sd = make_float4(params->bbox_stddev[0], params->bbox_stddev[1], params->bbox_stddev[2], params->bbox_stddev[3]);
-  const size_t smem = (size_t)(G > 0 ? G : 1) * (sizeof(float4) + sizeof(int32_t));
-  if (smem > 48 * 1024)
-    OD_CUDA(cudaFuncSetAttribute(detection_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  detection_target_kernel<<<(unsigned)B, kTgtThreads, smem, st>>>(
+  const size_t smem_iou = (size_t)(G > 0 ? G : 1) * sizeof(float4);      // <= 128 KiB at the G <= 8192 cap
+  if (smem_iou > 48 * 1024)
+    OD_CUDA(cudaFuncSetAttribute(detection_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_iou));
+  if (N > 0) {
+    const dim3 grid((unsigned)((N + kIouThreads - 1) / kIouThreads), (unsigned)B);
+    OD_CUDA(launch_pdl(detection_iou_kernel, grid, dim3(kIouThreads), smem_iou, st, dptr<float4>(proposals),
+                       dptr<int32_t>(gt_class_ids), dptr<float4>(gt_boxes), (int)N, (int)G, ws_i32, ws_f32, n_prop, dp));
+    OD_LAUNCH_CHECK("detection_iou_kernel");
+  } else {
+    OD_CUDA(cudaMemsetAsync(n_prop, 0, (size_t)B * sizeof(int32_t), st));
+  }
+  const size_t smem = (size_t)(G > 0 ? G : 1) * sizeof(int32_t);
+  OD_CUDA(launch_pdl(detection_target_kernel, dim3((unsigned)B), dim3(kTgtThreads), smem, st,
       dptr<float4>(proposals), dptr<int32_t>(gt_class_ids), dptr<float4>(gt_boxes), dptr<int32_t>(perm_pos),
       dptr<int32_t>(perm_neg), (int)N, (int)G, (int)R, sd, dptr<float4>(rois), dptr<int32_t>(roi_gt_class_ids),
-      dptr<float4>(roi_gt_box_deltas), ws_i32, ws_f32, gt_masks ? mask_src : nullptr, dp);
+      dptr<float4>(roi_gt_box_deltas), ws_i32, ws_f32, (const int32_t*)n_prop, gt_masks ? mask_src : nullptr, dp));
   OD_LAUNCH_CHECK("detection_target_kernel");
   if (gt_masks) {
     const dim3 grid((unsigned)R, (unsigned)B);

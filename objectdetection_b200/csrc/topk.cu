@@ -98,7 +98,10 @@ topk_hist1_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_st
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t i = i0 + u * kSelThreads;
-      if (i < ch.end) atomicAdd(&sh[(uint32_t)(topk_key(v[u], (uint32_t)i, ib) >> shift)], 1u);
+      if (i < ch.end) {
+        OD_DBG_IDX((uint32_t)(topk_key(v[u], (uint32_t)i, ib) >> shift), kBins);
+        atomicAdd(&sh[(uint32_t)(topk_key(v[u], (uint32_t)i, ib) >> shift)], 1u);
+      }
     }
   }
   __syncthreads();
@@ -238,7 +241,10 @@ topk_split_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_st
 #pragma unroll
     for (int u = 0; u < kSplitPer; ++u) {
       const int64_t i = t0 + u * kSelThreads + threadIdx.x;
-      if ((wmask >> u) & 1u) out[wpos++] = topk_key(v[u], (uint32_t)i, ib);
+      if ((wmask >> u) & 1u) {
+        OD_DBG_IDX(wpos, k);
+        out[wpos++] = topk_key(v[u], (uint32_t)i, ib);
+      }
       if ((cmask >> u) & 1u) {
         if (cpos < (uint32_t)cand_cap) cnd[cpos] = topk_key(v[u], (uint32_t)i, ib);   // beyond the capacity only the count grows
         ++cpos;
@@ -305,7 +311,10 @@ topk_tail_kernel(const float* __restrict__ scores, int64_t cols, int64_t row_str
       sel = ((c >> shift1) == (prefix >> shift1)) && ((c >> shift) >= thr);
     }
     const int2 sc = block_exclusive_scan<kTailThreads>(sel ? 1 : 0, warp_sums);
-    if (sel) out[base + (uint32_t)sc.x] = c;
+    if (sel) {
+      OD_DBG_IDX(base + (uint32_t)sc.x, buf_stride);
+      out[base + (uint32_t)sc.x] = c;
+    }
     base += (uint32_t)sc.y;
   }
 }
@@ -376,6 +385,7 @@ topk_merge_emit_kernel(const unsigned long long* __restrict__ buf, int64_t buf_s
   }
   const uint32_t imask = (1u << ib) - 1u;
   const uint32_t idx = imask - (uint32_t)(mine & imask);
+  OD_DBG_IDX(rank, k);
   idx_out[(int64_t)row * k + rank] = (int32_t)idx;
   if (val_out) val_out[(int64_t)row * k + rank] = scores[(int64_t)row * row_stride + (int64_t)idx * col_stride];
 }

@@ -61,6 +61,15 @@ def main():
             probs, bbox = _synth.rpn_outputs(np.random.RandomState(0), 2, anchors.shape[1])
             p, bb = cu(probs), cu(bbox)
             run(f"Proposals B=2 pre-NMS {Kpre}", lambda: Proposals(conf, 2, p, bb, anchors), iters=5)
+    if "cfg3" in cases:      # BASELINE configs[2]: DetectionTargetLayer, 2000 proposals, 100 GT, 200 sampled ROIs, batch 8
+        import _synth
+        from objectdetection_b200 import config
+        from objectdetection_b200.data_processor import BuildDetectionTargets
+        conf = config()
+        props, cls, gt, pp, pn = _synth.target_inputs(np.random.RandomState(3), 8, 2000, 100)
+        t = [cu(x) for x in (props, cls, gt, pp, pn)]
+        run("DetectionTargetLayer B=8 N=2000 G=100 R=200",
+            lambda: BuildDetectionTargets(conf, t[0], t[1], t[2], perm_pos=t[3], perm_neg=t[4]), iters=5)
     if "frcnn" in cases:
         h, w, na = 38, 63, 9
         fp = cu(rs.random_sample((1, h, w, 2 * na)).astype(np.float32))
