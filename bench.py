@@ -1027,7 +1027,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip scaling_b64 and the configs[2]/[3]/stress extras")
     ap.add_argument("--check", action="store_true", help="compare every shard's detections with the CPU oracle")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph)")
-    ap.add_argument("--lanes", type=int, default=2, help="steps in flight (1: strictly one step after the other)")
+    ap.add_argument("--lanes", type=int, default=4, help="steps in flight (1: strictly one step after the other)")
     ap.add_argument("--kernel-times", action="store_true", help="print per-kernel device times (CUPTI) to stderr")
     args = ap.parse_args()
     if args.impl == "reference":

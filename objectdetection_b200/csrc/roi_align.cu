@@ -379,8 +379,11 @@ roi_order_kernel(const float4* __restrict__ boxes, int32_t N, int32_t image_h, i
 // Arithmetic per output value is the reference's (crop_and_resize_op.cc): top = tl + (tr - tl) * xl, bot likewise,
 // out = top + (bot - top) * yl, so the results are bit-identical to crop_bins_kernel and to the oracle.
 constexpr int kRowsMaxPool = 16;
-constexpr int kRowsEntries = 16;                // outstanding ring entries (one feature row each)
-constexpr int kRowsPlans = 3;                   // plans in flight
+constexpr int kRowsEntries = 32;                // outstanding ring entries (one feature row each)
+#ifndef OD_ROWS_PLANS
+#define OD_ROWS_PLANS 3
+#endif
+constexpr int kRowsPlans = OD_ROWS_PLANS;       // plans in flight
 constexpr int kRowsStages = 2;                  // output staging slots (1 KiB each) per consumer warp, TMA-store variant
 constexpr int kRowsD4 = 64;                     // D = 256 floats = 64 quads = 1 KiB per pixel
 constexpr uint32_t kRowsPixelBytes = 1024;
@@ -541,8 +544,8 @@ __device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi
 
 // counter[0]: next ROI ticket, counter[1]: CTAs that have drawn their last ticket. Both are zero between launches: the
 // last CTA to finish resets them (the workspace is zero-initialised once by its owner).
-template <bool TMAST>
-__global__ void __launch_bounds__(512, 2)
+template <bool TMAST, int QPL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t ring_bytes, float extrap,
                  float4* __restrict__ out, int32_t* __restrict__ level_out, unsigned int* __restrict__ counter,
                  int32_t l2_prefetch, int32_t l2_keep, int32_t dbg) {
@@ -551,7 +554,8 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
   __shared__ RowsShared S;
   const int32_t t = threadIdx.x;
   const int32_t lane = t & 31, warp = t >> 5;
-  const int32_t n_cwarps = pw, n_cons = 32 * pw;   // one consumer warp per x bin
+  constexpr int kWarpsPerBin = 2 / QPL;            // QPL channel quads per lane: 2 -> one consumer warp per x bin, 1 -> two
+  const int32_t n_cwarps = pw * kWarpsPerBin, n_cons = 32 * n_cwarps;
   if (t == 0) {
     for (int32_t e = 0; e < kRowsEntries; ++e) {
       mbar_init(&S.full[e], 1);
@@ -703,13 +707,14 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
   }
 
   // -------------------------------------------------------------------- consumers
-  // warp = x bin, lane = channel quads `lane` and `lane + 32`: one output pixel (1 KiB) per warp and output row.
+  // QPL = 2: warp = x bin, lane = channel quads `lane` and `lane + 32`: one output pixel (1 KiB) per warp and output row.
+  // QPL = 1: two warps per x bin, one quad per lane (twice the warps for the same registers per thread).
   // TMAST: the pixel is staged in a per-warp shared-memory slot and leaves through the bulk-copy engine (lane 0 issues
   // one 1 KiB shared->global copy per output row and only ever waits for the slot it is about to overwrite), so the
   // number of stores in flight does not depend on registers or on LSU back-pressure.
-  const int32_t x = warp;
+  const int32_t x = warp / kWarpsPerBin, qoff = (warp % kWarpsPerBin) * 32 + lane;
   const float4 ext4 = make_float4(extrap, extrap, extrap, extrap);
-  float4* const stage = reinterpret_cast<float4*>(s_ring + ring_bytes) + warp * (kRowsStages * kRowsD4);
+  float4* const stage = reinterpret_cast<float4*>(s_ring + ring_bytes) + warp * (kRowsStages * kRowsD4);   // (TMAST: QPL = 2)
   const uint64_t pol_out = l2_policy_evict_first();
   int32_t e_idx = 0, st = 0;
   uint32_t e_phase = 0, c_head = 0;              // ring entry, its phase, and the issuer's head replayed locally
@@ -721,24 +726,25 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     float4* __restrict__ o = out + P.roi * ((int64_t)ph * pw * kRowsD4);
     if (mode == kRowsRing) {
       // Column ranks -> float4 index inside a ring row (+ the channel quad).
-      const int32_t xcl = P.x_cl[x] * kRowsD4 + lane, xcr = P.x_cr[x] * kRowsD4 + lane;
+      const int32_t xcl = P.x_cl[x] * kRowsD4 + qoff, xcr = P.x_cr[x] * kRowsD4 + qoff;
       const float xl = P.x_lerp[x];
       const int32_t nr = P.nr;
       const uint32_t row_bytes = P.row_bytes;
       // Rank-major walk: the y's whose top row has rank k are contiguous (P.yfirst), their bottom row is rank k or k+1.
       // Rows alternate between RA (even ranks) and RB (odd ranks). bottom - top is recomputed per y: a group holds 1.2 y's
       // on average, caching the difference would only cost registers.
-      float4 RA[2], RB[2];
-      RA[0] = RA[1] = RB[0] = RB[1] = ext4;
+      float4 RA[QPL], RB[QPL];
+#pragma unroll
+      for (int i = 0; i < QPL; ++i) RA[i] = RB[i] = ext4;
 #define OD_ROWS_LOAD(V)                                                                              \
   do {                                                                                               \
     if (dbg & 2) break;               /* timing experiment: no input stream at all */                \
     const uint32_t off_ = (c_head + row_bytes > ring_bytes) ? 0u : c_head;                           \
     c_head = off_ + row_bytes;                                                                       \
-    OD_DBG_ASSERT(c_head <= ring_bytes && (uint32_t)(xcr + 32) * 16u < row_bytes + 16u && xcl <= xcr, "ring read outside the row"); \
+    OD_DBG_ASSERT(c_head <= ring_bytes && (uint32_t)(xcr + 32 * (QPL - 1)) * 16u < row_bytes && xcl <= xcr, "ring read outside the row"); \
     mbar_wait(&S.full[e_idx], e_phase);                                                              \
     const float4* rowp = reinterpret_cast<const float4*>(s_ring + off_);                             \
-    _Pragma("unroll") for (int i = 0; i < 2; ++i) {                                                  \
+    _Pragma("unroll") for (int i = 0; i < QPL; ++i) {                                                \
       const float4 l_ = rowp[xcl + 32 * i], r_ = rowp[xcr + 32 * i];                                 \
       V[i] = axpy4p(l_, sub4p(r_, l_), xl);                                                          \
     }                                                                                                \
@@ -749,13 +755,12 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
       e_phase ^= 1u;                                                                                 \
     }                                                                                                \
   } while (0)
-#define OD_ROWS_PUT(V0, V1)                                                                          \
+#define OD_ROWS_PUT(V)                                                                               \
   if (TMAST) {                                                                                       \
     float4* sp_ = stage + st * kRowsD4;                                                              \
     if (lane == 0) bulk_wait_read<kRowsStages - 1>();   /* the copy that last read this slot is done */ \
     __syncwarp();                                                                                    \
-    sp_[lane] = V0;                                                                                  \
-    sp_[lane + 32] = V1;                                                                             \
+    _Pragma("unroll") for (int i = 0; i < QPL; ++i) sp_[lane + 32 * i] = V[i];                       \
     fence_proxy_async_smem();                                                                        \
     __syncwarp();                                                                                    \
     if (lane == 0) {                                                                                 \
@@ -764,8 +769,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     }                                                                                                \
     if (++st == kRowsStages) st = 0;                                                                 \
   } else if (!(dbg & 1)) {                                                                           \
-    stg_cs_f4(orow + lane, V0);                                                                      \
-    stg_cs_f4(orow + lane + 32, V1);                                                                 \
+    _Pragma("unroll") for (int i = 0; i < QPL; ++i) stg_cs_f4(orow + qoff + 32 * i, V[i]);           \
   }
 #define OD_ROWS_GROUP(CUR, NXT)                                                                      \
   {                                                                                                  \
@@ -777,15 +781,13 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     _Pragma("unroll 1") while (y < yend) {                                                           \
       const int2 nxt_ = P.ytab[y + 1];                                                               \
       const float yl = __int_as_float(ent.x);                                                        \
-      float4 v0_, v1_;                                                                               \
+      float4 v_[QPL];                                                                                \
       if (ent.y) {                    /* top row == bottom row: (top - top) * yl, as the reference */ \
-        v0_ = axpy4p(CUR[0], sub4p(CUR[0], CUR[0]), yl);                                             \
-        v1_ = axpy4p(CUR[1], sub4p(CUR[1], CUR[1]), yl);                                             \
+        _Pragma("unroll") for (int i = 0; i < QPL; ++i) v_[i] = axpy4p(CUR[i], sub4p(CUR[i], CUR[i]), yl); \
       } else {                                                                                       \
-        v0_ = axpy4p(CUR[0], sub4p(NXT[0], CUR[0]), yl);                                             \
-        v1_ = axpy4p(CUR[1], sub4p(NXT[1], CUR[1]), yl);                                             \
+        _Pragma("unroll") for (int i = 0; i < QPL; ++i) v_[i] = axpy4p(CUR[i], sub4p(NXT[i], CUR[i]), yl); \
       }                                                                                              \
-      OD_ROWS_PUT(v0_, v1_)                                                                          \
+      OD_ROWS_PUT(v_)                                                                                \
       ent = nxt_;                                                                                    \
       ++y;                                                                                           \
       orow += pw * kRowsD4;                                                                          \
@@ -793,7 +795,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     if (!more) break;                                                                                \
     ++k;                                                                                             \
   }
-      float4* __restrict__ orow = o + x * kRowsD4;    // this warp's pixel of output row 0
+      float4* __restrict__ orow = o + x * kRowsD4;    // this warp's pixel of output row 0 (TMAST: the bulk copy's target)
       int2 ent = P.ytab[0];
       int32_t y = 0, k = 0;
       OD_ROWS_LOAD(RA);
@@ -901,7 +903,7 @@ crop_pool_bins_kernel(RoiSource src, int64_t total_bins, int32_t oh, int32_t ow,
 struct RowsTuning {
   bool use_rows, dynamic, tma_store;
   int ring_kb;
-  int cps, min_pool, l2_prefetch, l2_keep, dbg;
+  int cps, qpl, min_pool, l2_prefetch, l2_keep, dbg;
 };
 static int env_int(const char* name, int dflt, int lo, int hi) {
   const char* v = getenv(name);
@@ -913,8 +915,9 @@ static const RowsTuning& rows_tuning() {
     RowsTuning r;
     const char* k = getenv("OD_ROI_KERNEL");
     r.use_rows = !(k && strcmp(k, "flat") == 0);
-    r.ring_kb = env_int("OD_ROI_RING_KB", 0, 0, 200);       // 0: derived from the CTA count per SM
-    r.cps = env_int("OD_ROI_CPS", 2, 1, 8);
+    r.ring_kb = env_int("OD_ROI_RING_KB", 0, 0, 222);       // 0: derived from the CTA count per SM
+    r.cps = env_int("OD_ROI_CPS", 1, 1, 2);
+    r.qpl = env_int("OD_ROI_QPL", 2, 1, 2);
     r.min_pool = env_int("OD_ROI_MIN_POOL", 10, 1, 17);
     r.dynamic = env_int("OD_ROI_DYNAMIC", 1, 0, 1) != 0;
     r.tma_store = env_int("OD_ROI_TMA_STORE", 0, 0, 1) != 0;   // measured slower (profiles/r2_roialign.md): opt-in
@@ -926,29 +929,32 @@ static const RowsTuning& rows_tuning() {
   return t;
 }
 
-template <bool TMAST>
+template <bool TMAST, int QPL, int MAXT, int MINB>
 static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, const RowsTuning& tn,
                               float extrap, float* out, int32_t* level_out, unsigned int* counter, cudaStream_t st) {
-  auto kern = crop_rows_kernel<TMAST>;
+  auto kern = crop_rows_kernel<TMAST, QPL, MAXT, MINB>;
   static uint32_t configured[64] = {0};    // dynamic shared memory opted in, per device
   static int sms[64] = {0};
   int dev = 0;
   OD_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) OD_FAIL(OD_ERR_DEVICE, "device index %d not supported", dev);
-  // shared memory per CTA: 227 KiB per SM shared by `cps` CTAs, minus the static part (plans, barriers) and 1 KiB that the
-  // hardware reserves per CTA; the staging slots of the TMA-store variant come out of the same budget
+  // Ring size. One CTA per SM (default): 176 KiB - the kernel alone is ~1 % faster with everything an SM has (221 KiB),
+  // but leaving ~45 KiB lets the small CTAs of concurrently running kernels (the other steps' proposal front and 7x7
+  // ROIAlign) become resident next to it, which is worth 8 % of whole-step throughput (profiles/r2_roialign.md).
+  // Two CTAs per SM: what is left of 227 KiB after the static part and the staging slots of the TMA-store variant.
   const uint32_t stage_bytes = TMAST ? (uint32_t)pw * kRowsStages * kRowsPixelBytes : 0u;
   uint32_t ring_bytes = tn.ring_kb ? (uint32_t)tn.ring_kb * 1024u
-                                   : ((227u * 1024u) / (uint32_t)tn.cps - 6u * 1024u - stage_bytes) & ~1023u;
+                        : (tn.cps == 1 && !TMAST) ? 176u * 1024u
+                                                  : ((227u * 1024u) / (uint32_t)tn.cps - 6u * 1024u - stage_bytes) & ~1023u;
   const uint32_t dyn = ring_bytes + stage_bytes;
-  if (dyn > 220u * 1024u) OD_FAIL(OD_ERR_PARAM, "OD_ROI_RING_KB too large: %u bytes of dynamic shared memory", dyn);
+  if (dyn > 222u * 1024u) OD_FAIL(OD_ERR_PARAM, "OD_ROI_RING_KB too large: %u bytes of dynamic shared memory", dyn);
   if (configured[dev] < dyn) {
     OD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     configured[dev] = dyn;
   }
   if (!sms[dev]) OD_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
   const int64_t grid = n_rois < (int64_t)sms[dev] * tn.cps ? n_rois : (int64_t)sms[dev] * tn.cps;
-  OD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)(32 * pw + 64)), (size_t)dyn, st, src, n_rois, ph, pw,
+  OD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)(32 * pw * (2 / QPL) + 64)), (size_t)dyn, st, src, n_rois, ph, pw,
                      ring_bytes, extrap, reinterpret_cast<float4*>(out), level_out, counter, tn.l2_prefetch, tn.l2_keep, tn.dbg));
   OD_LAUNCH_CHECK("crop_rows_kernel");
   return OD_OK;
@@ -956,16 +962,24 @@ static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, 
 
 // returns OD_OK after launching, or 1 when the shape is not served by this kernel (caller falls back to crop_bins).
 // `counter`: two zeroed uint32 in the caller's workspace (dynamic ROI scheduling) or NULL (static round robin).
+// one consumer warp per x bin + issuer + planner in a 512-thread CTA: pool widths up to 14
+static bool crop_rows_serves(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D) {
+  const RowsTuning& tn = rows_tuning();
+  const int32_t pmax = ph > pw ? ph : pw;
+  if (!tn.use_rows || D != 4 * kRowsD4 || ph > kRowsMaxPool || pw > 14 || pmax < tn.min_pool || src.mode > 1) return false;
+  return n_rois + 4096 <= 0x7FFFFFFFll;
+}
 static int launch_crop_rows(const RoiSource& src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap, float* out,
                             int32_t* level_out, unsigned int* counter, cudaStream_t st) {
   const RowsTuning& tn = rows_tuning();
-  const int32_t pmax = ph > pw ? ph : pw;
-  // one consumer warp per x bin + issuer + planner in a 512-thread CTA: pool widths up to 14
-  if (!tn.use_rows || D != 4 * kRowsD4 || ph > kRowsMaxPool || pw > 14 || pmax < tn.min_pool || src.mode > 1) return 1;
-  if (n_rois + 4096 > 0x7FFFFFFFll) return 1;
+  if (!crop_rows_serves(src, n_rois, ph, pw, D)) return 1;
   if (!tn.dynamic) counter = nullptr;
-  return tn.tma_store ? launch_crop_rows_t<true>(src, n_rois, ph, pw, tn, extrap, out, level_out, counter, st)
-                      : launch_crop_rows_t<false>(src, n_rois, ph, pw, tn, extrap, out, level_out, counter, st);
+#define OD_ROWS_GO(T, Q, M, B) return launch_crop_rows_t<T, Q, M, B>(src, n_rois, ph, pw, tn, extrap, out, level_out, counter, st)
+  if (tn.tma_store) OD_ROWS_GO(true, 2, 512, 2);
+  if (tn.qpl == 1 && tn.cps == 1) OD_ROWS_GO(false, 1, 1024, 1);    // 2 warps per x bin, one CTA per SM
+  if (tn.cps == 1) OD_ROWS_GO(false, 2, 512, 1);                    // one CTA per SM: up to 128 registers per thread
+  OD_ROWS_GO(false, 2, 512, 2);
+#undef OD_ROWS_GO
 }
 
 static int launch_crop_bins(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
@@ -973,11 +987,13 @@ static int launch_crop_bins(RoiSource src, int64_t n_rois, int32_t ph, int32_t p
                             int32_t* order_buf = nullptr) {
   if (n_rois == 0) return OD_OK;
   const int32_t D4 = D / 4;
-  // processing order (PyramidROIAlign with a sized workspace, enough ROIs for the order to matter, D = 256 paths only)
-  static const int use_order = env_int("OD_ROI_ORDER", 0, 0, 1);   // measured neutral (profiles/r2_roialign.md): opt-in
+  // processing order (PyramidROIAlign with a sized workspace, enough ROIs for the order to matter). Measured: +3 % on the
+  // persistent 14x14 kernel, -5 % on the flat 7x7 kernel (its pre-pass and the extra table read cost more than the L2
+  // hits return, profiles/r2_roialign.md), so only the shapes served by crop_rows_kernel are ordered.
+  static const int use_order = env_int("OD_ROI_ORDER", 1, 0, 2);   // 2: also the flat kernel
   src.order = nullptr;
   if (use_order && order_buf && src.mode == 0 && D == 4 * kRowsD4 && n_rois >= 512 && n_rois <= 0x7FFFFFFFll &&
-      src.rois_per_image <= kOrderThreads * kOrderPerThread) {
+      src.rois_per_image <= kOrderThreads * kOrderPerThread && (use_order == 2 || crop_rows_serves(src, n_rois, ph, pw, D))) {
     OD_CUDA(launch_pdl(roi_order_kernel, dim3((unsigned)src.batch), dim3(kOrderThreads), 0, st, src.boxes, src.rois_per_image,
                        src.image_h, src.image_w, src.min_level, src.num_levels, order_buf));
     OD_LAUNCH_CHECK("roi_order_kernel");

@@ -81,7 +81,10 @@ __device__ __forceinline__ bool prop_nonzero(float4 p) {
 }
 
 // (1) strip zero padding (:564-571) and (2) IoU rows -> max / first argmax (:576-579, :610) for proposals
-// [blockIdx.x * 256, +256) of image blockIdx.y. Outputs are indexed by the COMPACTED proposal index.
+// [blockIdx.x * 64, +64) of image blockIdx.y. Four lanes share a row: lane part p takes GT boxes p, p+4, ... and the
+// quad combines (greater value wins, equal values keep the smaller GT index = the first arg-max of the serial scan).
+// Outputs are indexed by the COMPACTED proposal index.
+constexpr int kIouRows = kIouThreads / 4;
 __global__ void __launch_bounds__(kIouThreads)
 detection_iou_kernel(const float4* __restrict__ proposals, const int32_t* __restrict__ gt_class_ids,
                      const float4* __restrict__ gt_boxes, int N, int G, int32_t* __restrict__ ws_i32,
@@ -89,8 +92,8 @@ detection_iou_kernel(const float4* __restrict__ proposals, const int32_t* __rest
   pdl_prologue();
   extern __shared__ float4 s_gt[];                        // [G] compacted GT boxes
   __shared__ int scratch[40];
-  __shared__ int s_base;
-  const int b = blockIdx.y, tid = threadIdx.x, r0 = blockIdx.x * kIouThreads;
+  __shared__ int s_base, s_rank[kIouRows], s_cnt[2];
+  const int b = blockIdx.y, tid = threadIdx.x, r0 = blockIdx.x * kIouRows;
   const float4* prop = proposals + (int64_t)b * N;
   const int32_t* gcls = gt_class_ids + (int64_t)b * G;
   const float4* gbox = gt_boxes + (int64_t)b * G;
@@ -107,32 +110,50 @@ detection_iou_kernel(const float4* __restrict__ proposals, const int32_t* __rest
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
   if ((tid & 31) == 0 && cnt) atomicAdd(&s_base, cnt);
+  // stable rank of this slice's non-zero rows (threads 0..63 = two warps)
+  if (tid < kIouRows) {
+    const bool nz = (r0 + tid < N) && prop_nonzero(prop[r0 + tid]);
+    const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = __popc(bal);
+    s_rank[tid] = nz ? __popc(bal & ((1u << (tid & 31)) - 1u)) : -1;
+  }
   __syncthreads();
-  const int base = s_base;
-  const int n_here = min(kIouThreads, N - r0);
-  const int total = block_stable_compact(
-      n_here, [&](int k) { return prop_nonzero(prop[r0 + k]); },
-      [&](int k, int r) {
-        const int i = base + r;                           // compacted index
-        OD_DBG_IDX(i, N);
-        const float4 p = prop[r0 + k];
-        float best = -INFINITY;
-        int arg = 0;
-        for (int j = 0; j < n_gt; ++j) {
-          const float v = target_iou(p, s_gt[j]);
-          if (dbg.iou) dbg.iou[((int64_t)b * N + i) * G + j] = v;
-          if (v > best) {
-            best = v;
-            arg = j;
-          }
-        }
-        prop_src[i] = r0 + k;
-        iou_max[i] = best;
-        iou_arg[i] = arg;
-        if (dbg.roi_iou_max) dbg.roi_iou_max[(int64_t)b * N + i] = best;
-      },
-      scratch);
-  if (tid == 0 && r0 + kIouThreads >= N) n_prop_out[b] = base + total;
+  const int k = tid >> 2, part = tid & 3;
+  int rank = s_rank[k];
+  if (rank >= 0 && k >= 32) rank += s_cnt[0];
+  const int i = s_base + rank;                            // compacted index (valid when rank >= 0)
+  const bool row = rank >= 0;                             // uniform per quad
+  float best = -INFINITY;
+  int arg = 0;
+  if (row) {
+    OD_DBG_IDX(i, N);
+    const float4 p = prop[r0 + k];
+    for (int j = part; j < n_gt; j += 4) {
+      const float v = target_iou(p, s_gt[j]);
+      if (dbg.iou) dbg.iou[((int64_t)b * N + i) * G + j] = v;
+      if (v > best) {
+        best = v;
+        arg = j;
+      }
+    }
+    if (best == -INFINITY) arg = 0;                       // nothing selected: the serial scan leaves arg at 0
+  }
+#pragma unroll
+  for (int d = 1; d < 4; d <<= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, d);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+    if (ov > best || (ov == best && oa < arg)) {
+      best = ov;
+      arg = oa;
+    }
+  }
+  if (row && part == 0) {
+    prop_src[i] = r0 + k;
+    iou_max[i] = best;
+    iou_arg[i] = arg;
+    if (dbg.roi_iou_max) dbg.roi_iou_max[(int64_t)b * N + i] = best;
+  }
+  if (tid == 0 && r0 + kIouRows >= N) n_prop_out[b] = s_base + s_cnt[0] + s_cnt[1];
 }
 
 __global__ void __launch_bounds__(kTgtThreads)
@@ -412,7 +433,7 @@ int od_detection_target_forward(const DLTensor* proposals, const DLTensor* gt_cl
   if (smem_iou > 48 * 1024)
     OD_CUDA(cudaFuncSetAttribute(detection_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_iou));
   if (N > 0) {
-    const dim3 grid((unsigned)((N + kIouThreads - 1) / kIouThreads), (unsigned)B);
+    const dim3 grid((unsigned)((N + kIouRows - 1) / kIouRows), (unsigned)B);
     OD_CUDA(launch_pdl(detection_iou_kernel, grid, dim3(kIouThreads), smem_iou, st, dptr<float4>(proposals),
                        dptr<int32_t>(gt_class_ids), dptr<float4>(gt_boxes), (int)N, (int)G, ws_i32, ws_f32, n_prop, dp));
     OD_LAUNCH_CHECK("detection_iou_kernel");
