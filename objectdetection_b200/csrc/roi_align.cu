@@ -380,6 +380,9 @@ roi_order_kernel(const float4* __restrict__ boxes, int32_t N, int32_t image_h, i
 // out = top + (bot - top) * yl, so the results are bit-identical to crop_bins_kernel and to the oracle.
 constexpr int kRowsMaxPool = 16;
 constexpr int kRowsEntries = 32;                // outstanding ring entries (one feature row each)
+#ifndef OD_ROWS_YUNROLL
+#define OD_ROWS_YUNROLL "unroll 1"
+#endif
 #ifndef OD_ROWS_PLANS
 #define OD_ROWS_PLANS 3
 #endif
@@ -522,7 +525,9 @@ __device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi
       P.run_rank[j] = lane;
       P.run_len[j] = (rest ? __ffs(rest) - 1 : nc) - lane;
     }
-    if ((uint32_t)nc * kRowsPixelBytes > ring_bytes) mode = kRowsFlat;
+    // A row may have to skip the tail of the ring (it never straddles the end): row + skipped tail must fit an EMPTY
+    // ring, which holds for every head position only if a row is at most half the ring. Wider rows take the flat path.
+    if (2u * (uint32_t)nc * kRowsPixelBytes > ring_bytes) mode = kRowsFlat;
     if (lane == 0) {
       P.nr = nr;
       P.ncols = nc;
@@ -672,6 +677,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
         for (int32_t k = 0; k < nr; ++k) {
           const bool wrap = head + bytes > ring_bytes;            // the tail a wrapped row skips counts as part of it
           const uint32_t need = bytes + (wrap ? ring_bytes - head : 0u);
+          OD_DBG_ASSERT(need <= ring_bytes, "a row and the ring tail it skips exceed the ring");
           while (used + need > ring_bytes || outstanding == kRowsEntries) {
             mbar_wait(&S.empty[old_idx], old_phase);              // reclaim the oldest entry (FIFO)
             used -= S.entry_fp[old_idx];
@@ -778,7 +784,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     OD_DBG_ASSERT(yend <= ph && P.roi >= 0 && P.roi < n_rois, "y group / ROI outside the crop");     \
     const bool more = k + 1 < nr;                                                                    \
     if (more) OD_ROWS_LOAD(NXT);                                                                     \
-    _Pragma("unroll 1") while (y < yend) {                                                           \
+    _Pragma(OD_ROWS_YUNROLL) while (y < yend) {                                                           \
       const int2 nxt_ = P.ytab[y + 1];                                                               \
       const float yl = __int_as_float(ent.x);                                                        \
       float4 v_[QPL];                                                                                \
