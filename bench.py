@@ -808,7 +808,7 @@ def run_b64(torch, dist, world, rank, dev, conf, args, barrier, max_over_ranks):
     """BASELINE configs[4] / SURVEY §8e: the 1024^2 heads at GLOBAL batch 64, B_local = 64 / N images per GPU. The RPN and
     head outputs come from the same host recipe as the headline (seeded per image block, so --check can regenerate them);
     the 5.7 GB/64 images of feature pyramid are drawn on the device. One step = the headline step over B_local images,
-    eager launches on one stream (at 32+ images per launch nothing is launch-bound)."""
+    eager launches (at 8+ images per launch nothing is launch-bound)."""
     from objectdetection_b200 import DetectionLayer, Proposals, utils
     from objectdetection_b200.distributed import gather_detections, shard_range
     from objectdetection_b200.maskrcnn import pyramid_roi_align
@@ -827,12 +827,37 @@ def run_b64(torch, dist, world, rank, dev, conf, args, barrier, max_over_ranks):
     p7 = torch.empty((1, Bl * N_ROIS, 7, 7, DEPTH), dtype=torch.float32, device=dev)
     p14 = torch.empty((1, Bl * N_ROIS, 14, 14, DEPTH), dtype=torch.float32, device=dev)
 
+    # The local batch is cut into `chunks` groups of images, one stream each: every layer of the path is per image, so
+    # the latency-bound proposal front / DetectionLayer of one group runs next to the HBM-bound ROIAlign launches of
+    # another (the same overlap as the headline's lanes, inside one step).
+    chunks = max(1, min(int(args.lanes), Bl // 2 if Bl >= 2 else 1))
+    spans = [shard_range(Bl, c, chunks) for c in range(chunks)]
+    cur = torch.cuda.current_stream()
+    streams = [cur] + [torch.cuda.Stream() for _ in range(chunks - 1)]
+    part = []
+    for (c0, c1) in spans:
+        n = c1 - c0
+        part.append(dict(n=n, anchors=anchors[c0:c1], window=window[c0:c1],
+                         inp={k: v[c0:c1] for k, v in inp.items()}, fmaps=[f[c0:c1] for f in fmaps],
+                         p7=p7[0, c0 * N_ROIS:c1 * N_ROIS], p14=p14[0, c0 * N_ROIS:c1 * N_ROIS]))
+    det_all_buf = torch.empty((Bl, conf.DETECTION_POST_NMS_INSTANCES, 6), dtype=torch.float32, device=dev)
+
+    def chunk_step(q, c0, c1):
+        props = Proposals(conf, q["n"], q["inp"]["probs"], q["inp"]["bbox"], q["anchors"]).get_proposals()
+        pyramid_roi_align(q["fmaps"], props, conf.IMAGE_SHAPE, [7, 7], out=q["p7"])
+        det = DetectionLayer(conf, conf.IMAGE_SHAPE, q["n"], q["window"], props, q["inp"]["hprobs"], q["inp"]["hbbox"]).get_detections()
+        pyramid_roi_align(q["fmaps"], props, conf.IMAGE_SHAPE, [14, 14], out=q["p14"])
+        det_all_buf[c0:c1].copy_(det)
+
     def step64():
-        props = Proposals(conf, Bl, inp["probs"], inp["bbox"], anchors).get_proposals()
-        pyramid_roi_align(fmaps, props, conf.IMAGE_SHAPE, [7, 7], out=p7)
-        det = DetectionLayer(conf, conf.IMAGE_SHAPE, Bl, window, props, inp["hprobs"], inp["hbbox"]).get_detections()
-        pyramid_roi_align(fmaps, props, conf.IMAGE_SHAPE, [14, 14], out=p14)
-        return gather_detections(det, batch=GLOBAL_B64) if world > 1 else det
+        for st_ in streams[1:]:
+            st_.wait_stream(cur)
+        for q, (c0, c1), st_ in zip(part, spans, streams):
+            with torch.cuda.stream(st_):
+                chunk_step(q, c0, c1)
+        for st_ in streams[1:]:
+            cur.wait_stream(st_)
+        return gather_detections(det_all_buf, batch=GLOBAL_B64) if world > 1 else det_all_buf
 
     for _ in range(3):
         det = step64()
@@ -847,7 +872,7 @@ def run_b64(torch, dist, world, rank, dev, conf, args, barrier, max_over_ranks):
     ms = max_over_ranks(a.elapsed_time(b)) / steps
     res = {"global_batch": GLOBAL_B64, "images_per_gpu": Bl, "scaling": "strong", "steps": steps, "warmup": 3,
            "ms_per_step": ms, "value": GLOBAL_B64 / (ms * 1e-3), "unit": "images/s",
-           "launch": "eager, one stream", "collective": "all_gather(detections) per step" if world > 1 else "none"}
+           "launch": f"eager, {chunks} groups of images on {chunks} streams", "collective": "all_gather(detections) per step" if world > 1 else "none"}
     if args.check:
         det_all = det.cpu().numpy()
         if rank == 0:
