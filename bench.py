@@ -403,7 +403,7 @@ def run_ours(args):
         return float(t.item())
 
     # ---- inputs: NSETS rotating sets, each in pinned host memory and resident in HBM
-    NSETS = max(2, min(int(args.lanes), 4))
+    NSETS = max(2, min(int(args.lanes), 8))
     host_sets, dev_sets = [], []
     for s in range(NSETS):
         raw = synth_inputs(1000 + 17 * rank + s, B, A)

@@ -316,7 +316,13 @@ roi_order_kernel(const float4* __restrict__ boxes, int32_t N, int32_t image_h, i
     key[j] = -1;
     if (n < N) {
       const float4 bx = __ldg(&boxes[(int64_t)b * N + n]);
-      const int32_t lv = roi_level_of(bx, image_h, image_w, min_level, min_level + num_levels - 1) - min_level;
+      // the order only steers locality (any order gives the same output), so the level key may be approximate: fast
+      // fp32 log2 (MUFU) instead of the correctly rounded fp64 log of roi_level_of, 1.5 us less on the serial path
+      const float v = sqrtf((bx.z - bx.x) * (bx.w - bx.y)) * sqrtf((float)(image_h * image_w)) * (1.0f / 224.0f);
+      const float lf = 4.0f + rintf(__log2f(v));                                     // NaN / <= 0 -> NaN or -inf
+      int32_t lv = (lf >= (float)min_level) ? (lf < (float)(min_level + num_levels) ? (int32_t)lf : min_level + num_levels - 1)
+                                           : min_level;                             // NaN -> min_level
+      lv -= min_level;
       const float yc = 0.5f * (bx.x + bx.z) * (float)kOrderBands;
       const int32_t band = (yc >= 0.0f) ? (yc < (float)kOrderBands ? (int32_t)yc : kOrderBands - 1) : 0;   // NaN -> 0
       key[j] = lv * kOrderBands + band;
@@ -392,7 +398,7 @@ constexpr int kRowsD4 = 64;                     // D = 256 floats = 64 quads = 1
 constexpr uint32_t kRowsPixelBytes = 1024;
 
 struct RowsPlan {
-  int2 ytab[kRowsMaxPool + 1];                  // ring mode, per y: {y_lerp bits, top row == bottom row}; one pad entry
+  int2 ytab[kRowsMaxPool + 2];                  // ring mode, per y: {y_lerp bits, top row == bottom row}; two pad entries
   int32_t yfirst[2 * kRowsMaxPool + 1];         // ring mode: first y whose TOP row has rank >= k (y's of rank k are contiguous)
   int32_t y_top[kRowsMaxPool], y_bot[kRowsMaxPool], y_ok[kRowsMaxPool];
   float y_lerp[kRowsMaxPool];
@@ -785,7 +791,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     const bool more = k + 1 < nr;                                                                    \
     if (more) OD_ROWS_LOAD(NXT);                                                                     \
     _Pragma(OD_ROWS_YUNROLL) while (y < yend) {                                                           \
-      const int2 nxt_ = P.ytab[y + 1];                                                               \
+      const int2 nxt_ = P.ytab[y + 2];      /* two rows ahead: the read is off the critical path */    \
       const float yl = __int_as_float(ent.x);                                                        \
       float4 v_[QPL];                                                                                \
       if (ent.y) {                    /* top row == bottom row: (top - top) * yl, as the reference */ \
@@ -794,7 +800,8 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
         _Pragma("unroll") for (int i = 0; i < QPL; ++i) v_[i] = axpy4p(CUR[i], sub4p(NXT[i], CUR[i]), yl); \
       }                                                                                              \
       OD_ROWS_PUT(v_)                                                                                \
-      ent = nxt_;                                                                                    \
+      ent = ent1;                                                                                    \
+      ent1 = nxt_;                                                                                   \
       ++y;                                                                                           \
       orow += pw * kRowsD4;                                                                          \
     }                                                                                                \
@@ -802,7 +809,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     ++k;                                                                                             \
   }
       float4* __restrict__ orow = o + x * kRowsD4;    // this warp's pixel of output row 0 (TMAST: the bulk copy's target)
-      int2 ent = P.ytab[0];
+      int2 ent = P.ytab[0], ent1 = P.ytab[1];
       int32_t y = 0, k = 0;
       OD_ROWS_LOAD(RA);
       for (;;) {
@@ -994,9 +1001,10 @@ static int launch_crop_bins(RoiSource src, int64_t n_rois, int32_t ph, int32_t p
   if (n_rois == 0) return OD_OK;
   const int32_t D4 = D / 4;
   // processing order (PyramidROIAlign with a sized workspace, enough ROIs for the order to matter). Measured: +3 % on the
-  // persistent 14x14 kernel, -5 % on the flat 7x7 kernel (its pre-pass and the extra table read cost more than the L2
-  // hits return, profiles/r2_roialign.md), so only the shapes served by crop_rows_kernel are ordered.
-  static const int use_order = env_int("OD_ROI_ORDER", 1, 0, 2);   // 2: also the flat kernel
+  // persistent 14x14 kernel. For the flat 7x7 kernel the launch itself gets ~2 us faster but its pre-pass adds more than
+  // that to a stand-alone call; with several steps in flight (the throughput case) that latency is hidden and the order is
+  // worth +2.5 % images/s, so it is on for both (profiles/r2_roialign.md).
+  static const int use_order = env_int("OD_ROI_ORDER", 2, 0, 2);   // 1: crop_rows_kernel only, 2: the flat kernel too
   src.order = nullptr;
   if (use_order && order_buf && src.mode == 0 && D == 4 * kRowsD4 && n_rois >= 512 && n_rois <= 0x7FFFFFFFll &&
       src.rois_per_image <= kOrderThreads * kOrderPerThread && (use_order == 2 || crop_rows_serves(src, n_rois, ph, pw, D))) {
