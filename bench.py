@@ -49,7 +49,7 @@ if ROOT not in sys.path:
 
 IMAGE = 1024
 B_PER_GPU = 2
-GLOBAL_B64 = 64
+GLOBAL_B64 = int(os.environ.get("OD_BENCH_GLOBAL_B", "64"))   # BASELINE configs[4]: 64 (the override is a developer aid: the 8-images-per-GPU shape of N=8 on one GPU)
 N_ROIS = 1000
 N_CLASSES = 81
 DEPTH = 256
@@ -849,15 +849,37 @@ def run_b64(torch, dist, world, rank, dev, conf, args, barrier, max_over_ranks):
         pyramid_roi_align(q["fmaps"], props, conf.IMAGE_SHAPE, [14, 14], out=q["p14"])
         det_all_buf[c0:c1].copy_(det)
 
+    graphs = [None] * chunks
+
     def step64():
         for st_ in streams[1:]:
             st_.wait_stream(cur)
-        for q, (c0, c1), st_ in zip(part, spans, streams):
+        for c, (q, (c0, c1), st_) in enumerate(zip(part, spans, streams)):
             with torch.cuda.stream(st_):
-                chunk_step(q, c0, c1)
+                if graphs[c] is not None:
+                    graphs[c].replay()
+                else:
+                    chunk_step(q, c0, c1)
         for st_ in streams[1:]:
             cur.wait_stream(st_)
         return gather_detections(det_all_buf, batch=GLOBAL_B64) if world > 1 else det_all_buf
+
+    # one eager pass per stream (workspaces, constant caches), then every group's chain becomes one CUDA graph: at 8-16
+    # images per GPU the ~25 launches of a group are launch-bound when issued one by one from Python
+    step64()
+    torch.cuda.synchronize()
+    if not args.no_graph:
+        cap = [torch.cuda.Stream() for _ in range(chunks)]
+        for c, (q, (c0, c1)) in enumerate(zip(part, spans)):
+            cap[c].wait_stream(cur)
+            with torch.cuda.stream(cap[c]):
+                chunk_step(q, c0, c1)            # eager on the capture stream: its workspaces exist before the capture
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=cap[c]):
+                chunk_step(q, c0, c1)
+            graphs[c] = g_
+        torch.cuda.synchronize()
 
     for _ in range(3):
         det = step64()
@@ -872,7 +894,8 @@ def run_b64(torch, dist, world, rank, dev, conf, args, barrier, max_over_ranks):
     ms = max_over_ranks(a.elapsed_time(b)) / steps
     res = {"global_batch": GLOBAL_B64, "images_per_gpu": Bl, "scaling": "strong", "steps": steps, "warmup": 3,
            "ms_per_step": ms, "value": GLOBAL_B64 / (ms * 1e-3), "unit": "images/s",
-           "launch": f"eager, {chunks} groups of images on {chunks} streams", "collective": "all_gather(detections) per step" if world > 1 else "none"}
+           "launch": (f"{chunks} groups of images, one CUDA graph each, on {chunks} streams" if graphs[0] is not None else
+                      f"eager, {chunks} groups of images on {chunks} streams"), "collective": "all_gather(detections) per step" if world > 1 else "none"}
     if args.check:
         det_all = det.cpu().numpy()
         if rank == 0:
