@@ -637,7 +637,7 @@ def run_ours(args):
                 "ms_per_launch": roi14_ms,
                 "measured": "CUDA events around the launch, in this run, steps issued one at a time" if LANES > 1 else
                             "CUDA events around the launch inside the timed region",
-                "with_two_steps_in_flight": {"ms_per_launch": roi14_ms_lanes, "frac": alg / (roi14_ms_lanes * 1e-3) / 1e9 / peak,
+                "with_steps_in_flight": {"ms_per_launch": roi14_ms_lanes, "frac": alg / (roi14_ms_lanes * 1e-3) / 1e9 / peak,
                                              "note": "the same events inside the headline timed region; the launch shares "
                                                      "HBM and SMs with the other lane's kernels"} if LANES > 1 else None}
 

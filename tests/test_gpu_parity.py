@@ -397,6 +397,25 @@ def test_roi_pooling_d256_rows_kernel_edge_cases(pool):
     assert all(int(w[:256].count_nonzero()) == 0 for w in _lib._zero_ws.values())   # the ticket counters; the rest is scratch
 
 
+@pytest.mark.parametrize("pool,n", [([14, 14], 700), ([7, 7], 700), ([14, 14], 4500)])
+def test_roi_pooling_processing_order(pool, n):
+    """>= 512 ROIs: roi_order_kernel buckets the ROIs by (approximate level, y band) and both ROIAlign kernels walk them in
+    that order; NaN / zero / flipped / outside boxes must land in valid buckets and every output row must still be the
+    row of ITS ROI. 4500 ROIs per image exceed the pre-pass's capacity (4096): index order, same results."""
+    rs = np.random.RandomState(77 + n + pool[0])
+    fmaps = [rs.random_sample((2, s, s, 256)).astype(f32) for s in (64, 32, 16, 8)]
+    props = _synth.rois_log_uniform(rs, 2, n, lo=4, hi=900)
+    props[0, 3] = [np.nan, 0.1, 0.5, 0.6]
+    props[0, 4] = [0.1, np.nan, np.nan, 0.6]
+    props[0, 5] = [0.9, 0.1, 0.2, 0.8]                                        # flipped
+    props[0, 6] = 0                                                           # zero area at the origin
+    props[0, 7] = [1.5, 1.5, 2.0, 2.0]                                        # outside
+    props[0, 8] = [-3.0, -3.0, -2.0, -2.0]                                    # negative centre
+    props[0, 9] = [np.inf, 0.0, np.inf, 1.0]
+    props[1, n - 50:] = 0                                                     # zero padding
+    _roi_align_check(fmaps, props, 1024, pool)
+
+
 def test_crop_and_resize_d256_rows_kernel():
     """tf.image.crop_and_resize entry (explicit box_ind, extrapolation value, skipped crops) on the D = 256 path."""
     from objectdetection_b200.maskrcnn import crop_and_resize
