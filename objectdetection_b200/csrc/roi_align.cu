@@ -957,7 +957,7 @@ static int launch_crop_rows_t(const RoiSource& src, int64_t n_rois, int32_t ph, 
   // Two CTAs per SM: what is left of 227 KiB after the static part and the staging slots of the TMA-store variant.
   const uint32_t stage_bytes = TMAST ? (uint32_t)pw * kRowsStages * kRowsPixelBytes : 0u;
   uint32_t ring_bytes = tn.ring_kb ? (uint32_t)tn.ring_kb * 1024u
-                        : (tn.cps == 1 && !TMAST) ? 176u * 1024u
+                        : (tn.cps == 1) ? 176u * 1024u - stage_bytes
                                                   : ((227u * 1024u) / (uint32_t)tn.cps - 6u * 1024u - stage_bytes) & ~1023u;
   const uint32_t dyn = ring_bytes + stage_bytes;
   if (dyn > 222u * 1024u) OD_FAIL(OD_ERR_PARAM, "OD_ROI_RING_KB too large: %u bytes of dynamic shared memory", dyn);
@@ -988,6 +988,7 @@ static int launch_crop_rows(const RoiSource& src, int64_t n_rois, int32_t ph, in
   if (!crop_rows_serves(src, n_rois, ph, pw, D)) return 1;
   if (!tn.dynamic) counter = nullptr;
 #define OD_ROWS_GO(T, Q, M, B) return launch_crop_rows_t<T, Q, M, B>(src, n_rois, ph, pw, tn, extrap, out, level_out, counter, st)
+  if (tn.tma_store && tn.cps == 1) OD_ROWS_GO(true, 2, 512, 1);
   if (tn.tma_store) OD_ROWS_GO(true, 2, 512, 2);
   if (tn.qpl == 1 && tn.cps == 1) OD_ROWS_GO(false, 1, 1024, 1);    // 2 warps per x bin, one CTA per SM
   if (tn.cps == 1) OD_ROWS_GO(false, 2, 512, 1);                    // one CTA per SM: up to 128 registers per thread
