@@ -445,6 +445,8 @@ def run_ours(args):
     lane_main = [main_stream] + [torch.cuda.Stream() for _ in range(LANES - 1)]
     lane_det = [torch.cuda.Stream(priority=-1) for _ in range(LANES)]   # high priority: small CTAs slip in between ROIAlign CTAs
     lane_cap = [torch.cuda.Stream() for _ in range(LANES)]              # capture streams (their workspaces belong to the graphs)
+    lane_roi7 = [torch.cuda.Stream() for _ in range(LANES)]             # --roi-concurrent: the 7x7 launch next to the 14x14 one
+    ev_roi7 = [torch.cuda.Event() for _ in range(NSETS)]
     det_stream = lane_det[0]
     # N > 1: every all_gather of every lane goes through ONE stream, in step order - collectives of one NCCL communicator
     # must be enqueued in the same order on all ranks and must not run concurrently with each other
@@ -501,7 +503,14 @@ def run_ours(args):
                         gather_stream.wait_event(ev_det_local[s_])
                         det = gather_detections(det, batch=world * B)
                         ev_det[s_].record(gather_stream)
-                graphs_c[s_].replay()
+                if args.roi_concurrent:      # both ROIAlign launches walk the same ROIs in the same order: share L2 lines
+                    lr = lane_roi7[lane_of(s_)]
+                    with torch.cuda.stream(lr):
+                        lr.wait_event(ev_prop[s_])
+                        graphs_c[s_].replay()
+                        ev_roi7[s_].record(lr)
+                else:
+                    graphs_c[s_].replay()
             else:
                 proposals = propose(inp)
                 roi7(inp, proposals, s_)
@@ -521,6 +530,8 @@ def run_ours(args):
                 roi_ev.append((e0, e1))
             if (use_graphs and graphs_a[s_] is not None) or world > 1:
                 lm.wait_event(ev_det[s_])       # join: the step ends when both branches are done
+            if use_graphs and graphs_a[s_] is not None and args.roi_concurrent:
+                lm.wait_event(ev_roi7[s_])
         return det, proposals
 
     def fork_lanes():      # the lanes start after everything already queued on the main stream
@@ -1075,6 +1086,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip scaling_b64 and the configs[2]/[3]/stress extras")
     ap.add_argument("--check", action="store_true", help="compare every shard's detections with the CPU oracle")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph)")
+    ap.add_argument("--roi-concurrent", action="store_true", help="experiment: 7x7 ROIAlign on its own stream next to the 14x14 launch")
     ap.add_argument("--lanes", type=int, default=4, help="steps in flight (1: strictly one step after the other)")
     ap.add_argument("--kernel-times", action="store_true", help="print per-kernel device times (CUPTI) to stderr")
     args = ap.parse_args()

@@ -416,6 +416,28 @@ def test_roi_pooling_processing_order(pool, n):
     _roi_align_check(fmaps, props, 1024, pool)
 
 
+def test_roi_pooling_without_workspace_static_round_robin():
+    """od_pyramid_roi_align_forward (no workspace): the persistent CTAs walk the ROIs in a fixed round robin, in index
+    order, without the order pre-pass - same bits."""
+    import ctypes
+    from objectdetection_b200 import _lib
+    rs = np.random.RandomState(31)
+    fmaps = [rs.random_sample((2, s, s, 256)).astype(f32) for s in (64, 32, 16, 8)]
+    props = _synth.rois_log_uniform(rs, 2, 400, lo=4, hi=900)
+    want, wlv = oracle.pyramid_roi_align(fmaps, props, 1024, 1024, 14, 14)
+    L = _lib.lib()
+    dl = _lib.DL()
+    fm = [cu(f) for f in fmaps]
+    rois = cu(props)
+    out = torch.empty((1, 800, 14, 14, 256), dtype=torch.float32, device="cuda")
+    lv = torch.empty((2, 400), dtype=torch.int32, device="cuda")
+    ptrs = (ctypes.c_void_p * 4)(*[dl(f) for f in fm])
+    _lib.check(L.od_pyramid_roi_align_forward(ptrs, 4, 2, dl(rois), 1024, 1024, 14, 14, dl(out), dl(lv),
+                                              _lib.stream_ptr(rois.device)), "od_pyramid_roi_align_forward")
+    assert_bits(host(out), want, "pooled (static round robin)")
+    assert np.array_equal(host(lv), wlv)
+
+
 def test_crop_and_resize_d256_rows_kernel():
     """tf.image.crop_and_resize entry (explicit box_ind, extrapolation value, skipped crops) on the D = 256 path."""
     from objectdetection_b200.maskrcnn import crop_and_resize
