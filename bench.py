@@ -544,7 +544,9 @@ def run_ours(args):
 
     if not args.no_graph:
         capture_graphs()
-    for i in range(max(args.warmup, 3)):
+    # every lane's graphs replay at least twice before the timed region (first replays upload the graph)
+    n_warm = max(args.warmup, 3, 2 * NSETS)
+    for i in range(n_warm):
         step(i % NSETS)
     torch.cuda.synchronize()
 
@@ -751,7 +753,7 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": shared_config(world),
             "launch": "eager, one stream" if args.no_graph else
