@@ -8,7 +8,10 @@
 // warp reads/writes 512 contiguous bytes. The reference's per-level where/gather, concat and
 // re-sort (maskrcnn.py:127-173) are not reproduced: each ROI writes straight to out[b*N+n].
 //
-//   crop_bins_kernel : the output is one flat array of bins (roi, y, x), each D*4 contiguous bytes. A CTA owns
+//   crop_rows_kernel : D = 256 and pool widths 10..14 (the 14x14 mask-branch pooling): one persistent CTA per SM, planner /
+//      issuer / consumer warps around a TMA-fed shared-memory ring of feature rows, separable blend (described below).
+//   roi_order_kernel : pre-pass of both kernels, the order in which the ROIs are walked (level by level, top to bottom).
+//   crop_bins_kernel : every other shape. The output is one flat array of bins (roi, y, x), each D*4 contiguous bytes. A CTA owns
 //      32 consecutive bins (every CTA does the same amount of work, ROI boundaries are irrelevant). Its
 //      first threads build a per-bin table in shared memory: level assignment + crop_and_resize grid of the bin's
 //      ROI -> image base pointer, the four tap offsets (in 16-byte units), the two lerp weights and a validity
@@ -363,32 +366,36 @@ roi_order_kernel(const float4* __restrict__ boxes, int32_t N, int32_t image_h, i
 }
 
 // ----------------------------------------------------------------------------- crop_rows_kernel
-// The TMA-staged, separable form of the same gather (D = 256, pool <= 16x16). Persistent CTAs (a few per SM), each
-// walking ROIs blockIdx.x, blockIdx.x + gridDim.x, ... with three kinds of warps that only meet through mbarriers:
+// The TMA-staged, separable form of the same gather (D = 256, pool height <= 16, pool width <= 14). ONE persistent CTA per
+// SM (512 threads, ~100 registers free to use, a 176 KiB ring), drawing ROIs from a ticket counter (in the order
+// roi_order_kernel wrote), with three kinds of warps that only meet through mbarriers:
 //
-//   planner   (1 warp) turns ROI geometry into a PLAN, a few ROIs ahead of everybody else (ring of kRowsPlans plans):
-//             crop_and_resize samples a ROI on a separable grid - bin (y, x) blends feature rows top(y)/bot(y) and columns
-//             left(x)/right(x). With a non-negative step the rows are non-decreasing in y, so the DISTINCT rows the ROI
-//             needs, in first-use order, are ranked 0..nr-1 by a short serial scan (same for the columns, whose
-//             consecutive ranks are merged into runs of adjacent pixels). A 14x14 crop of an 8-pixel ROI needs 9 rows of
-//             9 pixels instead of 784 taps.
+//   planner   (1 warp) turns ROI geometry into a PLAN, up to kRowsPlans ROIs ahead of the consumers. crop_and_resize samples
+//             a ROI on a separable grid - bin (y, x) blends feature rows top(y)/bot(y) and columns left(x)/right(x). With a
+//             non-negative step the taps are monotone, so the DISTINCT rows the ROI needs, in first-use = ascending order,
+//             are ranked 0..nr-1 with two ballots and a popcount (lanes 0-15: y samples, lanes 16-31: x samples); the
+//             columns likewise, consecutive column ranks merged into runs of adjacent pixels. A 14x14 crop of an 8-pixel
+//             ROI needs 9 rows of 9 pixels instead of 784 taps. The ticket is drawn two plans ahead and the box fetched one
+//             plan ahead, so no global round trip sits between two plans.
 //   issuer    (1 warp) streams the ranked rows of ROI after ROI into one shared-memory BYTE ring: one cp.async.bulk per
 //             (row, column run) - NHWC makes a run of pixels one contiguous block of len KiB - completion counted in bytes
 //             on the entry's `full` mbarrier; space is reclaimed in FIFO order as all consumer warps arrive on an entry's
 //             `empty` mbarrier. The ring never drains between ROIs; bytes in flight are set by the ring size, not by
-//             registers or occupancy.
-//   consumers thread = (x group, channel quad). On first use of a row it blends left/right for each of its x bins straight
-//             from the ring (2 LDS.128 per bin) into registers and releases the entry; each output row is then one lerp
-//             between the two cached rows and one streaming 16-byte store. Every feature pixel is read once from L2 per
-//             ROI and each x-blend is computed once per (row, x) instead of once per bin.
-//   ROIs the plan cannot serve (flipped / NaN boxes) take a per-bin path with direct loads on the consumer warps.
+//             registers or occupancy - the deeper the ring, the faster the kernel (profiles/r2_roialign.md).
+//   consumers (one warp per x bin, lane = channel quads `lane` and `lane + 32`) walk the ROW RANKS: the output rows whose
+//             top row has rank k are contiguous (yfirst), their bottom row is rank k or k+1. On first use a row is blended
+//             left/right straight from the ring (4 LDS.128) into registers and the entry released; every output row is then
+//             one lerp between the two cached rows and two streaming 16-byte stores. Every feature pixel is read once from
+//             L2 per ROI and each x-blend is computed once per (row, x) instead of once per bin.
+//   ROIs the plan cannot serve (flipped / NaN / partly outside boxes, rows wider than half the ring) take a per-bin path
+//   with direct loads on the consumer warps.
 // Arithmetic per output value is the reference's (crop_and_resize_op.cc): top = tl + (tr - tl) * xl, bot likewise,
 // out = top + (bot - top) * yl, so the results are bit-identical to crop_bins_kernel and to the oracle.
+// Template parameters select measured alternatives kept for A/B runs (env OD_ROI_*): TMAST = output rows staged in shared
+// memory and written by bulk shared->global copies (2-8 % slower), QPL = channel quads per lane (1: two warps per x bin),
+// MAXT/MINB = launch bounds (two 64-register CTAs per SM with half the ring each: 10 % slower).
 constexpr int kRowsMaxPool = 16;
 constexpr int kRowsEntries = 32;                // outstanding ring entries (one feature row each)
-#ifndef OD_ROWS_YUNROLL
-#define OD_ROWS_YUNROLL "unroll 1"
-#endif
 #ifndef OD_ROWS_PLANS
 #define OD_ROWS_PLANS 3
 #endif
@@ -407,7 +414,7 @@ struct RowsPlan {
   int32_t rows[2 * kRowsMaxPool];               // feature row of row-rank k
   int32_t run_col[kRowsMaxPool], run_rank[kRowsMaxPool], run_len[kRowsMaxPool];
   int32_t nr, ncols, nruns, mode;
-  int32_t mono, W;
+  int32_t W;
   int32_t keep;                                 // issuer: copy this ROI's rows with the L2 evict_last policy
   uint32_t row_bytes;                           // ncols KiB: one ring entry
   int64_t roi;
@@ -545,7 +552,6 @@ __device__ __forceinline__ void rows_make_plan(const RoiSource& src, int64_t roi
     P.roi = roi;
     P.base = m.base;
     P.W = m.W;
-    P.mono = mono;
     P.mode = mode;
     P.keep = l2_keep == 1 || (l2_keep == 2 && src.mode == 0 && level > src.min_level);
     if (level_out && src.mode == 0) level_out[roi] = level;
@@ -790,7 +796,7 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     OD_DBG_ASSERT(yend <= ph && P.roi >= 0 && P.roi < n_rois, "y group / ROI outside the crop");     \
     const bool more = k + 1 < nr;                                                                    \
     if (more) OD_ROWS_LOAD(NXT);                                                                     \
-    _Pragma(OD_ROWS_YUNROLL) while (y < yend) {                                                           \
+    _Pragma("unroll 1") while (y < yend) {                                                           \
       const int2 nxt_ = P.ytab[y + 2];      /* two rows ahead: the read is off the critical path */    \
       const float yl = __int_as_float(ent.x);                                                        \
       float4 v_[QPL];                                                                                \
@@ -908,11 +914,15 @@ crop_pool_bins_kernel(RoiSource src, int64_t total_bins, int32_t oh, int32_t ow,
 }
 
 // ----------------------------------------------------------------------------- host side
-// Tunables of the TMA-staged kernel, read once from the environment (A/B runs on one box without rebuilding):
+// Tunables of the TMA-staged kernel, read once from the environment (A/B runs on one box without rebuilding); the
+// defaults are the measured best (profiles/r2_roialign.md):
 //   OD_ROI_KERNEL=flat   forces crop_bins_kernel;       OD_ROI_MIN_POOL  smallest max(pool_h, pool_w) served (default 10);
-//   OD_ROI_RING_KB       shared-memory ring per CTA (default: what is left of the SM's shared memory for OD_ROI_CPS CTAs);
-//   OD_ROI_CPS           persistent CTAs per SM (default 2);    OD_ROI_TMA_STORE=1  staged bulk (TMA) stores instead of plain
-//   streaming stores;    OD_ROI_DYNAMIC=0  static round robin even with a workspace;   OD_ROI_ORDER=1  ROI order pre-pass.
+//   OD_ROI_CPS           persistent CTAs per SM: 1 (default, up to 128 registers) or 2 (64 registers, half the ring each);
+//   OD_ROI_RING_KB       shared-memory ring per CTA (default 176 with one CTA per SM, else what two CTAs can share);
+//   OD_ROI_QPL=1         two consumer warps per x bin (one channel quad per lane) instead of one;
+//   OD_ROI_TMA_STORE=1   output rows staged in shared memory and written by bulk shared->global copies;
+//   OD_ROI_DYNAMIC=0     static round robin even with a workspace;   OD_ROI_ORDER=0|1|2  ROI order pre-pass off / for this
+//   kernel only / for the flat kernel too (default);   OD_ROI_L2_KEEP, OD_ROI_L2_PREFETCH  L2 policy experiments.
 struct RowsTuning {
   bool use_rows, dynamic, tma_store;
   int ring_kb;
