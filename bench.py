@@ -369,7 +369,7 @@ def run_ours(args):
     from objectdetection_b200 import DetectionLayer, Proposals, _lib, utils
     from objectdetection_b200.config import config
     from objectdetection_b200.distributed import gather_detections
-    from objectdetection_b200.maskrcnn import pyramid_roi_align
+    from objectdetection_b200.maskrcnn import pyramid_roi_align, roi_processing_order
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -422,8 +422,15 @@ def run_ours(args):
     def propose(inp):
         return Proposals(conf, B, inp["probs"], inp["bbox"], anchors).get_proposals()
 
+    # The 7x7 and the 14x14 pooling of a step walk the same proposals: their processing order (level by level, top to
+    # bottom) is computed once per step - in front of the 7x7 launch - and handed to both calls (--no-shared-order: every
+    # call runs its own pre-pass, as it does for any caller that passes no order).
+    roi_orders = [None] * NSETS
+
     def roi7(inp, proposals, s_=0):
-        pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [7, 7], out=pooled7s[s_])
+        if not args.no_shared_order:
+            roi_orders[s_] = roi_processing_order(proposals, conf.IMAGE_SHAPE)
+        pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [7, 7], out=pooled7s[s_], order=roi_orders[s_])
 
     def detect(inp, proposals):
         return DetectionLayer(conf, conf.IMAGE_SHAPE, B, window, proposals, inp["hprobs"], inp["hbbox"]).get_detections()
@@ -524,7 +531,7 @@ def run_ours(args):
             if time_roi:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(lm)
-            pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [14, 14], out=pooled14s[s_])
+            pyramid_roi_align(inp["fmaps"], proposals, conf.IMAGE_SHAPE, [14, 14], out=pooled14s[s_], order=roi_orders[s_])
             if time_roi:
                 e1.record(lm)
                 roi_ev.append((e0, e1))
@@ -824,7 +831,7 @@ def run_b64(torch, dist, world, rank, dev, conf, args, barrier, max_over_ranks):
     eager launches (at 8+ images per launch nothing is launch-bound)."""
     from objectdetection_b200 import DetectionLayer, Proposals, utils
     from objectdetection_b200.distributed import gather_detections, shard_range
-    from objectdetection_b200.maskrcnn import pyramid_roi_align
+    from objectdetection_b200.maskrcnn import pyramid_roi_align, roi_processing_order
     lo, hi = shard_range(GLOBAL_B64, rank, world)
     Bl = hi - lo
     shapes = utils.get_resnet_stage_shapes(conf, conf.IMAGE_SHAPE)
@@ -857,9 +864,10 @@ def run_b64(torch, dist, world, rank, dev, conf, args, barrier, max_over_ranks):
 
     def chunk_step(q, c0, c1):
         props = Proposals(conf, q["n"], q["inp"]["probs"], q["inp"]["bbox"], q["anchors"]).get_proposals()
-        pyramid_roi_align(q["fmaps"], props, conf.IMAGE_SHAPE, [7, 7], out=q["p7"])
+        order = None if args.no_shared_order else roi_processing_order(props, conf.IMAGE_SHAPE)
+        pyramid_roi_align(q["fmaps"], props, conf.IMAGE_SHAPE, [7, 7], out=q["p7"], order=order)
         det = DetectionLayer(conf, conf.IMAGE_SHAPE, q["n"], q["window"], props, q["inp"]["hprobs"], q["inp"]["hbbox"]).get_detections()
-        pyramid_roi_align(q["fmaps"], props, conf.IMAGE_SHAPE, [14, 14], out=q["p14"])
+        pyramid_roi_align(q["fmaps"], props, conf.IMAGE_SHAPE, [14, 14], out=q["p14"], order=order)
         det_all_buf[c0:c1].copy_(det)
 
     graphs = [None] * chunks
@@ -1088,6 +1096,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip scaling_b64 and the configs[2]/[3]/stress extras")
     ap.add_argument("--check", action="store_true", help="compare every shard's detections with the CPU oracle")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph)")
+    ap.add_argument("--no-shared-order", action="store_true", help="every ROIAlign call computes its own ROI processing order")
     ap.add_argument("--roi-concurrent", action="store_true", help="experiment: 7x7 ROIAlign on its own stream next to the 14x14 launch")
     ap.add_argument("--lanes", type=int, default=4, help="steps in flight (1: strictly one step after the other)")
     ap.add_argument("--kernel-times", action="store_true", help="print per-kernel device times (CUPTI) to stderr")

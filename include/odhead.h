@@ -212,6 +212,17 @@ size_t od_pyramid_roi_align_workspace_bytes(void);
  * pixel is fetched from HBM once. Only the first od_pyramid_roi_align_workspace_bytes() bytes must be (and stay) zeroed.
  * The results do not depend on the order. */
 size_t od_pyramid_roi_align_workspace_bytes_n(int64_t n_rois);
+/* The processing order as a tensor of its own: order [B*N] i32, a permutation of 0..B*N-1 (N <= 4096 per image). A caller
+ * that pools the SAME rois with several pool shapes (the 7x7 and the 14x14 pooling of one step) computes it once and passes
+ * it to od_pyramid_roi_align_forward_ordered, which then skips its pre-pass; order == NULL behaves like ..._forward_ws.
+ * Entries outside [0, B*N) are skipped (their rows are not written), nothing is read or written out of bounds. */
+int od_roi_processing_order(const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t min_level, int32_t num_levels,
+                            DLTensor* order, void* stream);
+int od_pyramid_roi_align_forward_ordered(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
+                                         const DLTensor* rois, int32_t image_h, int32_t image_w,
+                                         int32_t pool_h, int32_t pool_w,
+                                         DLTensor* pooled, DLTensor* roi_level, const DLTensor* order,
+                                         void* ws, size_t ws_bytes, void* stream);
 int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
                                     const DLTensor* rois, int32_t image_h, int32_t image_w,
                                     int32_t pool_h, int32_t pool_w,

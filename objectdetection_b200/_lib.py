@@ -109,6 +109,9 @@ SIGNATURES = {
     "od_pyramid_roi_align_workspace_bytes_n": (c_size_t, [c_int64]),
     "od_pyramid_roi_align_forward_ws": (c_int, [POINTER(_P), c_int32, c_int32, _P, c_int32, c_int32, c_int32, c_int32,
                                                 _P, _P, _P, c_size_t, _P]),
+    "od_pyramid_roi_align_forward_ordered": (c_int, [POINTER(_P), c_int32, c_int32, _P, c_int32, c_int32, c_int32, c_int32,
+                                                     _P, _P, _P, _P, c_size_t, _P]),
+    "od_roi_processing_order": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "od_crop_and_resize": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, _P, _P]),
     "od_detection_target_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "od_detection_target_forward": (c_int, [_P, _P, _P, _P, _P, POINTER(TargetParams), _P, _P, _P, _P, _P,

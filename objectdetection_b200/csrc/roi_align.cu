@@ -246,12 +246,16 @@ crop_bins_kernel(RoiSource src, int64_t total_bins, int32_t bins_per_roi, int32_
     const int64_t fb = bin0 + i;
     int64_t roi = fb / bins_per_roi;
     const int32_t bin = (int32_t)(fb - roi * bins_per_roi);
+    bool valid = true;
     if (ORDERED) {
       roi = __ldg(&src.order[roi]);
+      valid = roi >= 0 && roi * bins_per_roi < total_bins;     // a caller-supplied order is not trusted: bad entry = no output
+      if (!valid) roi = 0;
       s_obin[i] = (uint32_t)(roi * bins_per_roi + bin);
     }
     const int32_t y = bin / pw;
-    bin_table_entry(src, roi, y, bin - y * pw, bin == 0, ph, pw, D4, level_out, &s_taps[i], &s_info[i]);
+    bin_table_entry(src, roi, y, bin - y * pw, bin == 0 && valid, ph, pw, D4, valid ? level_out : nullptr, &s_taps[i], &s_info[i]);
+    if (ORDERED && !valid) s_info[i].base_flag = (s_info[i].base_flag & ~(uintptr_t)3) | kBinSkip;
   }
   __syncthreads();
 
@@ -601,13 +605,16 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
     };
     auto bcast = [&](int64_t r) -> int64_t {        // the shuffle is what waits for the atomic: done one plan later
       if (counter) r = (int64_t)__shfl_sync(0xffffffffu, (unsigned int)r, 0);
-      if (src.order && r < n_rois) r = (int64_t)__ldg(&src.order[r]);      // ticket -> ROI in processing order
+      if (src.order && r < n_rois) {                                        // ticket -> ROI in processing order
+        r = (int64_t)__ldg(&src.order[r]);
+        if (r < 0 || r >= n_rois) r = -1;                                   // bad entry of a caller-supplied order: skipped
+      }
       return r;
     };
     auto fetch = [&](int64_t r, float4& bx, int32_t& bi) {
       bx = make_float4(0.f, 0.f, 0.f, 0.f);
       bi = 0;
-      if (r < n_rois) {
+      if (r >= 0 && r < n_rois) {
         bx = __ldg(&src.boxes[r]);
         if (src.mode == 1) bi = __ldg(&src.box_ind[r]);
       }
@@ -635,7 +642,15 @@ crop_rows_kernel(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, uint32_t
         }
         return;
       }
-      rows_make_plan(src, roi, box, bi, ph, pw, ring_bytes, l2_keep, lane, P, S, level_out);
+      if (roi < 0) {                                 // invalid order entry: an empty plan keeps the roles in step
+        if (lane == 0) {
+          P.roi = 0;
+          P.mode = kRowsSkip;
+        }
+        __syncwarp();
+      } else {
+        rows_make_plan(src, roi, box, bi, ph, pw, ring_bytes, l2_keep, lane, P, S, level_out);
+      }
       if (lane == 0) mbar_arrive(&S.plan_full[ps]);
       if (l2_prefetch && P.mode == kRowsRing) {
         // The planner runs a few ROIs ahead of the ring: pull this ROI's rows into L2 now, so that the ring copies issued
@@ -1006,9 +1021,18 @@ static int launch_crop_rows(const RoiSource& src, int64_t n_rois, int32_t ph, in
 #undef OD_ROWS_GO
 }
 
+static int launch_roi_order(const RoiSource& src, int32_t* order_buf, cudaStream_t st) {
+  OD_CUDA(launch_pdl(roi_order_kernel, dim3((unsigned)src.batch), dim3(kOrderThreads), 0, st, src.boxes, src.rois_per_image,
+                     src.image_h, src.image_w, src.min_level, src.num_levels, order_buf));
+  OD_LAUNCH_CHECK("roi_order_kernel");
+  return OD_OK;
+}
+
+// `order_buf`: scratch for the pre-pass (or NULL); `order_in`: an order the caller already has (od_roi_processing_order),
+// which saves the pre-pass - e.g. the 7x7 and the 14x14 pooling of one step walk the same ROIs.
 static int launch_crop_bins(RoiSource src, int64_t n_rois, int32_t ph, int32_t pw, int32_t D, float extrap,
                             float* out, int32_t* level_out, cudaStream_t st, unsigned int* counter = nullptr,
-                            int32_t* order_buf = nullptr) {
+                            int32_t* order_buf = nullptr, const int32_t* order_in = nullptr) {
   if (n_rois == 0) return OD_OK;
   const int32_t D4 = D / 4;
   // processing order (PyramidROIAlign with a sized workspace, enough ROIs for the order to matter). Measured: +3 % on the
@@ -1017,11 +1041,12 @@ static int launch_crop_bins(RoiSource src, int64_t n_rois, int32_t ph, int32_t p
   // worth +2.5 % images/s, so it is on for both (profiles/r2_roialign.md).
   static const int use_order = env_int("OD_ROI_ORDER", 2, 0, 2);   // 1: crop_rows_kernel only, 2: the flat kernel too
   src.order = nullptr;
-  if (use_order && order_buf && src.mode == 0 && D == 4 * kRowsD4 && n_rois >= 512 && n_rois <= 0x7FFFFFFFll &&
-      src.rois_per_image <= kOrderThreads * kOrderPerThread && (use_order == 2 || crop_rows_serves(src, n_rois, ph, pw, D))) {
-    OD_CUDA(launch_pdl(roi_order_kernel, dim3((unsigned)src.batch), dim3(kOrderThreads), 0, st, src.boxes, src.rois_per_image,
-                       src.image_h, src.image_w, src.min_level, src.num_levels, order_buf));
-    OD_LAUNCH_CHECK("roi_order_kernel");
+  const bool order_ok = use_order && src.mode == 0 && D == 4 * kRowsD4 && n_rois <= 0x7FFFFFFFll &&
+                        (use_order == 2 || crop_rows_serves(src, n_rois, ph, pw, D));
+  if (order_ok && order_in) {
+    src.order = order_in;
+  } else if (order_ok && order_buf && n_rois >= 512 && src.rois_per_image <= kOrderThreads * kOrderPerThread) {
+    OD_CHECK(launch_roi_order(src, order_buf, st));
     src.order = order_buf;
   }
   const int64_t bins_per_roi = (int64_t)ph * pw;
@@ -1079,10 +1104,45 @@ size_t od_pyramid_roi_align_workspace_bytes_n(int64_t n_rois) {
   return 256 + align_up((size_t)(n_rois > 0 ? n_rois : 0) * sizeof(int32_t), 256);
 }
 
+int od_roi_processing_order(const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t min_level, int32_t num_levels,
+                            DLTensor* order, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = -1;
+  DeviceScope dev_scope;
+  OD_CHECK(check_tensor(rois, "rois", F32, 3, true, &dev));
+  OD_CHECK(check_tensor(order, "order", I32, 1, true, &dev));
+  if (rois->shape[2] != 4) OD_FAIL(OD_ERR_SHAPE, "rois must be [B,N,4]");
+  if (num_levels < 1 || num_levels > OD_MAX_LEVELS) OD_FAIL(OD_ERR_PARAM, "num_levels %d not in [1,%d]", num_levels, OD_MAX_LEVELS);
+  const int64_t B = rois->shape[0], N = rois->shape[1];
+  if (order->shape[0] != B * N) OD_FAIL(OD_ERR_SHAPE, "order must be [B*N]");
+  if (B * N == 0) return OD_OK;
+  if (B * N > 0x7FFFFFFFll || B > 65535) OD_FAIL(OD_ERR_PARAM, "too many ROIs");
+  if (reinterpret_cast<uintptr_t>(dptr<float>(rois)) % 16) OD_FAIL(OD_ERR_LAYOUT, "rois not 16-byte aligned");
+  if (N > kOrderThreads * kOrderPerThread) OD_FAIL(OD_ERR_PARAM, "at most %d ROIs per image", kOrderThreads * kOrderPerThread);
+  RoiSource src;
+  memset(&src, 0, sizeof(src));
+  src.rois_per_image = (int32_t)N;
+  src.image_h = image_h;
+  src.image_w = image_w;
+  src.min_level = min_level;
+  src.num_levels = num_levels;
+  src.batch = (int32_t)B;
+  src.boxes = dptr<float4>(rois);
+  return launch_roi_order(src, dptr<int32_t>(order), st);
+}
+
 int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
                                     const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t pool_h,
                                     int32_t pool_w, DLTensor* pooled, DLTensor* roi_level, void* ws, size_t ws_bytes,
                                     void* stream) {
+  return od_pyramid_roi_align_forward_ordered(fmaps, num_levels, min_level, rois, image_h, image_w, pool_h, pool_w, pooled,
+                                              roi_level, nullptr, ws, ws_bytes, stream);
+}
+
+int od_pyramid_roi_align_forward_ordered(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,
+                                         const DLTensor* rois, int32_t image_h, int32_t image_w, int32_t pool_h,
+                                         int32_t pool_w, DLTensor* pooled, DLTensor* roi_level, const DLTensor* order,
+                                         void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!fmaps) OD_FAIL(OD_ERR_NULL, "fmaps is NULL");
   if (num_levels < 1 || num_levels > OD_MAX_LEVELS) OD_FAIL(OD_ERR_PARAM, "num_levels %d not in [1,%d]", num_levels, OD_MAX_LEVELS);
@@ -1136,8 +1196,12 @@ int od_pyramid_roi_align_forward_ws(const DLTensor* const* fmaps, int32_t num_le
   // workspace: [0,256) the ticket counters (stay zeroed), [256, 256 + 4*B*N) the ROI processing order (scratch)
   int32_t* order_buf = (ws && ws_bytes >= od_pyramid_roi_align_workspace_bytes_n(total))
                            ? reinterpret_cast<int32_t*>(static_cast<char*>(ws) + 256) : nullptr;
+  if (order) {
+    OD_CHECK(check_tensor(order, "order", I32, 1, true, &dev));
+    if (order->shape[0] != total) OD_FAIL(OD_ERR_SHAPE, "order must be [B*N]");
+  }
   return launch_crop_bins(src, total, pool_h, pool_w, (int32_t)D, 0.0f, dptr<float>(pooled), dptr<int32_t>(roi_level), st,
-                          static_cast<unsigned int*>(ws), order_buf);
+                          static_cast<unsigned int*>(ws), order_buf, dptr<int32_t>(order));
 }
 
 int od_pyramid_roi_align_forward(const DLTensor* const* fmaps, int32_t num_levels, int32_t min_level,

@@ -13,13 +13,28 @@ import torch
 from . import _lib
 
 
+def roi_processing_order(proposals, image_shape, levels=(2, 3, 4, 5)):
+    """The order in which the ROIAlign kernels walk ``proposals`` [B,N,4] (level by level, top to bottom, so that ROIs
+    reading the same feature pixels run close in time): int32 [B*N], a permutation of the row indices. Every
+    ``pyramid_roi_align`` call computes it itself; a caller that pools the same proposals with several pool shapes computes
+    it once and passes it as ``order=`` (N <= 4096 per image)."""
+    levels = [int(v) for v in levels]
+    rois = _lib.as_cuda(proposals, torch.float32)
+    order = torch.empty((rois.shape[0] * rois.shape[1],), dtype=torch.int32, device=rois.device)
+    dl = _lib.DL()
+    _lib.check(_lib.lib().od_roi_processing_order(dl(rois), int(image_shape[0]), int(image_shape[1]), min(levels), len(levels),
+                                                  dl(order), _lib.stream_ptr(rois.device)), "od_roi_processing_order")
+    return order
+
+
 def pyramid_roi_align(feature_maps, proposals, image_shape, pool_shape, levels=(2, 3, 4, 5), out=None,
-                      return_levels=False):
+                      return_levels=False, order=None):
     """FPN level assignment + bilinear crop_and_resize, one sample per bin (maskrcnn.py:104-187).
 
     feature_maps: list of [B,H_l,W_l,D] float32 NHWC CUDA tensors for the ascending, contiguous ``levels``;
     proposals: [B,N,4] normalised (y1,x1,y2,x2). Returns pooled [1,B*N,ph,pw,D] (row b*N+n <-> proposals[b,n])
-    and, if requested, roi_level [B,N] int32.
+    and, if requested, roi_level [B,N] int32. ``order``: optional result of ``roi_processing_order(proposals, ...)``
+    (saves the call's own pre-pass; the pooled values do not depend on it).
     """
     levels = [int(v) for v in levels]
     if levels != list(range(min(levels), min(levels) + len(levels))) or len(levels) != len(feature_maps):
@@ -37,9 +52,10 @@ def pyramid_roi_align(feature_maps, proposals, image_shape, pool_shape, levels=(
     ptrs = (ctypes.c_void_p * len(fmaps))(*[dl(f) for f in fmaps])
     L = _lib.lib()
     ws = _lib.zeroed_workspace(L.od_pyramid_roi_align_workspace_bytes_n(B * N), dev)   # ticket counter (stays zeroed) + ROI order
-    _lib.check(L.od_pyramid_roi_align_forward_ws(ptrs, len(fmaps), min(levels), dl(rois), int(image_shape[0]),
-                                                 int(image_shape[1]), ph, pw, dl(out), dl(lv), ws.data_ptr(),
-                                                 ws.numel(), _lib.stream_ptr(dev)), "od_pyramid_roi_align_forward_ws")
+    od = _lib.as_cuda(order, torch.int32, dev) if order is not None else None
+    _lib.check(L.od_pyramid_roi_align_forward_ordered(ptrs, len(fmaps), min(levels), dl(rois), int(image_shape[0]),
+                                                      int(image_shape[1]), ph, pw, dl(out), dl(lv), dl(od), ws.data_ptr(),
+                                                      ws.numel(), _lib.stream_ptr(dev)), "od_pyramid_roi_align_forward_ordered")
     return (out, lv) if return_levels else out
 
 

@@ -438,6 +438,35 @@ def test_roi_pooling_without_workspace_static_round_robin():
     assert np.array_equal(host(lv), wlv)
 
 
+@pytest.mark.parametrize("pool", [[14, 14], [7, 7]])
+def test_roi_pooling_caller_supplied_order(pool):
+    """roi_processing_order computed once and passed to the pooling call: same bits as the call's own pre-pass; the order
+    is a permutation; a corrupted order (out-of-range and duplicated entries) skips / repeats rows without touching
+    anything else - the rows of skipped ROIs keep their previous contents."""
+    from objectdetection_b200.maskrcnn import pyramid_roi_align, roi_processing_order
+    rs = np.random.RandomState(5 + pool[0])
+    fmaps = [rs.random_sample((2, s, s, 256)).astype(f32) for s in (64, 32, 16, 8)]
+    props = _synth.rois_log_uniform(rs, 2, 600, lo=4, hi=900)
+    props[1, 590:] = 0
+    want, _ = oracle.pyramid_roi_align(fmaps, props, 1024, 1024, pool[0], pool[1])
+    fm, pr = [cu(f) for f in fmaps], cu(props)
+    order = roi_processing_order(pr, [1024, 1024, 3])
+    assert sorted(host(order).tolist()) == list(range(1200))
+    got = host(pyramid_roi_align(fm, pr, [1024, 1024, 3], pool, order=order))
+    assert_bits(got, want, "pooled with a caller-supplied order")
+    bad = host(order).copy()
+    skipped = [int(bad[3]), int(bad[700])]
+    bad[3], bad[700] = -1, 5000                       # two ROIs are never visited ...
+    bad[10] = bad[11]                                 # ... one is visited twice, one (bad[10]'s old ROI) not at all
+    skipped.append(int(host(order)[10]))
+    out = torch.full((1, 1200, pool[0], pool[1], 256), -7.0, dtype=torch.float32, device="cuda")
+    got2 = host(pyramid_roi_align(fm, pr, [1024, 1024, 3], pool, out=out, order=cu(bad.astype(np.int32))))
+    keep = np.ones(1200, bool)
+    keep[skipped] = False
+    assert_bits(got2[0, keep], want[0, keep], "rows of the visited ROIs")
+    assert (got2[0, ~keep] == -7.0).all(), "rows of skipped ROIs must stay untouched"
+
+
 def test_crop_and_resize_d256_rows_kernel():
     """tf.image.crop_and_resize entry (explicit box_ind, extrapolation value, skipped crops) on the D = 256 path."""
     from objectdetection_b200.maskrcnn import crop_and_resize
