@@ -12,7 +12,11 @@ GPU (weak scaling: every rank owns its own 2 images; N>1 adds one all-gather of 
 One step = Proposals -> { DetectionLayer (synthetic head outputs) || PyramidROIAlign 7x7 (1000 ROIs/img) }
            -> PyramidROIAlign 14x14 (1000 ROIs/img)   [+ all_gather(detections) on the DetectionLayer branch when N>1]
            (DetectionLayer and the 7x7 ROIAlign both depend on the proposals only and run on two streams; the step ends
-           when both branches and the 14x14 launch are done)
+           when both branches and the 14x14 launch are done; the ROI processing order is computed once per step and
+           shared by the two pooling calls).
+Consecutive steps work on different images and share nothing: --lanes L (default 4) keeps L steps in flight (step i on
+lane i % L: own streams, input set and outputs), so the latency-bound proposal front of one step runs underneath the
+HBM-bound ROIAlign launches of the others. All K steps run between the two timing events.
 
 Reported on ONE JSON line (rank 0):
   value        images/s with the inputs resident in HBM, CUDA events around exactly K steps, max over ranks
@@ -20,13 +24,15 @@ Reported on ONE JSON line (rank 0):
                buffers the layer classes read) and the detections read back (D2H) every step; next to it the bare
                concurrent-H2D ceiling of the same buffers on the same ranks
   roofline     the dominant kernel (the 14x14 ROIAlign launch, crop_rows_kernel): algorithmic bytes / CUDA-event
-               duration measured inside the timed region, against MEASURED_PEAKS.json
+               duration, against MEASURED_PEAKS.json. Measured in a second timed pass of the same step with the steps
+               issued one at a time (with_steps_in_flight = the same events inside the headline region, where the launch
+               shares HBM and SMs with other steps); traffic = ncu DRAM bytes of the same build (profiles/ncu_traffic.json)
   cpu_baseline the CPU oracle (C restatement of the reference's algorithm, OpenMP) on the same workload, all host
                threads and one thread
   scaling_b64  BASELINE.json configs[4]: the same heads at GLOBAL batch 64 sharded 64/N images per GPU (strong scaling),
                every N, device-timed, max over ranks
   extra        (N=1) configs[2] training chain, configs[3] Faster R-CNN heads, the 100k-box NMS stress case - each with
-               the CPU oracle timed beside it - and the step time without CUDA graphs
+               the CPU oracle timed beside it - the step time without CUDA graphs and with one step at a time
 `--impl reference` times the CPU restatement alone on the same global batch (the reference itself is TF-1.x graph code;
 TensorFlow is not installable in this image) and prints the same line with "impl": "reference".
 `--check` compares the gathered detections of every shard (headline and batch-64 runs) with the CPU oracle.
