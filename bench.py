@@ -505,6 +505,8 @@ def run_ours(args):
                 ev_prop[s_].record(lm)
                 with torch.cuda.stream(ld):
                     ld.wait_event(ev_prop[s_])
+                    if world > 1:      # the previous gather of this set has read static_det before it is overwritten
+                        ld.wait_event(ev_det[s_])
                     graphs_b[s_].replay()
                     det = static_det[s_]
                     if world > 1:      # the path's only collective, hidden under the ROIAlign launches
@@ -530,6 +532,7 @@ def run_ours(args):
                 det = detect(inp, proposals)
                 if world > 1:
                     ev_det_local[s_].record(lm)
+                    det.record_stream(gather_stream)          # read there after this stream may have moved on
                     with torch.cuda.stream(gather_stream):
                         gather_stream.wait_event(ev_det_local[s_])
                         det = gather_detections(det, batch=world * B)
@@ -541,8 +544,13 @@ def run_ours(args):
             if time_roi:
                 e1.record(lm)
                 roi_ev.append((e0, e1))
-            if (use_graphs and graphs_a[s_] is not None) or world > 1:
-                lm.wait_event(ev_det[s_])       # join: the step ends when both branches are done
+            # join: the lane's step ends when both branches are done. With N > 1 the lane waits for its OWN detections
+            # only; the all_gather trails on the gather stream (the ranks then synchronise through a queue of collectives,
+            # not once per step) and the timed region ends after the last one (join_lanes).
+            if world > 1:
+                lm.wait_event(ev_det_local[s_])
+            elif use_graphs and graphs_a[s_] is not None:
+                lm.wait_event(ev_det[s_])
             if use_graphs and graphs_a[s_] is not None and args.roi_concurrent:
                 lm.wait_event(ev_roi7[s_])
         return det, proposals
@@ -551,9 +559,11 @@ def run_ours(args):
         for l_ in range(1, LANES):
             lane_main[l_].wait_stream(main_stream)
 
-    def join_lanes():      # ... and the main stream continues when every lane is done
+    def join_lanes():      # ... and the main stream continues when every lane (and every all_gather) is done
         for l_ in range(1, LANES):
             main_stream.wait_stream(lane_main[l_])
+        if gather_stream is not None:
+            main_stream.wait_stream(gather_stream)
 
     if not args.no_graph:
         capture_graphs()
@@ -572,6 +582,9 @@ def run_ours(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
+    if world > 1:      # the host barrier releases the ranks ~0.1 ms apart; one tiny all_reduce in front of the first event
+        align = torch.zeros(1, device=dev)      # lines the timed regions up on the device clock (it is not timed itself)
+        dist.all_reduce(align)
     launches0 = L.od_launch_count()
     wall0 = time.time()
     ev0.record()
@@ -701,6 +714,8 @@ def run_ours(args):
                 h2d((i + 1) % NSETS)                 # overlaps with this step's kernels
             lm.wait_event(ready[s_])
             d, _ = step(s_)
+            if world > 1:
+                lm.wait_event(ev_det[s_])            # the D2H below reads the gathered detections
             with torch.cuda.stream(lm):
                 det_host[s_].copy_(d[rank * B:(rank + 1) * B], non_blocking=True)   # D2H of this rank's detections
                 consumed[s_].record(lm)
